@@ -1,0 +1,164 @@
+"""Pins the C oracle (oracle/scl_oracle.c) to the reference: KATs, committed golden vectors
+(generated from the unmodified reference by oracle/gen_golden.py) and, when /root/reference is
+present, the live reference on fresh random inputs.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import scl_oracle as so
+from oracle.ref_loader import reference_available
+from tests.golden_util import case_id, load_golden, with_garbage
+
+CASES = load_golden()
+
+
+def make_oracle(c):
+    p = c["params"]
+    if c["coder"] in ("rans", "tans"):
+        o = so.Oracle.rans(c["freqs"], DATA_BLOCK_SIZE_BITS=p["DATA_BLOCK_SIZE_BITS"], NUM_BITS_OUT=p["NUM_BITS_OUT"],
+                           RANGE_FACTOR=p["RANGE_FACTOR"], tans=c["coder"] == "tans")
+        # NUM_STATE_BITS recomputed by the oracle wrapper must equal what the reference derived
+        assert so.ref_get_bit_width(p["RANGE_FACTOR"] * sum(c["freqs"]) * (1 << p["NUM_BITS_OUT"]) - 1) == p["NUM_STATE_BITS"]
+        return o
+    if c["coder"] == "range":
+        return so.Oracle.range_coder(c["freqs"], **p)
+    kind = so.MODEL_ADAPTIVE_IID if c["model"]["kind"] == "adaptive_iid" else so.MODEL_FIXED
+    return so.Oracle.aec(c["freqs"], model=kind, max_allowed_total_freq=c["model"]["max_total"], **p)
+
+
+def test_kat_rans_literal():
+    # rANS.py:303-360: Frequencies A:3 B:3 C:2, data A,C,B -> 00011 1011 10 01 0
+    o = so.Oracle.rans([3, 3, 2], DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1)
+    enc, nbits = o.encode_block([0, 2, 1])
+    assert so.bits_to_str(enc, nbits) == "00011" + "1011" + "10" + "01" + "0"
+    dec, used = o.decode_block(enc, nbits)
+    assert dec.tolist() == [0, 2, 1] and used == nbits
+
+
+def test_kat_tans_literal_and_tables():
+    # tANS.py:285-337 (tables) and :340-415 (bits)
+    o = so.Oracle.tans([3, 3, 2], DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1)
+    enc, nbits = o.encode_block([0, 2, 1])
+    assert so.bits_to_str(enc, nbits) == "00011101110010"
+    t = o.tans_tables_for(8)
+    # base_encode_step_table: (A,3..5)->8..10, (B,3..5)->11..13, (C,2..3)->14..15
+    assert t["enc_table"].tolist() == [8, 9, 10, 11, 12, 13, 14, 15]
+    assert t["enc_row"].tolist() == [0, 3, 6]
+    assert t["nbits_base"].tolist() == [1, 1, 2]
+    assert t["thresh"].tolist() == [12, 12, 16]
+    # base_decode_step_table: 8..15 -> (A,3)(A,4)(A,5)(B,3)(B,4)(B,5)(C,2)(C,3)
+    assert t["dec_sym"].tolist() == [0, 0, 0, 1, 1, 1, 2, 2]
+    assert t["dec_shrunk"].tolist() == [3, 4, 5, 3, 4, 5, 2, 3]
+
+
+@pytest.mark.parametrize("c", CASES, ids=case_id)
+def test_oracle_matches_golden(c):
+    o = make_oracle(c)
+    mf = np.array(c["freqs"], dtype=np.uint64) if c["coder"] == "aec" else None
+    enc, nbits = o.encode_block(c["data"], model_freq=mf)
+    assert nbits == c["nbits"]
+    assert enc.tobytes() == c["enc"].tobytes()
+    if c["coder"] == "aec":
+        assert mf.tolist() == c["model"]["final_freqs"]
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    mf = np.array(c["freqs"], dtype=np.uint64) if c["coder"] == "aec" else None
+    dec, used = o.decode_block(packed, total, model_freq=mf, cap=max(16, c["n"]))
+    assert dec.tolist() == c["data"].tolist()
+    assert used == c["consumed"] == c["nbits"]
+
+
+def test_oracle_decode_at_bit_offset():
+    c = next(c for c in CASES if c["coder"] == "rans" and c["n"] > 100)
+    o = make_oracle(c)
+    bits = np.unpackbits(c["enc"])[: c["nbits"]]
+    for off in (1, 5, 8, 13):
+        packed = np.packbits(np.concatenate([np.ones(off, dtype=np.uint8), bits, np.zeros(9, dtype=np.uint8)]))
+        dec, used = o.decode_block(packed, c["nbits"] + 9, bit_offset=off, cap=c["n"])
+        assert dec.tolist() == c["data"].tolist() and used == c["nbits"]
+
+
+def test_oracle_batch_matches_single():
+    rng = np.random.default_rng(5)
+    freqs = [5, 1, 9, 1]
+    o = so.Oracle.rans(freqs, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)
+    sym = rng.choice(4, size=(37, 64), p=np.array(freqs) / 16).astype(np.uint8)
+    sizes = rng.integers(0, 65, size=37).astype(np.uint32)
+    out, bits, status = o.encode_batch(sym, sizes=sizes, out_stride=160)
+    assert (status == 0).all()
+    for b in range(37):
+        enc, nb = o.encode_block(sym[b, : sizes[b]])
+        assert nb == bits[b] and out[b, : (nb + 7) // 8].tobytes() == enc.tobytes()
+    offs = (np.arange(37, dtype=np.uint64) * 160 * 8)
+    dec, dsz, used, st = o.decode_batch(out, offs, bits, out_stride=64)
+    assert (st == 0).all() and (dsz == sizes).all() and (used == bits).all()
+    for b in range(37):
+        assert dec[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+
+
+def test_oracle_error_statuses():
+    o = so.Oracle.rans([1, 1, 2])
+    with pytest.raises(so.OracleError) as e:
+        o.encode_block([0, 3])
+    assert e.value.code == 1  # KeyError in the reference
+    enc, nbits = o.encode_block([0, 1, 2, 2])
+    bad = enc.copy()
+    bad[5] ^= 0x10  # corrupt the state field
+    with pytest.raises(so.OracleError):
+        o.decode_block(bad, nbits)
+    o5 = so.Oracle.rans([1, 1, 2], DATA_BLOCK_SIZE_BITS=2)
+    with pytest.raises(so.OracleError) as e:
+        o5.encode_block([0, 1, 2, 2])  # size 4 does not fit 2 bits: OverflowError in the reference
+    assert e.value.code == 3
+
+
+# ------------------------------------------------------------------------------------------
+# live cross-check against the unmodified reference (build container only)
+# ------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+
+
+@needs_ref
+def test_live_reference_rans_tans_range_random():
+    from oracle.ref_loader import import_reference
+
+    import_reference()
+    from scl.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from scl.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+    from scl.compressors.tANS import tANSEncoder, tANSParams
+    from scl.core.data_block import DataBlock
+    from scl.core.prob_dist import Frequencies
+
+    rng = np.random.default_rng(1234)
+    for trial in range(12):
+        n_sym = int(rng.integers(1, 9))
+        freqs = [int(x) for x in rng.integers(1, 40, size=n_sym)]
+        nbo = int(rng.choice([1, 1, 2, 8]))
+        rf = int(rng.choice([1, 3, 1 << 4, 1 << 12, 1 << 16]))
+        n = int(rng.integers(0, 120))
+        data = rng.integers(0, n_sym, size=n).astype(np.uint8)
+        fr = Frequencies({i: f for i, f in enumerate(freqs)})
+        params = rANSParams(fr, NUM_BITS_OUT=nbo, RANGE_FACTOR=rf)
+        ref = rANSEncoder(params).encode_block(DataBlock(data.tolist()))
+        o = so.Oracle.rans(freqs, NUM_BITS_OUT=nbo, RANGE_FACTOR=rf)
+        enc, nbits = o.encode_block(data)
+        assert nbits == len(ref) and enc.tobytes() == ref.tobytes(), (freqs, nbo, rf)
+        dec, used = rANSDecoder(params).decode_block(ref)
+        d2, u2 = o.decode_block(enc, nbits, cap=max(16, n))
+        assert d2.tolist() == list(dec.data_list) and u2 == used
+        # range coder on the same data
+        rp = RangeCoderParams()
+        ref = RangeEncoder(rp, fr).encode_block(DataBlock(data.tolist()))
+        o = so.Oracle.range_coder(freqs)
+        enc, nbits = o.encode_block(data)
+        assert nbits == len(ref) and enc.tobytes() == ref.tobytes()
+        dec, used = RangeDecoder(rp, fr).decode_block(ref)
+        d2, u2 = o.decode_block(enc, nbits, cap=max(16, n))
+        assert d2.tolist() == list(dec.data_list) and u2 == used
+    # tANS == rANS bits for power-of-two M
+    freqs = [3, 4, 9]
+    fr = Frequencies({i: f for i, f in enumerate(freqs)})
+    data = rng.integers(0, 3, size=200).astype(np.uint8)
+    ref = tANSEncoder(tANSParams(fr, RANGE_FACTOR=1 << 6)).encode_block(DataBlock(data.tolist()))
+    enc, nbits = so.Oracle.tans(freqs, RANGE_FACTOR=1 << 6).encode_block(data)
+    assert nbits == len(ref) and enc.tobytes() == ref.tobytes()
+    enc2, nbits2 = so.Oracle.rans(freqs, RANGE_FACTOR=1 << 6).encode_block(data)
+    assert nbits2 == nbits and enc2.tobytes() == enc.tobytes()
