@@ -1,0 +1,96 @@
+"""Shared plumbing of the four GPU coders: symbol <-> byte translation for the single-block
+reference API and the batched tensor API on top of a DeviceCoder handle."""
+import numpy as np
+import torch
+
+from ..core.data_block import DataBlock
+from ..core.prob_dist import Frequencies
+from ..device import DecodedBlocks, DeviceCoder, EncodedBlocks
+from ..utils.bitarray_utils import BitArray
+
+
+class GpuCoderBase:
+    """Mixin.  Subclasses provide `_freqs()` (the Frequencies defining the alphabet) and
+    `_make_cabi_params()`; the DeviceCoder is created lazily on first use."""
+
+    _dev = None
+    _dev_key = None
+
+    def _freqs(self) -> Frequencies:
+        raise NotImplementedError
+
+    def _make_cabi_params(self):
+        raise NotImplementedError
+
+    # ---- handle --------------------------------------------------------------------------
+    def _cache_key(self):
+        f = self._freqs()
+        return (tuple(f.alphabet), tuple(int(x) for x in f.freq_list))
+
+    def device_coder(self) -> DeviceCoder:
+        key = self._cache_key()
+        if self._dev is None or self._dev_key != key:
+            alpha, freq = self._freqs().to_arrays()
+            self._dev = DeviceCoder(self._make_cabi_params(), alpha, freq)
+            self._dev_key = key
+            self._alpha_bytes = alpha
+            self._sym2byte = {s: int(b) for s, b in zip(self._freqs().alphabet, alpha)}
+            self._byte2sym = {int(b): s for s, b in zip(self._freqs().alphabet, alpha)}
+            self._native = self._freqs().byte_alphabet()[1]
+        return self._dev
+
+    # ---- single-block translation ----------------------------------------------------------
+    def _block_to_tensor(self, data_block: DataBlock) -> torch.Tensor:
+        dev = self.device_coder()
+        d = data_block.data_list
+        if isinstance(d, torch.Tensor) and d.dtype == torch.uint8 and self._native:
+            return d.reshape(1, -1).to(dev.device)
+        seq = d.tolist() if hasattr(d, "tolist") else list(d)
+        try:
+            arr = np.fromiter((self._sym2byte[s] for s in seq), dtype=np.uint8, count=len(seq))
+        except KeyError as e:  # same error the reference raises from freq_dict[s]
+            raise KeyError(e.args[0]) from None
+        return torch.from_numpy(arr).reshape(1, -1).to(dev.device)
+
+    def _row_to_block(self, row: np.ndarray) -> DataBlock:
+        if self._native:
+            return DataBlock(row.tolist())
+        return DataBlock([self._byte2sym[int(b)] for b in row])
+
+    # ---- batched API ---------------------------------------------------------------------
+    def encode_blocks(self, data, sizes=None) -> EncodedBlocks:
+        """Encode B independent blocks: data uint8 [B, N] (device or host tensor / ndarray)."""
+        return self.device_coder().encode_blocks(data, sizes=sizes)
+
+    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, out=None) -> DecodedBlocks:
+        """Decode B independent streams into uint8 [B, >=max_block_len]."""
+        return self.device_coder().decode_blocks(enc, max_block_len, out=out)
+
+    # ---- reference single-block API --------------------------------------------------------
+    def _encode_one(self, data_block: DataBlock, model=None) -> BitArray:
+        t = self._block_to_tensor(data_block)
+        enc = self.device_coder().encode_blocks(t, model=model)
+        enc.check()
+        return enc.block(0)
+
+    def _decode_one(self, bitarray: BitArray, model=None):
+        dev = self.device_coder()
+        enc = EncodedBlocks.from_bitarrays([bitarray], device=dev.device)
+        # the block size is in the stream; a stream of n bits cannot hold more than n symbols'
+        # worth of header-declared data that we are willing to allocate for
+        size_cap = self._peek_size(bitarray)
+        dec = dev.decode_blocks(enc, size_cap, model=model)
+        dec.check()
+        n = int(dec.sizes[0])
+        row = dec.symbols[0, :n].cpu().numpy()
+        return self._row_to_block(row), int(dec.bits_consumed[0])
+
+    def _peek_size(self, bitarray: BitArray) -> int:
+        nbits = self._size_bits()
+        head = bitarray[:nbits]
+        if len(head) == 0:
+            raise ValueError("non-empty bitarray expected")
+        return int(head.to01(), 2)
+
+    def _size_bits(self) -> int:
+        return int(self.params.DATA_BLOCK_SIZE_BITS)

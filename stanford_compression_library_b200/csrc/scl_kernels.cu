@@ -1,0 +1,687 @@
+// scl_kernels.cu -- sm_100a kernels and the C-ABI (include/scl_b200.h).
+//
+// Execution model: one warp lane == one DataBlock.  A CTA first stages the coder's
+// lookup tables into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), then every
+// lane runs the reference's per-block state machine from scl_lane.cuh on its own block.
+// There is no dense contraction anywhere on this path, so no tensor-core code: the kernels are
+// integer ALU + LSU work bounded by HBM traffic and instruction issue.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "scl_lane.cuh"
+#include "scl_tables.hpp"
+
+namespace scl {
+
+// ------------------------------------------------------------------------------------------------
+// TMA table staging: one elected thread issues cp.async.bulk (UBLKCP) global -> shared and the
+// whole CTA waits on the mbarrier's transaction count.  bytes % 16 == 0, both sides 16-B aligned.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *mbar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void tma_expect(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(mbar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// stage one table; every thread of the CTA must call this
+__device__ __forceinline__ void stage_table(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *mbar) {
+    mbar_init(mbar);
+    if (threadIdx.x == 0) {
+        tma_expect(mbar, bytes);
+        // a single bulk copy may move at most 2^20-16 bytes; tables here are <= 64 KiB
+        tma_bulk_g2s(smem_dst, gsrc, bytes, mbar);
+    }
+    mbar_wait(mbar, 0);
+}
+
+struct BlockIo {  // per-launch I/O description shared by all encode kernels
+    const uint8_t *sym;
+    uint64_t sym_stride;
+    const uint32_t *sizes;
+    uint32_t block_len;
+    uint64_t n_blocks;
+    uint8_t *out;
+    uint64_t out_stride;
+    uint64_t *bit_off;
+    uint64_t *bit_len;
+    uint32_t *status;
+};
+struct DecodeIo {
+    const uint8_t *in;
+    uint64_t in_bytes;
+    const uint64_t *bit_off;
+    const uint64_t *bit_len;
+    uint64_t n_blocks;
+    uint8_t *sym;
+    uint64_t sym_stride;
+    uint32_t *sizes;
+    uint64_t *consumed;
+    uint32_t *status;
+};
+
+__device__ __forceinline__ uint64_t avail_bits_of(const DecodeIo &io, uint64_t b, uint64_t off) {
+    if (io.bit_len) return io.bit_len[b];
+    uint64_t tot = io.in_bytes * 8;
+    return tot > off ? tot - off : 0;
+}
+
+constexpr int kThreads = 128;
+
+// ------------------------------------------------------------------------------------------------
+// rANS kernels
+// ------------------------------------------------------------------------------------------------
+template <bool CHECK>
+__global__ void __launch_bounds__(kThreads) rans32_encode_kernel(const RansEnc32 *__restrict__ g_tab, RansConst c, BlockIo io) {
+    __shared__ RansEnc32 s_tab[256];
+    __shared__ uint64_t mbar;
+    stage_table(s_tab, g_tab, sizeof(s_tab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    LifoBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint64_t bits = 0;
+    uint32_t st = rans32_encode_lane<CHECK>(s_tab, c, io.sym + b * io.sym_stride, n, w, bits);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kThreads) rans32_decode_kernel(const RansDec32 *__restrict__ g_lut, uint32_t lut_bytes, RansConst c,
+                                                                 DecodeIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ uint64_t mbar;
+    RansDec32 *s_lut = (RansDec32 *)s_dyn;
+    stage_table(s_lut, g_lut, lut_bytes, &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint64_t used = 0;
+    uint32_t st = rans32_decode_lane(s_lut, c, r, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kThreads) rans64_encode_kernel(const RansGeneric *__restrict__ g_tab, RansConst c, BlockIo io) {
+    __shared__ RansGeneric s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(RansGeneric), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    LifoBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint64_t bits = 0;
+    uint32_t st = rans64_encode_lane(s_tab, c, io.sym + b * io.sym_stride, n, w, bits);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kThreads) rans64_decode_kernel(const RansGeneric *__restrict__ g_tab, RansConst c, DecodeIo io) {
+    __shared__ RansGeneric s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(RansGeneric), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint64_t used = 0;
+    uint32_t st = rans64_decode_lane(s_tab, c, r, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tANS kernels.  Tables (L entries each) are built on the device, one thread per state, by
+// inverting the rANS decode step exactly as tANS.py:88-99 / :208-215 cache it.
+// ------------------------------------------------------------------------------------------------
+__global__ void tans_build_kernel(const RansGeneric *__restrict__ t, RansConst c, const uint32_t *__restrict__ row_of_idx,
+                                  uint32_t *__restrict__ enc_table, uint32_t *__restrict__ dec_packed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.L) return;
+    tans_build_entry(*t, c, row_of_idx, enc_table, dec_packed, i);
+}
+
+template <bool SMEM_TABLE>
+__global__ void __launch_bounds__(kThreads) tans_encode_kernel(const TansSym *__restrict__ g_sym, const uint32_t *__restrict__ g_enc,
+                                                               uint32_t table_bytes, RansConst c, BlockIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ TansSym s_sym[256];
+    __shared__ uint64_t mbar;
+    mbar_init(&mbar);
+    if (threadIdx.x == 0) {
+        tma_expect(&mbar, (uint32_t)sizeof(s_sym) + (SMEM_TABLE ? table_bytes : 0u));
+        tma_bulk_g2s(s_sym, g_sym, sizeof(s_sym), &mbar);
+        if (SMEM_TABLE) tma_bulk_g2s(s_dyn, g_enc, table_bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+    const uint32_t *enc = SMEM_TABLE ? (const uint32_t *)s_dyn : g_enc;
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    LifoBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint64_t bits = 0;
+    uint32_t st = tans_encode_lane(s_sym, enc, c, io.sym + b * io.sym_stride, n, w, bits);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+    io.status[b] = st;
+}
+
+template <bool SMEM_TABLE>
+__global__ void __launch_bounds__(kThreads) tans_decode_kernel(const uint32_t *__restrict__ g_dec, uint32_t table_bytes, RansConst c,
+                                                               DecodeIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ uint64_t mbar;
+    if (SMEM_TABLE) stage_table(s_dyn, g_dec, table_bytes, &mbar);
+    const uint32_t *dec = SMEM_TABLE ? (const uint32_t *)s_dyn : g_dec;
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint64_t used = 0;
+    uint32_t st = tans_decode_lane(dec, c, r, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// range coder kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) range_encode_kernel(const RangeTab *__restrict__ g_tab, RangeConst c, BlockIo io) {
+    __shared__ RangeTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(RangeTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint64_t bits = 0;
+    uint32_t st = range_encode_lane(s_tab, c, io.sym + b * io.sym_stride, n, w, bits);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *__restrict__ g_tab, RangeConst c, DecodeIo io) {
+    __shared__ RangeTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(RangeTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint64_t used = 0;
+    uint32_t st = range_decode_lane(s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arithmetic coder kernels: 32 lanes per CTA, each lane's 256-counter model is a Fenwick tree in
+// shared memory, lane-interleaved (element i of lane l at word i*32 + l => every access of a
+// warp hits 32 distinct banks whatever the per-lane index).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAecThreads = 32;
+struct SmemTree {
+    uint32_t *base;  // &smem[lane]
+    __device__ __forceinline__ uint32_t get(uint32_t i) const { return base[i * kAecThreads]; }
+    __device__ __forceinline__ void set(uint32_t i, uint32_t v) { base[i * kAecThreads] = v; }
+};
+constexpr uint32_t kAecTreeBytes = 257 * kAecThreads * 4;
+
+__device__ __forceinline__ uint64_t aec_load_model(SmemTree &F, const AecTab &tab, const AecConst &c, const uint64_t *model) {
+    uint64_t total = 0;
+    F.set(0, 0);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t f = 0;
+        if (i < c.n_sym) f = model ? (uint32_t)model[i] : tab.init_freq[i];
+        F.set(i + 1, f);
+        total += f;
+    }
+    fen_build(F);
+    return total;
+}
+__device__ __forceinline__ void aec_store_model(SmemTree &F, const AecConst &c, uint64_t *model) {
+    if (!model) return;
+    fen_unbuild(F);
+    for (uint32_t i = 0; i < c.n_sym; ++i) model[i] = F.get(i + 1);
+}
+
+__global__ void __launch_bounds__(kAecThreads) aec_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kAecThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    SmemTree F{(uint32_t *)s_dyn + threadIdx.x};
+    uint64_t *my_model = model ? model + b * c.n_sym : nullptr;
+    uint64_t total = aec_load_model(F, s_tab, c, my_model);
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint64_t bits = 0, total_out = 0;
+    uint32_t st = aec_encode_lane(F, s_tab, c, total, io.sym + b * io.sym_stride, n, w, bits, total_out);
+    aec_store_model(F, c, my_model);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kAecThreads) aec_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * kAecThreads + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    SmemTree F{(uint32_t *)s_dyn + threadIdx.x};
+    uint64_t *my_model = model ? model + b * c.n_sym : nullptr;
+    uint64_t total = aec_load_model(F, s_tab, c, my_model);
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint64_t used = 0, total_out = 0;
+    uint32_t st = aec_decode_lane(F, s_tab, c, total, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size,
+                                  used, total_out);
+    aec_store_model(F, c, my_model);
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream packing: bit-granular copy of each block's stream to a byte-aligned destination
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t src_byte_at_bit(const uint8_t *src, uint64_t pos) {  // 8 bits starting at bit `pos`
+    uint64_t by = pos >> 3;
+    uint32_t sh = (uint32_t)(pos & 7);
+    uint32_t v = ((uint32_t)src[by] << 8);
+    if (sh) v |= src[by + 1];
+    return (v >> (8 - sh)) & 0xFFu;
+}
+
+// one CTA per block; FRAMED adds the reference's block framing (encoded_stream.py:22-46,93-103)
+template <bool FRAMED>
+__global__ void __launch_bounds__(kThreads) pack_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_bit_off,
+                                                         const uint64_t *__restrict__ bit_len, uint8_t *__restrict__ dst,
+                                                         const uint64_t *__restrict__ dst_byte_off) {
+    const uint64_t b = blockIdx.x;
+    const uint64_t off = src_bit_off[b], nbits = bit_len[b];
+    uint8_t *d = dst + dst_byte_off[b];
+    if (!FRAMED) {
+        const uint64_t nbytes = (nbits + 7) >> 3;
+        for (uint64_t i = threadIdx.x; i < nbytes; i += kThreads) {
+            uint64_t rem = nbits - 8 * i;  // bits of the stream left at byte i (>= 1)
+            uint32_t v;
+            if (rem >= 8) {
+                v = src_byte_at_bit(src, off + 8 * i);
+            } else {  // last partial byte: take only `rem` bits, zero-pad on the right (tobytes())
+                v = 0;
+                for (uint32_t k = 0; k < (uint32_t)rem; ++k) {
+                    uint64_t p = off + 8 * i + k;
+                    v |= ((src[p >> 3] >> (7 - (p & 7))) & 1u) << (7 - k);
+                }
+            }
+            d[i] = (uint8_t)v;
+        }
+    } else {
+        // padded payload = [num_pad : 3][0 * num_pad][stream]; its length is a whole number of bytes
+        const uint32_t num_pad = (uint32_t)((8 - (nbits + 3) % 8) % 8);
+        const uint64_t lead = 3 + num_pad;
+        const uint64_t payload_bytes = (nbits + lead) >> 3;
+        if (threadIdx.x < 4) d[threadIdx.x] = (uint8_t)(payload_bytes >> (8 * (3 - threadIdx.x)));  // u32 big-endian
+        for (uint64_t i = threadIdx.x; i < payload_bytes; i += kThreads) {
+            uint32_t v = 0;
+            if (8 * i >= lead) {
+                v = src_byte_at_bit(src, off + 8 * i - lead);
+            } else {
+                for (uint32_t k = 0; k < 8; ++k) {
+                    uint64_t q = 8 * i + k;
+                    uint32_t bit;
+                    if (q < 3)
+                        bit = (num_pad >> (2 - q)) & 1u;
+                    else if (q < lead)
+                        bit = 0;
+                    else {
+                        uint64_t p = off + (q - lead);
+                        bit = (src[p >> 3] >> (7 - (p & 7))) & 1u;
+                    }
+                    v |= bit << (7 - k);
+                }
+            }
+            d[4 + i] = (uint8_t)v;
+        }
+    }
+}
+
+}  // namespace scl
+
+// ====================================================================================================
+// C-ABI
+// ====================================================================================================
+using namespace scl;
+
+struct scl_coder {
+    scl_params p;
+    RansHost *rans = nullptr;
+    TansHost *tans = nullptr;
+    RangeHost *range = nullptr;
+    AecHost *aec = nullptr;
+    // device tables
+    RansEnc32 *d_enc32 = nullptr;
+    RansDec32 *d_dec32 = nullptr;
+    uint32_t dec32_bytes = 0;
+    RansGeneric *d_gen = nullptr;
+    TansSym *d_tsym = nullptr;
+    uint32_t *d_tenc = nullptr, *d_tdec = nullptr;
+    uint32_t ttab_bytes = 0;
+    RangeTab *d_range = nullptr;
+    AecTab *d_aec = nullptr;
+};
+
+static thread_local char g_cuda_err[256] = "";
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return SCL_E_CUDA;
+}
+#define SCL_CUDA(call)                                     \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+extern "C" const char *scl_last_cuda_error(void) { return g_cuda_err; }
+extern "C" const char *scl_version(void) { return "scl_b200 0.1 (sm_100a)"; }
+
+template <typename T>
+static int upload(T **dptr, const void *src, size_t bytes, size_t alloc_bytes, cudaStream_t s) {
+    SCL_CUDA(cudaMalloc((void **)dptr, alloc_bytes));
+    if (alloc_bytes > bytes) SCL_CUDA(cudaMemsetAsync(*dptr, 0, alloc_bytes, s));
+    SCL_CUDA(cudaMemcpyAsync(*dptr, src, bytes, cudaMemcpyHostToDevice, s));
+    return SCL_E_OK;
+}
+static size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// smem budget for staging tANS tables next to the static tables (227 KiB per CTA on sm_100a)
+static const uint32_t kTansSmemTableMax = 160 * 1024;
+
+extern "C" void scl_coder_destroy(scl_coder *c) {
+    if (!c) return;
+    cudaFree(c->d_enc32);
+    cudaFree(c->d_dec32);
+    cudaFree(c->d_gen);
+    cudaFree(c->d_tsym);
+    cudaFree(c->d_tenc);
+    cudaFree(c->d_tdec);
+    cudaFree(c->d_range);
+    cudaFree(c->d_aec);
+    delete c->rans;
+    delete c->tans;
+    delete c->range;
+    delete c->aec;
+    delete c;
+}
+
+extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabet, const uint64_t *freq, uint32_t n_sym, void *stream,
+                                scl_coder **out) {
+    if (!params || !freq || !out) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    scl_coder *c = new (std::nothrow) scl_coder();
+    if (!c) return SCL_E_INVALID;
+    c->p = *params;
+    int rc = SCL_E_OK;
+    switch (params->coder) {
+    case SCL_CODER_RANS: {
+        c->rans = new RansHost();
+        rc = c->rans->init(*params, alphabet, freq, n_sym);
+        if (rc) break;
+        RansHost &r = *c->rans;
+        rc = upload(&c->d_gen, &r.gen, sizeof(RansGeneric), sizeof(RansGeneric), s);
+        if (!rc && r.enc32) rc = upload(&c->d_enc32, r.enc_tab.data(), sizeof(RansEnc32) * 256, sizeof(RansEnc32) * 256, s);
+        if (!rc && r.dec32) {
+            c->dec32_bytes = (uint32_t)round16(r.dec_lut.size() * sizeof(RansDec32));
+            rc = upload(&c->d_dec32, r.dec_lut.data(), r.dec_lut.size() * sizeof(RansDec32), c->dec32_bytes, s);
+        }
+        break;
+    }
+    case SCL_CODER_TANS: {
+        c->tans = new TansHost();
+        rc = c->tans->init(*params, alphabet, freq, n_sym);
+        if (rc) break;
+        TansHost &t = *c->tans;
+        uint32_t *d_rows = nullptr;
+        rc = upload(&c->d_gen, &t.r.gen, sizeof(RansGeneric), sizeof(RansGeneric), s);
+        if (!rc) rc = upload(&c->d_tsym, t.sym_tab.data(), sizeof(TansSym) * 256, sizeof(TansSym) * 256, s);
+        if (!rc) rc = upload(&d_rows, t.row_of_idx.data(), sizeof(uint32_t) * n_sym, sizeof(uint32_t) * n_sym, s);
+        if (rc) break;
+        c->ttab_bytes = (uint32_t)round16(t.r.c.L * 4);
+        cudaError_t e = cudaMalloc((void **)&c->d_tenc, c->ttab_bytes);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_tdec, c->ttab_bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tenc, 0, c->ttab_bytes, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tdec, 0, c->ttab_bytes, s);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "tANS table alloc");
+            cudaFree(d_rows);
+            break;
+        }
+        uint32_t grid = (uint32_t)((t.r.c.L + 255) / 256);
+        tans_build_kernel<<<grid, 256, 0, s>>>(c->d_gen, t.r.c, d_rows, c->d_tenc, c->d_tdec);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d_rows);
+        if (e != cudaSuccess) rc = cuda_fail(e, "tans_build_kernel");
+        break;
+    }
+    case SCL_CODER_RANGE: {
+        c->range = new RangeHost();
+        rc = c->range->init(*params, alphabet, freq, n_sym);
+        if (!rc) rc = upload(&c->d_range, &c->range->t, sizeof(RangeTab), sizeof(RangeTab), s);
+        break;
+    }
+    case SCL_CODER_AEC: {
+        c->aec = new AecHost();
+        rc = c->aec->init(*params, alphabet, freq, n_sym);
+        if (!rc) rc = upload(&c->d_aec, &c->aec->t, sizeof(AecTab), sizeof(AecTab), s);
+        break;
+    }
+    default:
+        rc = SCL_E_INVALID;
+    }
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(s);  // host staging buffers die with this call
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    if (rc) {
+        scl_coder_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return SCL_E_OK;
+}
+
+extern "C" uint64_t scl_coder_max_encoded_bytes(const scl_coder *c, uint64_t block_len) {
+    uint64_t bits = 0;
+    if (c->rans) bits = c->rans->max_encoded_bits(block_len);
+    if (c->tans) bits = c->tans->r.max_encoded_bits(block_len);
+    if (c->range) bits = c->range->max_encoded_bits(block_len);
+    if (c->aec) bits = c->aec->max_encoded_bits(block_len);
+    uint64_t bytes = (bits + 7) / 8 + 4;  // + one spare word: the last partial word is written whole
+    return (bytes + 15) & ~15ull;
+}
+
+extern "C" int scl_coder_path(const scl_coder *c, int decode) {
+    if (c->rans) return decode ? (c->rans->dec32 ? 0 : 1) : (c->rans->enc32 ? 0 : 1);
+    return 0;
+}
+
+static int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return SCL_E_OK;
+}
+
+extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
+                                 uint64_t n_blocks, uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_bit_offset,
+                                 uint64_t *d_out_bit_len, uint64_t *d_model, uint32_t *d_status, void *stream) {
+    if (!c || !d_out || !d_out_bit_offset || !d_out_bit_len || !d_status) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    if (!d_sym && (d_sizes || block_len)) return SCL_E_INVALID;
+    if ((out_stride & 15) || (((uintptr_t)d_out) & 15) || out_stride < 16) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    BlockIo io{d_sym, sym_stride, d_sizes, block_len, n_blocks, d_out, out_stride, d_out_bit_offset, d_out_bit_len, d_status};
+    uint32_t grid = (uint32_t)((n_blocks + kThreads - 1) / kThreads);
+    if (c->rans) {
+        const RansHost &r = *c->rans;
+        if (r.enc32) {
+            if (r.c.check_sym)
+                rans32_encode_kernel<true><<<grid, kThreads, 0, s>>>(c->d_enc32, r.c, io);
+            else
+                rans32_encode_kernel<false><<<grid, kThreads, 0, s>>>(c->d_enc32, r.c, io);
+        } else {
+            rans64_encode_kernel<<<grid, kThreads, 0, s>>>(c->d_gen, r.c, io);
+        }
+        return check_launch("rans_encode_kernel");
+    }
+    if (c->tans) {
+        const TansHost &t = *c->tans;
+        if (c->ttab_bytes <= kTansSmemTableMax) {
+            SCL_CUDA(cudaFuncSetAttribute(tans_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
+            tans_encode_kernel<true><<<grid, kThreads, c->ttab_bytes, s>>>(c->d_tsym, c->d_tenc, c->ttab_bytes, t.r.c, io);
+        } else {
+            tans_encode_kernel<false><<<grid, kThreads, 0, s>>>(c->d_tsym, c->d_tenc, 0, t.r.c, io);
+        }
+        return check_launch("tans_encode_kernel");
+    }
+    if (c->range) {
+        range_encode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
+        return check_launch("range_encode_kernel");
+    }
+    if (c->aec) {
+        uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
+        aec_encode_kernel<<<g, kAecThreads, kAecTreeBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_encode_kernel");
+    }
+    return SCL_E_INVALID;
+}
+
+extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64_t in_bytes, const uint64_t *d_bit_offset,
+                                 const uint64_t *d_bit_len, uint64_t n_blocks, uint8_t *d_sym, uint64_t sym_stride, uint32_t *d_sizes,
+                                 uint64_t *d_bits_consumed, uint64_t *d_model, uint32_t *d_status, void *stream) {
+    if (!c || !d_in || !d_bit_offset || !d_sizes || !d_bits_consumed || !d_status) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    if (!d_sym && sym_stride) return SCL_E_INVALID;
+    if (((uintptr_t)d_in) & 15) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    DecodeIo io{d_in, in_bytes, d_bit_offset, d_bit_len, n_blocks, d_sym, sym_stride, d_sizes, d_bits_consumed, d_status};
+    uint32_t grid = (uint32_t)((n_blocks + kThreads - 1) / kThreads);
+    if (c->rans) {
+        const RansHost &r = *c->rans;
+        if (r.dec32)
+            rans32_decode_kernel<<<grid, kThreads, c->dec32_bytes, s>>>(c->d_dec32, c->dec32_bytes, r.c, io);
+        else
+            rans64_decode_kernel<<<grid, kThreads, 0, s>>>(c->d_gen, r.c, io);
+        return check_launch("rans_decode_kernel");
+    }
+    if (c->tans) {
+        const TansHost &t = *c->tans;
+        if (c->ttab_bytes <= kTansSmemTableMax) {
+            SCL_CUDA(cudaFuncSetAttribute(tans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
+            tans_decode_kernel<true><<<grid, kThreads, c->ttab_bytes, s>>>(c->d_tdec, c->ttab_bytes, t.r.c, io);
+        } else {
+            tans_decode_kernel<false><<<grid, kThreads, 0, s>>>(c->d_tdec, 0, t.r.c, io);
+        }
+        return check_launch("tans_decode_kernel");
+    }
+    if (c->range) {
+        range_decode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
+        return check_launch("range_decode_kernel");
+    }
+    if (c->aec) {
+        uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
+        aec_decode_kernel<<<g, kAecThreads, kAecTreeBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_decode_kernel");
+    }
+    return SCL_E_INVALID;
+}
+
+extern "C" int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
+                               uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream) {
+    if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    pack_kernel<false><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
+                                                                                  d_dst_byte_offset);
+    return check_launch("pack_kernel");
+}
+
+extern "C" int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
+                                uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream) {
+    if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    pack_kernel<true><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
+                                                                                 d_dst_byte_offset);
+    return check_launch("frame_kernel");
+}
+
+extern "C" int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries, void *stream) {
+    if (!c || !c->tans || n_entries != c->tans->r.c.L) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    SCL_CUDA(cudaMemcpyAsync(enc_table, c->d_tenc, n_entries * 4, cudaMemcpyDeviceToHost, s));
+    SCL_CUDA(cudaMemcpyAsync(dec_packed, c->d_tdec, n_entries * 4, cudaMemcpyDeviceToHost, s));
+    SCL_CUDA(cudaStreamSynchronize(s));
+    return SCL_E_OK;
+}

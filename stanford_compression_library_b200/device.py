@@ -1,0 +1,210 @@
+"""Device-side objects: a coder handle (tables in HBM) and the batched encoded/decoded forms.
+
+PyTorch is used only for device memory, streams and (in sharding.py) torch.distributed; all
+coding work is done by the CUDA kernels behind the C-ABI (include/scl_b200.h).
+"""
+from dataclasses import dataclass
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .utils.bitarray_utils import BitArray
+
+_STATUS_EXC = {
+    _cabi.ST_BAD_SYMBOL: (KeyError, "symbol not in the Frequencies alphabet"),
+    _cabi.ST_STATE_MISMATCH: (AssertionError, "rANS/tANS end state != INITIAL_STATE (corrupt stream)"),
+    _cabi.ST_OVERFLOW: (OverflowError, "block size does not fit DATA_BLOCK_SIZE_BITS, or the output slot is too small"),
+    _cabi.ST_TRUNCATED: (ValueError, "encoded stream ended inside a block"),
+    _cabi.ST_TOTAL_FREQ: (AssertionError, "the frequency total is too large (>= MAX_ALLOWED_TOTAL_FREQ)"),
+    _cabi.ST_EMPTY_BLOCK: (ValueError, "arithmetic decoder: a block of size 0 cannot be decoded (the reference does not terminate on it)"),
+}
+
+
+def require_cuda():
+    _cabi.lib()  # raises BackendUnavailable if the extension is not built
+    if not torch.cuda.is_available():
+        raise _cabi.BackendUnavailable("no CUDA device: this backend has no CPU fallback")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def raise_for_status(status: torch.Tensor):
+    """Turn per-block status words into the exception the reference would have raised."""
+    bad = torch.nonzero(status)
+    if bad.numel() == 0:
+        return
+    b = int(bad[0])
+    code = int(status[b])
+    exc, msg = _STATUS_EXC.get(code, (RuntimeError, "status %d" % code))
+    raise exc("block %d: %s" % (b, msg))
+
+
+@dataclass
+class EncodedBlocks:
+    """Output of `encode_blocks`: per-block bit streams inside one device byte buffer.
+
+    Block b is bits [bit_offset[b], bit_offset[b] + bit_len[b]) of `buf` (MSB-first).
+    """
+
+    buf: torch.Tensor  # uint8 [n_bytes], device
+    bit_offset: torch.Tensor  # int64 [B]
+    bit_len: torch.Tensor  # int64 [B]
+    status: torch.Tensor  # int32 [B]
+    out_stride: int = 0
+
+    @property
+    def n_blocks(self):
+        return int(self.bit_len.numel())
+
+    def check(self):
+        raise_for_status(self.status)
+        return self
+
+    def total_bytes(self) -> int:
+        """Sum over blocks of ceil(bit_len / 8): the `C` of the roofline accounting."""
+        return int(((self.bit_len + 7) // 8).sum())
+
+    def block(self, b: int) -> BitArray:
+        off, n = int(self.bit_offset[b]), int(self.bit_len[b])
+        first, last = off >> 3, (off + n + 7) >> 3
+        host = self.buf[first:last].cpu().numpy()
+        return BitArray.from_packed(host, n, off - 8 * first)
+
+    def packed_offsets(self):
+        nbytes = (self.bit_len + 7) // 8
+        return torch.cumsum(nbytes, 0) - nbytes, int(nbytes.sum())
+
+    def pack(self) -> "EncodedBlocks":
+        """Contiguous, byte-aligned, left-aligned streams == concatenated BitArray.tobytes()."""
+        offs, total = self.packed_offsets()
+        dst = torch.zeros(total + 16, dtype=torch.uint8, device=self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            rc = _cabi.lib().scl_pack_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
+        _cabi.check(rc, "scl_pack_blocks")
+        return EncodedBlocks(dst, offs * 8, self.bit_len, self.status, 0)
+
+    def frame(self):
+        """Bytes of the reference's EncodedBlockWriter file format (encoded_stream.py:150-175).
+
+        Returns (uint8 device tensor, int64 byte offsets [B+1])."""
+        nbytes = 4 + (self.bit_len + 3 + 7) // 8
+        ends = torch.cumsum(nbytes, 0)
+        offs = ends - nbytes
+        total = int(ends[-1]) if self.n_blocks else 0
+        dst = torch.zeros(total + 16, dtype=torch.uint8, device=self.buf.device)
+        with torch.cuda.device(self.buf.device):
+            rc = _cabi.lib().scl_frame_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
+        _cabi.check(rc, "scl_frame_blocks")
+        return dst[:total], torch.cat([offs, ends[-1:]]) if self.n_blocks else offs
+
+    @classmethod
+    def from_bitarrays(cls, blocks, device="cuda"):
+        """Host BitArrays -> device buffer (each block byte-aligned, 16 B of slack at the end)."""
+        packed = [np.frombuffer(b.tobytes(), dtype=np.uint8) for b in blocks]
+        lens = np.array([len(b) for b in blocks], dtype=np.int64)
+        nbytes = np.array([p.size for p in packed], dtype=np.int64)
+        offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.int64) if len(blocks) else np.zeros(0, dtype=np.int64)
+        host = np.concatenate(packed + [np.zeros(16, dtype=np.uint8)]) if packed else np.zeros(16, dtype=np.uint8)
+        return cls(torch.from_numpy(host).to(device), torch.from_numpy(offs * 8).to(device), torch.from_numpy(lens).to(device),
+                   torch.zeros(len(blocks), dtype=torch.int32, device=device), 0)
+
+
+@dataclass
+class DecodedBlocks:
+    symbols: torch.Tensor  # uint8 [B, stride]
+    sizes: torch.Tensor  # int32 [B]
+    bits_consumed: torch.Tensor  # int64 [B]
+    status: torch.Tensor  # int32 [B]
+
+    def check(self):
+        raise_for_status(self.status)
+        return self
+
+
+class DeviceCoder:
+    """Owns one `scl_coder` handle (parameters + lookup tables resident in HBM)."""
+
+    def __init__(self, params: _cabi.SclParams, alphabet: np.ndarray, freq: np.ndarray, device=None):
+        require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n_sym = int(freq.size)
+        alphabet = np.ascontiguousarray(alphabet, dtype=np.uint8)
+        freq = np.ascontiguousarray(freq, dtype=np.uint64)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().scl_coder_create(ctypes.byref(params), alphabet.ctypes.data_as(ctypes.c_void_p), freq.ctypes.data_as(ctypes.c_void_p),
+                                              self.n_sym, _stream(), ctypes.byref(h))
+        _cabi.check(rc, "scl_coder_create")
+        self._h = h
+        self.params = params
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _cabi.lib().scl_coder_destroy(h)
+            except Exception:
+                pass
+
+    def max_encoded_bytes(self, block_len: int) -> int:
+        return int(_cabi.lib().scl_coder_max_encoded_bytes(self._h, int(block_len)))
+
+    def path(self, decode: bool) -> str:
+        return "fast32" if _cabi.lib().scl_coder_path(self._h, 1 if decode else 0) == 0 else "generic64"
+
+    def _to_device(self, t, dtype):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.ascontiguousarray(t))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    def encode_blocks(self, data, sizes=None, model=None, out_stride=None) -> EncodedBlocks:
+        """data: uint8 [B, N] (device, or host -- copied).  sizes: optional int32 [B] (ragged)."""
+        data = self._to_device(data, torch.uint8)
+        if data.dim() == 1:
+            data = data[None, :]
+        B, N = data.shape
+        if sizes is not None:
+            sizes = self._to_device(sizes, torch.int32)
+        stride = out_stride or self.max_encoded_bytes(N)
+        buf = torch.empty(B * stride + 16, dtype=torch.uint8, device=self.device)
+        bit_off = torch.empty(B, dtype=torch.int64, device=self.device)
+        bit_len = torch.empty(B, dtype=torch.int64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().scl_encode_blocks(self._h, _ptr(data) if N else _ptr(buf), data.stride(0) if N else 0, _ptr(sizes), N, B, _ptr(buf), stride,
+                                               _ptr(bit_off), _ptr(bit_len), _ptr(model), _ptr(status), _stream())
+        _cabi.check(rc, "scl_encode_blocks")
+        return EncodedBlocks(buf, bit_off, bit_len, status, stride)
+
+    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, model=None, out=None) -> DecodedBlocks:
+        B = enc.n_blocks
+        stride = (int(max_block_len) + 15) // 16 * 16 if out is None else out.stride(0)
+        stride = max(stride, 16)
+        if out is None:
+            out = torch.empty((B, stride), dtype=torch.uint8, device=self.device)
+        sizes = torch.empty(B, dtype=torch.int32, device=self.device)
+        used = torch.empty(B, dtype=torch.int64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().scl_decode_blocks(self._h, _ptr(enc.buf), enc.buf.numel(), _ptr(enc.bit_offset), _ptr(enc.bit_len), B, _ptr(out), stride,
+                                               _ptr(sizes), _ptr(used), _ptr(model), _ptr(status), _stream())
+        _cabi.check(rc, "scl_decode_blocks")
+        return DecodedBlocks(out, sizes, used, status)
+
+    def tans_tables(self, L: int):
+        enc = np.zeros(L, dtype=np.uint32)
+        dec = np.zeros(L, dtype=np.uint32)
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().scl_tans_tables_to_host(self._h, enc.ctypes.data_as(ctypes.c_void_p), dec.ctypes.data_as(ctypes.c_void_p), L, _stream())
+        _cabi.check(rc, "scl_tans_tables_to_host")
+        return enc, dec

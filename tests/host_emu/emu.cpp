@@ -1,0 +1,205 @@
+// emu.cpp -- CPU lane-emulation harness (TEST INFRASTRUCTURE ONLY; never loaded by the product).
+//
+// Compiles the product's __host__ __device__ per-lane recurrences (csrc/scl_lane.cuh) and the
+// host table builders (csrc/scl_tables.hpp) with plain g++ and runs them one "lane" at a time
+// with the same I/O contract as scl_encode_blocks / scl_decode_blocks.  It lets the `not gpu`
+// test tier check the integer logic the kernels execute against the oracle without a GPU; the
+// `-m gpu` tier then checks the real kernels through the C-ABI.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../stanford_compression_library_b200/csrc/scl_lane.cuh"
+#include "../../stanford_compression_library_b200/csrc/scl_tables.hpp"
+
+using namespace scl;
+
+namespace {
+struct HostTree {
+    uint32_t f[257];
+    uint32_t get(uint32_t i) const { return f[i]; }
+    void set(uint32_t i, uint32_t v) { f[i] = v; }
+};
+struct Emu {
+    scl_params p;
+    RansHost *rans = nullptr;
+    TansHost *tans = nullptr;
+    RangeHost *range = nullptr;
+    AecHost *aec = nullptr;
+    std::vector<uint32_t> tenc, tdec;
+    ~Emu() {
+        delete rans;
+        delete tans;
+        delete range;
+        delete aec;
+    }
+};
+uint64_t load_model(HostTree &F, const AecTab &tab, const AecConst &c, const uint64_t *model) {
+    uint64_t total = 0;
+    F.set(0, 0);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t f = 0;
+        if (i < c.n_sym) f = model ? (uint32_t)model[i] : tab.init_freq[i];
+        F.set(i + 1, f);
+        total += f;
+    }
+    fen_build(F);
+    return total;
+}
+void store_model(HostTree &F, const AecConst &c, uint64_t *model) {
+    if (!model) return;
+    fen_unbuild(F);
+    for (uint32_t i = 0; i < c.n_sym; ++i) model[i] = F.get(i + 1);
+}
+}  // namespace
+
+extern "C" {
+
+int emu_create(const scl_params *params, const uint8_t *alphabet, const uint64_t *freq, uint32_t n_sym, void **out) {
+    Emu *e = new Emu();
+    e->p = *params;
+    int rc;
+    switch (params->coder) {
+    case SCL_CODER_RANS:
+        e->rans = new RansHost();
+        rc = e->rans->init(*params, alphabet, freq, n_sym);
+        break;
+    case SCL_CODER_TANS: {
+        e->tans = new TansHost();
+        rc = e->tans->init(*params, alphabet, freq, n_sym);
+        if (rc) break;
+        uint64_t L = e->tans->r.c.L;
+        e->tenc.assign(L, 0);
+        e->tdec.assign(L, 0);
+        for (uint64_t i = 0; i < L; ++i)
+            tans_build_entry(e->tans->r.gen, e->tans->r.c, e->tans->row_of_idx.data(), e->tenc.data(), e->tdec.data(), i);
+        break;
+    }
+    case SCL_CODER_RANGE:
+        e->range = new RangeHost();
+        rc = e->range->init(*params, alphabet, freq, n_sym);
+        break;
+    case SCL_CODER_AEC:
+        e->aec = new AecHost();
+        rc = e->aec->init(*params, alphabet, freq, n_sym);
+        break;
+    default:
+        rc = SCL_E_INVALID;
+    }
+    if (rc) {
+        delete e;
+        return rc;
+    }
+    *out = e;
+    return 0;
+}
+void emu_destroy(void *h) { delete (Emu *)h; }
+
+int emu_path(void *h, int decode) {
+    Emu *e = (Emu *)h;
+    if (e->rans) return decode ? (e->rans->dec32 ? 0 : 1) : (e->rans->enc32 ? 0 : 1);
+    return 0;
+}
+// force the generic 64-bit rANS path (to test it on parameter sets the fast path would take)
+void emu_force_generic(void *h) {
+    Emu *e = (Emu *)h;
+    if (e->rans) e->rans->enc32 = e->rans->dec32 = false;
+}
+uint64_t emu_max_encoded_bytes(void *h, uint64_t block_len) {
+    Emu *e = (Emu *)h;
+    uint64_t bits = 0;
+    if (e->rans) bits = e->rans->max_encoded_bits(block_len);
+    if (e->tans) bits = e->tans->r.max_encoded_bits(block_len);
+    if (e->range) bits = e->range->max_encoded_bits(block_len);
+    if (e->aec) bits = e->aec->max_encoded_bits(block_len);
+    uint64_t bytes = (bits + 7) / 8 + 4;
+    return (bytes + 15) & ~15ull;
+}
+int emu_tans_tables(void *h, uint32_t *enc, uint32_t *dec, uint64_t n) {
+    Emu *e = (Emu *)h;
+    if (!e->tans || n != e->tans->r.c.L) return SCL_E_INVALID;
+    memcpy(enc, e->tenc.data(), n * 4);
+    memcpy(dec, e->tdec.data(), n * 4);
+    return 0;
+}
+
+int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const uint32_t *sizes, uint32_t block_len, uint64_t n_blocks,
+                      uint8_t *out, uint64_t out_stride, uint64_t *bit_off, uint64_t *bit_len, uint64_t *model, uint32_t *status) {
+    Emu *e = (Emu *)h;
+    if ((out_stride & 15) || (((uintptr_t)out) & 15)) return SCL_E_INVALID;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        uint32_t n = sizes ? sizes[b] : block_len;
+        uint8_t *slot = out + b * out_stride;
+        const uint8_t *row = sym + b * sym_stride;
+        uint64_t bits = 0;
+        uint32_t st;
+        bool lifo = true;
+        if (e->rans || e->tans) {
+            LifoBitWriter w;
+            w.init(slot, slot + out_stride);
+            if (e->rans) {
+                RansHost &r = *e->rans;
+                if (r.enc32)
+                    st = r.c.check_sym ? rans32_encode_lane<true>(r.enc_tab.data(), r.c, row, n, w, bits)
+                                       : rans32_encode_lane<false>(r.enc_tab.data(), r.c, row, n, w, bits);
+                else
+                    st = rans64_encode_lane(r.gen, r.c, row, n, w, bits);
+            } else {
+                st = tans_encode_lane(e->tans->sym_tab.data(), e->tenc.data(), e->tans->r.c, row, n, w, bits);
+            }
+        } else {
+            lifo = false;
+            FwdBitWriter w;
+            w.init(slot, slot + out_stride);
+            if (e->range) {
+                st = range_encode_lane(e->range->t, e->range->c, row, n, w, bits);
+            } else {
+                HostTree F;
+                uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
+                uint64_t total = load_model(F, e->aec->t, e->aec->c, mm), tout = 0;
+                st = aec_encode_lane(F, e->aec->t, e->aec->c, total, row, n, w, bits, tout);
+                store_model(F, e->aec->c, mm);
+            }
+        }
+        bit_len[b] = bits;
+        bit_off[b] = lifo ? (b + 1) * out_stride * 8 - bits : b * out_stride * 8;
+        status[b] = st;
+    }
+    return 0;
+}
+
+int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint64_t *bit_off, const uint64_t *bit_len, uint64_t n_blocks,
+                      uint8_t *sym, uint64_t sym_stride, uint32_t *sizes, uint64_t *consumed, uint64_t *model, uint32_t *status) {
+    Emu *e = (Emu *)h;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        BitReader r;
+        uint64_t off = bit_off[b];
+        r.init(in, in_bytes, off);
+        uint64_t avail = bit_len ? bit_len[b] : (in_bytes * 8 > off ? in_bytes * 8 - off : 0);
+        uint8_t *row = sym + b * sym_stride;
+        uint32_t size = 0, st;
+        uint64_t used = 0;
+        if (e->rans) {
+            RansHost &rh = *e->rans;
+            st = rh.dec32 ? rans32_decode_lane(rh.dec_lut.data(), rh.c, r, row, sym_stride, size, used)
+                          : rans64_decode_lane(rh.gen, rh.c, r, row, sym_stride, size, used);
+            if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
+        } else if (e->tans) {
+            st = tans_decode_lane(e->tdec.data(), e->tans->r.c, r, row, sym_stride, size, used);
+            if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
+        } else if (e->range) {
+            st = range_decode_lane(e->range->t, e->range->c, r, avail, row, sym_stride, size, used);
+        } else {
+            HostTree F;
+            uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
+            uint64_t total = load_model(F, e->aec->t, e->aec->c, mm), tout = 0;
+            st = aec_decode_lane(F, e->aec->t, e->aec->c, total, r, avail, row, sym_stride, size, used, tout);
+            store_model(F, e->aec->c, mm);
+        }
+        sizes[b] = size;
+        consumed[b] = used;
+        status[b] = st;
+    }
+    return 0;
+}
+}

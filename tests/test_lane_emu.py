@@ -1,0 +1,207 @@
+"""CPU tier: the product's per-lane recurrences (csrc/scl_lane.cuh) and host table builders
+(csrc/scl_tables.hpp), compiled for the host by tests/host_emu, against the golden vectors from
+the unmodified reference and against the C oracle on random inputs.  The same comparisons run
+against the real CUDA kernels in tests/test_gpu_parity.py (-m gpu)."""
+import numpy as np
+import pytest
+
+from oracle import scl_oracle as so
+from tests.emu_util import EmuCoder, extract_bits, params_from_case
+from tests.golden_util import case_id, load_golden, with_garbage
+
+CASES = load_golden()
+
+
+def _roundtrip_case(c, force_generic=False):
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    if force_generic:
+        coder.force_generic()
+    n = c["n"]
+    model = np.array([c["freqs"]], dtype=np.uint64) if c["coder"] == "aec" else None
+    out, off, ln, st = coder.encode(c["data"].reshape(1, -1), model=model)
+    assert st[0] == 0
+    assert int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    if c["coder"] == "aec":
+        assert model[0].tolist() == c["model"]["final_freqs"]
+    # decode stream + garbage placed at an odd bit offset
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    lead = 5
+    bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
+    buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
+    model = np.array([c["freqs"]], dtype=np.uint64) if c["coder"] == "aec" else None
+    if c["coder"] == "aec" and n == 0:
+        return
+    sym, sizes, used, st = coder.decode(buf, [lead], [total], max(n, 1), model=model)
+    assert st[0] == 0
+    assert int(sizes[0]) == n
+    assert sym[0, :n].tolist() == c["data"].tolist()
+    assert int(used[0]) == c["consumed"]
+    return coder
+
+
+@pytest.mark.parametrize("c", CASES, ids=case_id)
+def test_emu_matches_golden(c):
+    _roundtrip_case(c)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "rans"], ids=case_id)
+def test_emu_generic_rans_path_matches_golden(c):
+    _roundtrip_case(c, force_generic=True)
+
+
+def test_fast_path_selection():
+    by_note = {c["note"]: c for c in CASES}
+    z = by_note["cfg2 zipf default params"]
+    coder = EmuCoder(params_from_case(z), None, z["freqs"])
+    assert coder.path(False) == 0 and coder.path(True) == 0  # both fast for the benchmark table
+    z8 = by_note["cfg2 zipf NBO=8 RF=2^12"]
+    coder = EmuCoder(params_from_case(z8), None, z8["freqs"])
+    assert coder.path(False) == 0 and coder.path(True) == 0
+    big = by_note["H ~ 2^46: 64-bit state"]
+    coder = EmuCoder(params_from_case(big), None, big["freqs"])
+    assert coder.path(False) == 1 and coder.path(True) == 1
+    npo2 = by_note["cfg1 counts+1 (M not a power of two) default params"]
+    coder = EmuCoder(params_from_case(npo2), None, npo2["freqs"])
+    assert coder.path(False) == 0 and coder.path(True) == 1  # magic-number division still applies to encode
+
+
+def test_tans_tables_kat():
+    c = next(c for c in CASES if c["coder"] == "tans" and c["note"].startswith("KAT"))
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    enc, dec = coder.tans_tables(8)
+    assert enc.tolist() == [8, 9, 10, 11, 12, 13, 14, 15]  # tANS.py:297-306
+    assert [(int(e) & 0xFF, int(e) >> 8) for e in dec] == [(0, 3), (0, 4), (0, 5), (1, 3), (1, 4), (1, 5), (2, 2), (2, 3)]  # :322-331
+
+
+def _random_freqs(rng, n_sym, total=None):
+    f = rng.integers(1, 50, size=n_sym).astype(np.int64)
+    if total is not None:  # normalise to an exact total, keep >= 1
+        f = np.maximum(1, np.floor(f / f.sum() * (total - n_sym)).astype(np.int64) + 1)
+        f[0] += total - f.sum()
+        assert f.min() >= 1 and f.sum() == total
+    return [int(x) for x in f]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_emu_vs_oracle_random_rans_tans(seed):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(seed)
+    n_sym = int(rng.choice([2, 3, 17, 256]))
+    pow2 = bool(rng.integers(0, 2))
+    freqs = _random_freqs(rng, n_sym, total=int(rng.choice([256, 1024, 4096])) if pow2 else None)
+    nbo = int(rng.choice([1, 1, 2, 4, 8]))
+    rf = int(rng.choice([1, 2, 1 << 4, 1 << 8, 1 << 12, 1 << 16]))
+    M = sum(freqs)
+    H = rf * M * (1 << nbo) - 1
+    nsb = so.ref_get_bit_width(H)
+    B, N = 9, int(rng.integers(1, 300))
+    p = np.array(freqs, dtype=np.float64)
+    sym = rng.choice(n_sym, size=(B, N), p=p / p.sum()).astype(np.uint8)
+    sizes = rng.integers(0, N + 1, size=B).astype(np.uint32)
+    oracle = so.Oracle.rans(freqs, NUM_BITS_OUT=nbo, RANGE_FACTOR=rf)
+    coders = [("rans", _cabi.CODER_RANS)]
+    if pow2 and nbo == 1 and rf * M <= (1 << 20):
+        coders.append(("tans", _cabi.CODER_TANS))
+    for name, kind in coders:
+        prm = SclParams(coder=kind, data_block_size_bits=32, num_bits_out=nbo, range_factor=rf, num_state_bits=nsb, precision=0, model=0,
+                        max_allowed_total_freq=0)
+        coder = EmuCoder(prm, None, freqs)
+        out, off, ln, st = coder.encode(sym, sizes=sizes)
+        assert (st == 0).all()
+        for b in range(B):
+            enc, nb = oracle.encode_block(sym[b, : sizes[b]])
+            assert nb == ln[b], (name, b)
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (name, b)
+        dsym, dsz, used, st = coder.decode(out, off, ln, N)
+        assert (st == 0).all() and (dsz == sizes).all() and (used == ln).all()
+        for b in range(B):
+            assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_emu_vs_oracle_random_range_aec(seed):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(100 + seed)
+    n_sym = int(rng.choice([2, 5, 64, 256]))
+    freqs = _random_freqs(rng, n_sym)
+    B, N = 6, int(rng.integers(1, 400))
+    p = np.array(freqs, dtype=np.float64)
+    sym = rng.choice(n_sym, size=(B, N), p=p / p.sum()).astype(np.uint8)
+    sizes = rng.integers(1, N + 1, size=B).astype(np.uint32)
+    # range coder
+    oracle = so.Oracle.range_coder(freqs)
+    prm = SclParams(coder=_cabi.CODER_RANGE, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, freqs)
+    out, off, ln, st = coder.encode(sym, sizes=sizes)
+    assert (st == 0).all()
+    for b in range(B):
+        enc, nb = oracle.encode_block(sym[b, : sizes[b]])
+        assert nb == ln[b] and extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes()
+    dsym, dsz, used, st = coder.decode(out, off, ln, N)
+    assert (st == 0).all() and (dsz == sizes).all() and (used == ln).all()
+    for b in range(B):
+        assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+    # arithmetic coder, adaptive from uniform, fresh model per block; PRECISION 32 and 16
+    for P, max_total in ((32, 1 << 30), (16, 1 << 14), (32, 700)):
+        uni = [1] * n_sym
+        oracle = so.Oracle.aec(uni, PRECISION=P, max_allowed_total_freq=max_total)
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=P,
+                        model=_cabi.MODEL_ADAPTIVE_IID, max_allowed_total_freq=max_total)
+        coder = EmuCoder(prm, None, uni)
+        out, off, ln, st = coder.encode(sym, sizes=sizes)
+        assert (st == 0).all(), st
+        for b in range(B):
+            enc, nb = oracle.encode_block(sym[b, : sizes[b]])
+            assert nb == ln[b], (P, b)
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes()
+        dsym, dsz, used, st = coder.decode(out, off, ln, N)
+        assert (st == 0).all() and (dsz == sizes).all() and (used == ln).all()
+        for b in range(B):
+            assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+
+
+def test_emu_alphabet_mapping_and_bad_symbol():
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    freqs = [3, 3, 2]
+    alphabet = np.array([65, 66, 67], dtype=np.uint8)  # 'A','B','C' coded as their byte values
+    prm = SclParams(coder=_cabi.CODER_RANS, data_block_size_bits=5, num_bits_out=1, range_factor=1, num_state_bits=4, precision=0, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, alphabet, freqs)
+    out, off, ln, st = coder.encode(np.array([[65, 67, 66]], dtype=np.uint8))
+    assert st[0] == 0 and so.bits_to_str(extract_bits(out, off[0], ln[0]), int(ln[0])) == "00011101110010"
+    sym, sizes, used, st = coder.decode(out, off, ln, 3)
+    assert sym[0, :3].tolist() == [65, 67, 66] and used[0] == 14
+    out, off, ln, st = coder.encode(np.array([[65, 68, 66]], dtype=np.uint8))
+    assert st[0] == _cabi.ST_BAD_SYMBOL
+
+
+def test_emu_status_words():
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    freqs = [1, 1, 2]
+    prm = SclParams(coder=_cabi.CODER_RANS, data_block_size_bits=32, num_bits_out=1, range_factor=1 << 16, num_state_bits=19, precision=0,
+                    model=0, max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, freqs)
+    sym = np.array([[0, 1, 2, 2, 1, 0, 2, 2]], dtype=np.uint8)
+    out, off, ln, st = coder.encode(sym)
+    corrupt = out.copy()
+    corrupt[int(off[0]) // 8 + 5] ^= 0x20  # flip a state bit
+    _, _, _, st = coder.decode(corrupt, off, ln, 8)
+    assert st[0] == _cabi.ST_STATE_MISMATCH
+    # output slot too small -> overflow status, no out-of-bounds write (UBSan/ASan-clean)
+    out, off, ln, st = coder.encode(np.zeros((1, 64), dtype=np.uint8) + 1, out_stride=16)
+    assert st[0] == _cabi.ST_OVERFLOW
+    # size does not fit DATA_BLOCK_SIZE_BITS
+    prm2 = SclParams(coder=_cabi.CODER_RANS, data_block_size_bits=2, num_bits_out=1, range_factor=1 << 16, num_state_bits=19, precision=0,
+                     model=0, max_allowed_total_freq=0)
+    out, off, ln, st = EmuCoder(prm2, None, freqs).encode(sym)
+    assert st[0] == _cabi.ST_OVERFLOW
