@@ -58,13 +58,13 @@ class GpuCoderBase:
         return DataBlock([self._byte2sym[int(b)] for b in row])
 
     # ---- batched API ---------------------------------------------------------------------
-    def encode_blocks(self, data, sizes=None) -> EncodedBlocks:
+    def encode_blocks(self, data, sizes=None, reuse: EncodedBlocks = None) -> EncodedBlocks:
         """Encode B independent blocks: data uint8 [B, N] (device or host tensor / ndarray)."""
-        return self.device_coder().encode_blocks(data, sizes=sizes)
+        return self.device_coder().encode_blocks(data, sizes=sizes, reuse=reuse)
 
-    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, out=None) -> DecodedBlocks:
+    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, out=None, reuse: DecodedBlocks = None) -> DecodedBlocks:
         """Decode B independent streams into uint8 [B, >=max_block_len]."""
-        return self.device_coder().decode_blocks(enc, max_block_len, out=out)
+        return self.device_coder().decode_blocks(enc, max_block_len, out=out, reuse=reuse)
 
     # ---- reference single-block API --------------------------------------------------------
     def _encode_one(self, data_block: DataBlock, model=None) -> BitArray:

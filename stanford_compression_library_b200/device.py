@@ -167,39 +167,49 @@ class DeviceCoder:
             t = t.to(dtype)
         return t.to(self.device, non_blocking=True).contiguous()
 
-    def encode_blocks(self, data, sizes=None, model=None, out_stride=None) -> EncodedBlocks:
-        """data: uint8 [B, N] (device, or host -- copied).  sizes: optional int32 [B] (ragged)."""
+    def encode_blocks(self, data, sizes=None, model=None, out_stride=None, reuse: EncodedBlocks = None) -> EncodedBlocks:
+        """data: uint8 [B, N] (device, or host -- copied).  sizes: optional int32 [B] (ragged).
+        `reuse`: an EncodedBlocks from an earlier call of the same shape whose buffers are overwritten
+        (no allocation in the call)."""
         data = self._to_device(data, torch.uint8)
         if data.dim() == 1:
             data = data[None, :]
         B, N = data.shape
         if sizes is not None:
             sizes = self._to_device(sizes, torch.int32)
-        stride = out_stride or self.max_encoded_bytes(N)
-        buf = torch.empty(B * stride + 16, dtype=torch.uint8, device=self.device)
-        bit_off = torch.empty(B, dtype=torch.int64, device=self.device)
-        bit_len = torch.empty(B, dtype=torch.int64, device=self.device)
-        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        if reuse is not None:
+            stride, buf, bit_off, bit_len, status = reuse.out_stride, reuse.buf, reuse.bit_offset, reuse.bit_len, reuse.status
+            assert buf.numel() >= B * stride and bit_len.numel() == B
+        else:
+            stride = out_stride or self.max_encoded_bytes(N)
+            buf = torch.empty(B * stride + 16, dtype=torch.uint8, device=self.device)
+            bit_off = torch.empty(B, dtype=torch.int64, device=self.device)
+            bit_len = torch.empty(B, dtype=torch.int64, device=self.device)
+            status = torch.empty(B, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             rc = _cabi.lib().scl_encode_blocks(self._h, _ptr(data) if N else _ptr(buf), data.stride(0) if N else 0, _ptr(sizes), N, B, _ptr(buf), stride,
                                                _ptr(bit_off), _ptr(bit_len), _ptr(model), _ptr(status), _stream())
         _cabi.check(rc, "scl_encode_blocks")
-        return EncodedBlocks(buf, bit_off, bit_len, status, stride)
+        return reuse if reuse is not None else EncodedBlocks(buf, bit_off, bit_len, status, stride)
 
-    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, model=None, out=None) -> DecodedBlocks:
+    def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, model=None, out=None, reuse: DecodedBlocks = None) -> DecodedBlocks:
         B = enc.n_blocks
-        stride = (int(max_block_len) + 15) // 16 * 16 if out is None else out.stride(0)
-        stride = max(stride, 16)
-        if out is None:
-            out = torch.empty((B, stride), dtype=torch.uint8, device=self.device)
-        sizes = torch.empty(B, dtype=torch.int32, device=self.device)
-        used = torch.empty(B, dtype=torch.int64, device=self.device)
-        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        if reuse is not None:
+            out, sizes, used, status = reuse.symbols, reuse.sizes, reuse.bits_consumed, reuse.status
+            stride = out.stride(0)
+        else:
+            stride = (int(max_block_len) + 15) // 16 * 16 if out is None else out.stride(0)
+            stride = max(stride, 16)
+            if out is None:
+                out = torch.empty((B, stride), dtype=torch.uint8, device=self.device)
+            sizes = torch.empty(B, dtype=torch.int32, device=self.device)
+            used = torch.empty(B, dtype=torch.int64, device=self.device)
+            status = torch.empty(B, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             rc = _cabi.lib().scl_decode_blocks(self._h, _ptr(enc.buf), enc.buf.numel(), _ptr(enc.bit_offset), _ptr(enc.bit_len), B, _ptr(out), stride,
                                                _ptr(sizes), _ptr(used), _ptr(model), _ptr(status), _stream())
         _cabi.check(rc, "scl_decode_blocks")
-        return DecodedBlocks(out, sizes, used, status)
+        return reuse if reuse is not None else DecodedBlocks(out, sizes, used, status)
 
     def tans_tables(self, L: int):
         enc = np.zeros(L, dtype=np.uint32)

@@ -1,0 +1,311 @@
+"""GPU tier (-m gpu): the CUDA kernels, called through the C-ABI / the drop-in classes, against
+ (a) the golden vectors generated from the unmodified reference,
+ (b) the C oracle on seeded random batches, and
+ (c) size-independent properties at the BASELINE.json sizes (round trip, exact bit accounting).
+Bit-exact everywhere: this path is pure integer arithmetic."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scl_oracle as so
+from tests.golden_util import case_id, load_golden, with_garbage
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_golden()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    from stanford_compression_library_b200 import _cabi
+
+    _cabi.lib()  # must be the built CUDA library, loudly
+    yield
+
+
+def _F(freqs):
+    from stanford_compression_library_b200 import Frequencies
+
+    return Frequencies({i: int(f) for i, f in enumerate(freqs)})
+
+
+def make_codec(c):
+    """(encoder, decoder) drop-in objects for a golden case."""
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, FixedFreqModel
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+
+    p = c["params"]
+    if c["coder"] in ("rans", "tans"):
+        P, E, D = (tANSParams, tANSEncoder, tANSDecoder) if c["coder"] == "tans" else (rANSParams, rANSEncoder, rANSDecoder)
+        params = P(_F(c["freqs"]), DATA_BLOCK_SIZE_BITS=p["DATA_BLOCK_SIZE_BITS"], NUM_BITS_OUT=p["NUM_BITS_OUT"], RANGE_FACTOR=p["RANGE_FACTOR"])
+        assert params.NUM_STATE_BITS == p["NUM_STATE_BITS"]
+        return E(params), D(params)
+    if c["coder"] == "range":
+        params = RangeCoderParams(**p)
+        return RangeEncoder(params, _F(c["freqs"])), RangeDecoder(params, _F(c["freqs"]))
+    params = AECParams(**p)
+    cls = AdaptiveIIDFreqModel if c["model"]["kind"] == "adaptive_iid" else FixedFreqModel
+    m = cls(_F(c["freqs"]), c["model"]["max_total"])
+    return ArithmeticEncoder(params, m), ArithmeticDecoder(params, copy.deepcopy(m))
+
+
+@pytest.mark.parametrize("c", CASES, ids=case_id)
+def test_dropin_classes_match_golden(c):
+    from stanford_compression_library_b200 import BitArray, DataBlock
+
+    enc, dec = make_codec(c)
+    ba = enc.encode_block(DataBlock(c["data"].tolist()))
+    assert isinstance(ba, BitArray)
+    assert len(ba) == c["nbits"]
+    assert ba.tobytes() == c["enc"].tobytes()
+    if c["coder"] == "aec":
+        assert [int(x) for x in enc.freq_model.freqs_current.freq_list] == c["model"]["final_freqs"]
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    block, used = dec.decode_block(BitArray.from_packed(packed, total))
+    assert list(block.data_list) == c["data"].tolist()
+    assert used == c["consumed"] == c["nbits"]
+
+
+def test_kat_string_symbols():
+    # rANS.py:303-360 / tANS.py:340-415 with the reference's own symbols "A","B","C"
+    from stanford_compression_library_b200 import BitArray, DataBlock, Frequencies
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+
+    freq = Frequencies({"A": 3, "B": 3, "C": 2})
+    data = DataBlock(["A", "C", "B"])
+    expected = BitArray("00011" + "1011" + "10" + "01" + "0")
+    for P, E, D in ((rANSParams, rANSEncoder, rANSDecoder), (tANSParams, tANSEncoder, tANSDecoder)):
+        params = P(freq, DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1)
+        assert params.INITIAL_STATE == 8 and params.NUM_STATE_BITS == 4
+        got = E(params).encode_block(data)
+        assert got == expected
+        block, used = D(params).decode_block(got + BitArray("1101"))
+        assert block.data_list == ["A", "C", "B"] and used == 14
+    # tANS lookup tables built on the device (tANS.py:285-337)
+    enc = tANSEncoder(tANSParams(freq, DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1))
+    assert enc.base_encode_step_table == {("A", 3): 8, ("A", 4): 9, ("A", 5): 10, ("B", 3): 11, ("B", 4): 12, ("B", 5): 13, ("C", 2): 14, ("C", 3): 15}
+    assert enc.shrink_state_num_out_bits_base_table == {"A": 1, "B": 1, "C": 2}
+    assert enc.shrink_state_thresh_table == {"A": 12, "B": 12, "C": 16}
+    dec = tANSDecoder(tANSParams(freq, DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1))
+    assert dec.base_decode_step_table == {8: ("A", 3), 9: ("A", 4), 10: ("A", 5), 11: ("B", 3), 12: ("B", 4), 13: ("B", 5), 14: ("C", 2), 15: ("C", 3)}
+    assert dec.expand_state_num_bits_table == {2: 2, 3: 2, 4: 1, 5: 1}
+    with pytest.raises(KeyError):
+        rANSEncoder(rANSParams(freq)).encode_block(DataBlock(["A", "Z"]))
+
+
+def _compare_batch_with_oracle(coder_enc, coder_dec, oracle, data, sizes=None, sample=None):
+    """encode on the GPU, compare every (sampled) block's bits with the oracle, decode, compare."""
+    B, N = data.shape
+    e = coder_enc.encode_blocks(data, sizes=sizes).check()
+    host = data.cpu().numpy()
+    hs = None if sizes is None else sizes.cpu().numpy().astype(np.uint32)
+    idx = range(B) if sample is None else sample
+    sub = np.ascontiguousarray(host[list(idx)])
+    subsz = None if hs is None else np.ascontiguousarray(hs[list(idx)])
+    ref_out, ref_bits, ref_st = oracle.encode_batch(sub, sizes=subsz, out_stride=e.out_stride + 64)
+    assert (ref_st == 0).all()
+    off = e.bit_offset.cpu().numpy()
+    ln = e.bit_len.cpu().numpy()
+    buf = e.buf.cpu().numpy()
+    for j, b in enumerate(idx):
+        assert int(ln[b]) == int(ref_bits[j]), "block %d: bit length %d != oracle %d" % (b, ln[b], ref_bits[j])
+        first, last = int(off[b]) >> 3, (int(off[b]) + int(ln[b]) + 7) >> 3
+        bits = np.unpackbits(buf[first:last])[int(off[b]) - 8 * first :][: int(ln[b])]
+        assert np.packbits(bits).tobytes() == ref_out[j, : (int(ln[b]) + 7) // 8].tobytes(), "block %d: bits differ from the oracle" % b
+    d = coder_dec.decode_blocks(e, N).check()
+    want_sizes = torch.full((B,), N, dtype=torch.int32, device=data.device) if sizes is None else sizes.to(torch.int32)
+    assert torch.equal(d.sizes, want_sizes)
+    assert torch.equal(d.bits_consumed, e.bit_len)
+    if sizes is None:
+        assert torch.equal(d.symbols[:, :N], data)
+    else:
+        mask = torch.arange(N, device=data.device)[None, :] < sizes[:, None]
+        assert torch.equal(d.symbols[:, :N][mask], data[mask])
+    return e, d
+
+
+@pytest.mark.parametrize("kw", [{}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12), dict(NUM_BITS_OUT=2, RANGE_FACTOR=1 << 10), dict(NUM_BITS_OUT=16, RANGE_FACTOR=1 << 20)],
+                         ids=["default", "nbo8_rf12", "nbo2_rf10", "nbo16_rf20_generic64"])
+def test_rans_batch_vs_oracle_zipf(kw):
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    params = rANSParams(zipf_frequencies(), **kw)
+    B, N = (1024, 4096) if "RANGE_FACTOR" not in kw or kw["RANGE_FACTOR"] != 1 << 20 else (256, 1024)
+    data = sample_blocks(fl, B, N, seed=1, device="cuda:0")
+    sizes = torch.randint(0, N + 1, (B,), device="cuda:0", dtype=torch.int32)
+    oracle = so.Oracle.rans(fl, **kw)
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    _compare_batch_with_oracle(enc, dec, oracle, data)
+    _compare_batch_with_oracle(enc, dec, oracle, data, sizes=sizes)
+
+
+def test_rans_non_power_of_two_total_and_uniform_cfg1():
+    # BASELINE cfg1: 4 KiB uniform bytes; table {b:16} and the counts+1 table (M = 4352)
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 256, size=(64, 4096)).astype(np.uint8)
+    data = torch.from_numpy(u).cuda()
+    for fl in ([16] * 256, (np.bincount(u[0], minlength=256) + 1).tolist()):
+        for kw in ({}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)):
+            params = rANSParams(_F(fl), **kw)
+            _compare_batch_with_oracle(rANSEncoder(params), rANSDecoder(params), so.Oracle.rans(fl, **kw), data)
+
+
+def test_tans_batch_vs_oracle_and_equals_rans():
+    from stanford_compression_library_b200.compressors.rANS import rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    data = sample_blocks(fl, 512, 4096, seed=2, device="cuda:0")
+    for rf in (1, 4, 1 << 8):  # 4096-, 16384- (shared memory) and 2^20-state (global memory) tables
+        params = tANSParams(zipf_frequencies(), RANGE_FACTOR=rf)
+        e, _ = _compare_batch_with_oracle(tANSEncoder(params), tANSDecoder(params), so.Oracle.tans(fl, RANGE_FACTOR=rf), data, sample=range(0, 512, 7))
+        r = rANSEncoder(rANSParams(zipf_frequencies(), RANGE_FACTOR=rf)).encode_blocks(data).check()
+        assert torch.equal(r.bit_len, e.bit_len)
+        assert torch.equal(r.pack().buf, e.pack().buf)  # identical bitstreams
+
+
+def test_range_batch_vs_oracle():
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    data = sample_blocks(fl, 512, 4096, seed=3, device="cuda:0")
+    sizes = torch.randint(0, 4097, (512,), device="cuda:0", dtype=torch.int32)
+    params = RangeCoderParams()
+    enc, dec = RangeEncoder(params, zipf_frequencies()), RangeDecoder(params, zipf_frequencies())
+    _compare_batch_with_oracle(enc, dec, so.Oracle.range_coder(fl), data, sizes=sizes, sample=range(0, 512, 5))
+    # extreme skew edge cases of range_coder.py:351-367
+    skew = [1, 1, 65534]
+    d2 = torch.from_numpy(np.stack([np.tile([0, 1, 2], 200), np.zeros(600, dtype=np.int64), np.full(600, 2)]).astype(np.uint8)).cuda()
+    enc, dec = RangeEncoder(params, _F(skew)), RangeDecoder(params, _F(skew))
+    _compare_batch_with_oracle(enc, dec, so.Oracle.range_coder(skew), d2)
+
+
+def test_aec_batch_vs_oracle_cfg4_shape():
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list
+
+    fl = zipf_freq_list()
+    data = sample_blocks(fl, 1024, 1024, seed=4, device="cuda:0")
+    sizes = torch.randint(1, 1025, (1024,), device="cuda:0", dtype=torch.int32)
+    params = AECParams()
+    uni = [1] * 256
+    enc = ArithmeticEncoder(params, AdaptiveIIDFreqModel(_F(uni), params.MAX_ALLOWED_TOTAL_FREQ))
+    dec = ArithmeticDecoder(params, AdaptiveIIDFreqModel(_F(uni), params.MAX_ALLOWED_TOTAL_FREQ))
+    oracle = so.Oracle.aec(uni)
+    _compare_batch_with_oracle(enc, dec, oracle, data, sample=range(0, 1024, 9))
+    _compare_batch_with_oracle(enc, dec, oracle, data, sizes=sizes, sample=range(0, 1024, 11))
+    assert enc.freq_model.freqs_current.freq_list == uni  # batched calls do not mutate the host model
+
+
+def test_aec_model_persists_across_encode_block_calls():
+    # the reference never resets the model between blocks (data_encoder_decoder.py:23-27)
+    from stanford_compression_library_b200 import DataBlock
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+
+    rng = np.random.default_rng(7)
+    blocks = [rng.integers(0, 4, size=200).astype(np.uint8) for _ in range(3)]
+    params = AECParams()
+    enc = ArithmeticEncoder(params, AdaptiveIIDFreqModel(_F([1, 1, 1, 1]), params.MAX_ALLOWED_TOTAL_FREQ))
+    dec = ArithmeticDecoder(params, AdaptiveIIDFreqModel(_F([1, 1, 1, 1]), params.MAX_ALLOWED_TOTAL_FREQ))
+    oracle = so.Oracle.aec([1, 1, 1, 1])
+    mf = np.array([1, 1, 1, 1], dtype=np.uint64)
+    for blk in blocks:
+        ref_bytes, ref_bits = oracle.encode_block(blk, model_freq=mf)
+        ba = enc.encode_block(DataBlock(blk.tolist()))
+        assert len(ba) == ref_bits and ba.tobytes() == ref_bytes.tobytes()
+        assert [int(x) for x in enc.freq_model.freqs_current.freq_list] == mf.tolist()
+        out, used = dec.decode_block(ba)
+        assert list(out.data_list) == blk.tolist() and used == ref_bits
+
+
+def test_pack_and_frame_kernels():
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    params = rANSParams(zipf_frequencies())  # 61-bit header: streams are not byte aligned
+    data = sample_blocks(fl, 300, 512, seed=5, device="cuda:0")
+    sizes = torch.randint(0, 513, (300,), device="cuda:0", dtype=torch.int32)
+    enc = rANSEncoder(params)
+    e = enc.encode_blocks(data, sizes=sizes).check()
+    packed = e.pack()
+    framed, foffs = e.frame()
+    hb, ho, hl = packed.buf.cpu().numpy(), (packed.bit_offset // 8).cpu().numpy(), e.bit_len.cpu().numpy()
+    fb, fo = framed.cpu().numpy(), foffs.cpu().numpy()
+    for b in range(300):
+        ba = e.block(b)
+        nb = (len(ba) + 7) // 8
+        assert hb[ho[b] : ho[b] + nb].tobytes() == ba.tobytes()
+        # reference framing (encoded_stream.py:22-46, 93-103): header + padded payload
+        n = len(ba)
+        num_pad = (8 - (n + 3) % 8) % 8
+        bits = np.concatenate([[(num_pad >> 2) & 1, (num_pad >> 1) & 1, num_pad & 1], np.zeros(num_pad, dtype=np.uint8), np.array(ba.tolist(), dtype=np.uint8)]).astype(np.uint8)
+        payload = np.packbits(bits).tobytes()
+        want = len(payload).to_bytes(4, "big") + payload
+        assert fb[fo[b] : fo[b + 1]].tobytes() == want
+    # decoding straight from the packed (left-aligned) form gives the same result
+    d = rANSDecoder(params).decode_blocks(packed, 512).check()
+    assert torch.equal(d.sizes, sizes) and torch.equal(d.bits_consumed, e.bit_len)
+
+
+@pytest.mark.parametrize("kw", [{}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)], ids=["default", "nbo8_rf12"])
+def test_rans_full_size_roundtrip_cfg2(kw):
+    """BASELINE cfg2 at full size: 65536 blocks x 4 KiB.  Properties: exact round trip, bits
+    consumed == bits produced for every block, end state accepted, compressed size close to the
+    table's cross-entropy; plus a strided sample of blocks bit-compared with the oracle."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    params = rANSParams(zipf_frequencies(), **kw)
+    B, N = 65536, 4096
+    data = sample_blocks(fl, B, N, seed=6, device="cuda:0")
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    e, d = _compare_batch_with_oracle(enc, dec, so.Oracle.rans(fl, **kw), data, sample=range(0, B, 2048))
+    p = np.array(fl) / 4096.0
+    xent = float(-(p * np.log2(p)).sum())  # data drawn from the table itself
+    bits_per_sym = float(e.bit_len.sum()) / (B * N)
+    assert abs(bits_per_sym - xent) < 0.05, (bits_per_sym, xent)
+
+
+def test_try_lossless_compression_harness_with_trailing_bits():
+    # mirrors scl/utils/test_utils.py:73-108 + rANS.py:363-401 on the drop-in classes
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.utils.test_utils import get_random_data_block, try_lossless_compression
+
+    freqs_list = [
+        Frequencies({"A": 1, "B": 1, "C": 2}),
+        Frequencies({"A": 12, "B": 34, "C": 1, "D": 45}),
+        Frequencies({"A": 34, "B": 35, "C": 546, "D": 1, "E": 13, "F": 245}),
+        Frequencies({"A": 5, "B": 5, "C": 5, "D": 5, "E": 5, "F": 5}),
+        Frequencies({"A": 1, "B": 3}),
+    ]
+    params_list = [
+        rANSParams(freqs_list[0]),
+        rANSParams(freqs_list[1]),
+        rANSParams(freqs_list[2], NUM_BITS_OUT=8),
+        rANSParams(freqs_list[3], RANGE_FACTOR=1 << 12),
+        rANSParams(freqs_list[4], RANGE_FACTOR=1 << 4),
+    ]
+    for freq, params in zip(freqs_list, params_list):
+        block = get_random_data_block(freq.get_prob_dist(), 10000, seed=0)
+        ok, nbits, _ = try_lossless_compression(block, rANSEncoder(params), rANSDecoder(params), add_extra_bits_to_encoder_output=True)
+        assert ok
