@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- the BASELINE.json metric: rANS encode+decode MB/s (uncompressed bytes) on Zipf-1.0
+bytes, blocks of 4 KiB, sharded by block range over N GPUs; % of the HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one encode pass + one decode pass over this rank's batch of blocks.  Per-GPU work is
+fixed (weak scaling): 262 144 blocks x 4 KiB = 1 GiB per GPU, so N=8 is exactly BASELINE
+configs[4] (8 GiB over 8 GPUs); configs[1] (65 536 blocks on one GPU) is measured in the same
+run at N=1 and reported under "also".  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK_LEN = 4096
+BLOCKS_PER_GPU = 262144
+METRIC = "rans_encode_plus_decode_throughput"
+UNIT = "MB/s"
+# headline parameter set = the reference's defaults, rANSParams(freqs) (rANS.py:88-95);
+# the 32-bit-state / byte-renormalisation set is measured beside it
+VARIANTS = {
+    "default": {},
+    "nbo8_rf4096": dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12),
+}
+HEADLINE = "default"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(fl, kw, data_host, n_threads, label):
+    """The oracle (C restatement of the reference's loops, oracle/scl_oracle.c) on the host cores:
+    encode + decode of a bounded sample of the same workload.  A reported baseline, not a target."""
+    import numpy as np
+
+    from oracle import scl_oracle as so
+
+    oracle = so.Oracle.rans(fl, **kw)
+    B, N = data_host.shape
+    stride = 2 * N + 64
+    t0 = time.perf_counter()
+    out, bits, st = oracle.encode_batch(data_host, out_stride=stride, n_threads=n_threads)
+    t1 = time.perf_counter()
+    offs = np.arange(B, dtype=np.uint64) * np.uint64(stride * 8)
+    dec, sz, used, st2 = oracle.decode_batch(out, offs, bits, N, n_threads=n_threads)
+    t2 = time.perf_counter()
+    assert (st == 0).all() and (st2 == 0).all() and (dec == data_host).all()
+    nbytes = B * N
+    return {
+        "value": nbytes / (t2 - t0) / 1e6, "unit": UNIT, "cores": n_threads, "kind": "port",
+        "sample": "%d blocks x %d B of the same Zipf batch, %s; encode %.1f MB/s, decode %.1f MB/s" % (B, N, label, nbytes / (t1 - t0) / 1e6, nbytes / (t2 - t1) / 1e6),
+        "note": "C restatement of the reference's per-symbol loops (OpenMP across blocks); the reference itself is pure Python "
+                "(~0.01-0.02 MB/s/core, BASELINE.md section 3) and cannot run on the GPU box",
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path (the oracle port -- the Python reference
+    cannot travel to the GPU box) on all host threads, same metric / config, bounded sample per step."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import scl_oracle as so
+    from stanford_compression_library_b200.workloads import zipf_freq_list, zipf_probabilities
+
+    so.build()
+    fl = zipf_freq_list()
+    threads = so.max_threads()
+    B = min(BLOCKS_PER_GPU, 1024 * threads)
+    rng = np.random.default_rng(0)
+    data = rng.choice(256, size=(B, BLOCK_LEN), p=np.array(zipf_probabilities())).astype(np.uint8)
+    kw = VARIANTS[HEADLINE]
+    res = None
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = cpu_baseline(fl, kw, data, threads, HEADLINE)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = B * BLOCK_LEN * len(times) / total / 1e6
+    res["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "rANS encode+decode, %d-block x %d B sample per step of the Zipf-1.0 batch, rANSParams %s" % (B, BLOCK_LEN, HEADLINE),
+                   "params": HEADLINE, "block_len": BLOCK_LEN},
+        "cpu_baseline": res,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks-per-gpu", type=int, default=BLOCKS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from stanford_compression_library_b200 import build as scl_build
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.device import EncodedBlocks
+    from stanford_compression_library_b200.sharding import broadcast_frequencies, gather_compressed_sizes, shard_range
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        scl_build.build()
+    if world > 1:
+        dist.barrier()
+
+    # frequency table: built on rank 0, broadcast over NCCL (the only collective on this path)
+    freqs = broadcast_frequencies(zipf_frequencies() if rank == 0 else None)
+    fl = [int(f) for f in freqs.freq_list]
+    B, N = args.blocks_per_gpu, BLOCK_LEN
+    lo, hi = shard_range(B * world, rank, world)  # this rank's blocks of the global stream
+    data = sample_blocks(zipf_probabilities(), B, N, seed=rank, device=dev)
+    peak, peak_src = measured_peak_gbs()
+    sampler = ClockSampler(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def bench_variant(name, data, steps, warmup, sample_clocks=False):
+        params = rANSParams(freqs, **VARIANTS[name])
+        enc, dec = rANSEncoder(params), rANSDecoder(params)
+        e = enc.encode_blocks(data)
+        d = dec.decode_blocks(e, N)
+        e.check(), d.check()
+        assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e.bit_len), "round trip failed"
+        nB = data.shape[0]
+        C = e.total_bytes()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        for _ in range(warmup):
+            enc.encode_blocks(data, reuse=e)
+            dec.decode_blocks(e, N, reuse=d)
+        barrier()
+        if sample_clocks:
+            sampler.start()
+        for i in range(steps):
+            ev[i][0].record()
+            enc.encode_blocks(data, reuse=e)
+            ev[i][1].record()
+            dec.decode_blocks(e, N, reuse=d)
+            ev[i][2].record()
+        barrier()
+        clocks = sampler.stop() if sample_clocks else None
+        total_ms = ev[0][0].elapsed_time(ev[-1][2])
+        enc_ms = sorted(ev[i][0].elapsed_time(ev[i][1]) for i in range(steps))
+        dec_ms = sorted(ev[i][1].elapsed_time(ev[i][2]) for i in range(steps))
+        t = torch.tensor([total_ms, sum(enc_ms) / steps, sum(dec_ms) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        total_ms, enc_avg, dec_avg = t.tolist()
+        raw = nB * N
+        return dict(name=name, params=params, enc=enc, dec=dec, e=e, d=d, C=C, raw=raw, total_ms=total_ms, enc_ms=enc_avg, dec_ms=dec_avg,
+                    enc_best=enc_ms[0], dec_best=dec_ms[0], clocks=clocks, steps=steps,
+                    paths=(enc.device_coder().path(False), dec.device_coder().path(True)))
+
+    def summarize(r, n_gpus):
+        raw, C = r["raw"], r["C"]
+        out = {
+            "value": n_gpus * raw * r["steps"] / (r["total_ms"] * 1e-3) / 1e6,
+            "ms_per_step": r["total_ms"] / r["steps"],
+            "encode_MBps": n_gpus * raw / (r["enc_ms"] * 1e-3) / 1e6,
+            "decode_MBps": n_gpus * raw / (r["dec_ms"] * 1e-3) / 1e6,
+            "encode_ms": r["enc_ms"], "decode_ms": r["dec_ms"],
+            "compressed_bytes_per_gpu": C, "bits_per_symbol": 8.0 * C / raw, "kernel_paths": r["paths"],
+            "roofline_encode_frac": (raw + C) / (r["enc_ms"] * 1e-3) / 1e9 / peak,
+            "roofline_decode_frac": (raw + C) / (r["dec_ms"] * 1e-3) / 1e9 / peak,
+            "hbm_read_only_frac": {"encode": raw / (r["enc_ms"] * 1e-3) / 1e9 / peak, "decode": C / (r["dec_ms"] * 1e-3) / 1e9 / peak},
+        }
+        return out
+
+    head = bench_variant(HEADLINE, data, args.steps, args.warmup, sample_clocks=True)
+    others = {k: bench_variant(k, data, max(5, args.steps // 2), 3) for k in VARIANTS if k != HEADLINE}
+    hs = summarize(head, world)
+
+    # ---- roofline of the dominant kernel (the longer of the two launches of a step) ----------
+    dom = "decode" if head["dec_ms"] >= head["enc_ms"] else "encode"
+    dom_ms = max(head["dec_ms"], head["enc_ms"])
+    alg_bytes = head["raw"] + head["C"]  # N + C per launch: enc reads N writes C, dec reads C writes N
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic = tj.get("rans32_%s_kernel" % dom, {}).get("dram_bytes_per_launch_at_%d_blocks" % B)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "rans32_%s_kernel" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": dom_ms, "encode_frac": hs["roofline_encode_frac"], "decode_frac": hs["roofline_decode_frac"],
+                "hbm_read_only_frac": hs["hbm_read_only_frac"]}
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------
+    # step = H2D raw -> encode -> pack -> D2H compressed + lengths ; H2D compressed -> decode -> D2H raw
+    params = head["params"]
+    enc, dec = head["enc"], head["dec"]
+    host_in = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
+    host_in.copy_(data)
+    host_out = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
+    packed0 = head["e"].pack()
+    host_c = torch.empty(packed0.buf.numel(), dtype=torch.uint8, pin_memory=True)
+    host_len = torch.empty(B, dtype=torch.int64, pin_memory=True)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        dd = host_in.to(dev, non_blocking=True)
+        e = enc.encode_blocks(dd, reuse=head["e"])
+        p = e.pack()
+        host_c[: p.buf.numel()].copy_(p.buf, non_blocking=True)
+        host_len.copy_(e.bit_len, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the encoded result is now on the host
+        # decode side: compressed stream from host memory
+        lens = host_len.to(dev, non_blocking=True)
+        nbytes = (lens + 7) // 8
+        offs = (torch.cumsum(nbytes, 0) - nbytes) * 8
+        cbuf = host_c[: p.buf.numel()].to(dev, non_blocking=True)
+        d = dec.decode_blocks(EncodedBlocks(cbuf, offs, lens, e.status, 0), N, reuse=head["d"])
+        host_out.copy_(d.symbols[:, :N], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h2d = host_in.numel() + lens.numel() * 8 + cbuf.numel()
+        d2h = p.buf.numel() + lens.numel() * 8 + host_out.numel()
+
+    e2e_step()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    assert torch.equal(host_out, host_in), "e2e round trip failed"
+    tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * B * N * e2e_steps / (tt.item() * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "note": "pinned host buffers; PCIe copies of raw and packed streams inside the timed region, per GPU"}
+
+    # total compressed size of the global stream (all-gather of 8 x u64)
+    sizes, my_off = gather_compressed_sizes(head["C"])
+
+    also = {}
+    for k, r in others.items():
+        also[k] = summarize(r, world)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # BASELINE configs[1] (65 536 blocks x 4 KiB on one GPU) in the same run
+        for k in VARIANTS:
+            r = bench_variant(k, data[:65536], max(5, args.steps // 2), 3)
+            also["cfg2_65536_blocks_" + k] = summarize(r, 1)
+        from oracle import scl_oracle as so
+
+        so.build()
+        threads = so.max_threads()
+        nb = min(B, 1024 * threads)
+        cpu = cpu_baseline(fl, VARIANTS[HEADLINE], data[:nb].cpu().numpy(), threads, HEADLINE)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": hs["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": hs["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {
+                "workload": "rANS encode+decode, %d blocks x %d B Zipf-1.0 bytes per GPU (x%d GPUs = %.2f GiB; N=8 is BASELINE configs[4]), "
+                            "256-symbol static Frequencies (M=4096), reference-default rANSParams (NUM_BITS_OUT=1, RANGE_FACTOR=2^16)" % (B, N, world, world * B * N / 2**30),
+                "params": HEADLINE, "blocks_per_gpu": B, "block_len": N, "parallelism": "block-range sharding, %d rank(s), no payload collective" % world,
+                "l2": "inputs (1 GiB raw, ~0.8 GiB coded per GPU) exceed the 126 MB L2; no explicit flush",
+            },
+            "encode_MBps": hs["encode_MBps"], "decode_MBps": hs["decode_MBps"], "bits_per_symbol": hs["bits_per_symbol"],
+            "kernel_paths": hs["kernel_paths"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps,
+            "clocks": head["clocks"], "also": also, "global_compressed_bytes": int(sum(sizes)),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

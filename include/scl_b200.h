@@ -98,7 +98,7 @@ int scl_coder_create(const scl_params *params, const uint8_t *alphabet, const ui
 void scl_coder_destroy(scl_coder *c);
 
 /* Worst-case encoded size in BYTES of one block of `block_len` symbols, rounded up to the
- * slot alignment (16).  Use it as out_stride. */
+ * sector size (32).  Use it as out_stride. */
 uint64_t scl_coder_max_encoded_bytes(const scl_coder *c, uint64_t block_len);
 
 /* Which kernel family the handle selected: 0 = 32-bit-state fast path, 1 = generic 64-bit. */
@@ -152,6 +152,10 @@ int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, con
 /* ---- introspection (tests pin the tANS tables against tANS.py:285-337) -------------------- */
 int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries,
                             void *stream);
+
+/* Test hook: route the 32-bit rANS fast path to the first-generation kernels (per-lane direct
+ * global access) instead of the TMA/ring kernels, so both generations stay parity-tested. */
+void scl_debug_force_v1(int on);
 
 const char *scl_last_cuda_error(void);
 const char *scl_version(void);

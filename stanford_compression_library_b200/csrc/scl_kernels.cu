@@ -10,7 +10,11 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder entry point is fetched at run time)
+
+#include "scl_fast.cuh"
 #include "scl_lane.cuh"
 #include "scl_tables.hpp"
 
@@ -168,6 +172,139 @@ __global__ void __launch_bounds__(kThreads) rans64_decode_kernel(const RansGener
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rANS fast path, second generation (scl_fast.cuh).  Persistent kernels: one CTA per SM, `W`
+// warps per CTA (host-chosen so that tasks / (SMs * W) is just below an integer: the work is
+// one sequential chain per block, so rounds cannot be split and a partial last round idles SMs).
+// A task = 32 consecutive blocks = one warp.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kTileCols = 64;                  // bytes of each block's row per TMA tile
+constexpr uint32_t kTileBytes = 32 * kTileCols;     // 32 rows (one per lane)
+constexpr uint32_t kTileStages = 2;
+constexpr uint32_t kEncWarpSmem = kTileStages * kTileBytes + kEncRingWords * 128;  // tiles + ring, per warp
+constexpr uint32_t kEncTabBytes = 256 * kEncTabCopies * sizeof(RansEnc32);         // 32 KiB
+constexpr uint32_t kDecWarpSmem = (kDecRingWords + 1) * 128;                       // ring + wrap duplicate
+constexpr uint32_t kMaxWarps = 28;
+
+__device__ __forceinline__ void tma_tile_2d(void *smem_dst, const CUtensorMap *tmap, int32_t c0, int32_t c1, uint64_t *mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(mbar))
+        : "memory");
+}
+
+// smem layout: [tiles+rings per warp ...][table 32 KiB][mbarriers]
+template <uint32_t NBO, bool CHECK>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+    rans32_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const RansEnc32 *__restrict__ g_tab8, RansConst c, BlockIo io,
+                            uint32_t n_tasks) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
+    uint32_t *ring = (uint32_t *)(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane;
+    const RansEnc32 *s_tab = (const RansEnc32 *)(smem + W * kEncWarpSmem);
+    uint64_t *mbars = (uint64_t *)(smem + W * kEncWarpSmem + kEncTabBytes);
+    uint64_t *tab_bar = mbars + W * kTileStages;
+    uint64_t *my_bar = mbars + warp * kTileStages;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(tab_bar)) : "memory");
+        for (uint32_t i = 0; i < W * kTileStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_expect(tab_bar, kEncTabBytes);
+        tma_bulk_g2s((void *)s_tab, g_tab8, kEncTabBytes, tab_bar);
+    }
+    mbar_wait(tab_bar, 0);
+
+    const RansEnc32 *my_tab = s_tab + (lane & (kEncTabCopies - 1));  // this lane's bank-rotated replica
+    const uint32_t n = io.block_len;
+    const uint32_t n_tiles = (n + kTileCols - 1) / kTileCols;
+    const uint32_t total_warps = gridDim.x * W;
+    uint32_t tile_seq = 0;  // tiles consumed by this warp so far (selects stage and mbarrier parity)
+    const uint32_t swz = (lane >> 1) & 3;
+
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+        const uint64_t b = (uint64_t)task * 32 + lane;
+        const bool active = b < io.n_blocks;
+        if (lane == 0) {
+            for (uint32_t t = 0; t < kTileStages && t < n_tiles; ++t) {
+                uint32_t st = (tile_seq + t) % kTileStages;
+                tma_expect(my_bar + st, kTileBytes);
+                tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)(t * kTileCols), (int32_t)(task * 32), my_bar + st);
+            }
+        }
+        EncLaneV2 L;
+        uint8_t *slot = io.out + (active ? b : 0) * io.out_stride;
+        L.init((uint32_t)c.L, ring, slot, slot + io.out_stride);
+        for (uint32_t t = 0; t < n_tiles; ++t, ++tile_seq) {
+            const uint32_t st = tile_seq % kTileStages;
+            mbar_wait(my_bar + st, (tile_seq / kTileStages) & 1);
+            const uint8_t *row = tiles + st * kTileBytes + lane * kTileCols;
+            const uint32_t left = n - t * kTileCols;
+#pragma unroll 1
+            for (uint32_t ch = 0; ch < kTileCols / 16; ++ch) {
+                if (ch * 16 >= left) break;
+                const uint32_t cnt = left - ch * 16 >= 16 ? 16u : left - ch * 16;
+                const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));  // 64-byte TMA swizzle: conflict-free LDS.128
+                if (active) {
+                    u32x4 v = {q.x, q.y, q.z, q.w};
+                    enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies, v, cnt);
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && t + kTileStages < n_tiles) {
+                tma_expect(my_bar + st, kTileBytes);
+                tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)((t + kTileStages) * kTileCols), (int32_t)(task * 32), my_bar + st);
+            }
+        }
+        if (active) {
+            L.put(L.x, c.NSB);  // header in front of the payload (rANS.py:199,206-208)
+            uint32_t st = SCL_ST_OK;
+            if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
+            L.put64((uint64_t)n, c.DBSB);
+            uint64_t bits = L.finish();
+            if (L.bad) st = SCL_ST_BAD_SYMBOL;
+            if (L.ovf) st = SCL_ST_OVERFLOW;
+            io.bit_len[b] = bits;
+            io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+            io.status[b] = st;
+        }
+        __syncwarp();
+    }
+}
+
+template <uint32_t NBO>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+    rans32_decode_v2_kernel(const RansDec32 *__restrict__ g_lut, uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *ring = (uint32_t *)(smem + warp * kDecWarpSmem) + lane;
+    const RansDec32 *s_lut = (const RansDec32 *)(smem + W * kDecWarpSmem);
+    stage_table((void *)s_lut, g_lut, lut_bytes, &mbar);
+    const uint32_t total_warps = gridDim.x * W;
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+        const uint64_t b = (uint64_t)task * 32 + lane;
+        if (b < io.n_blocks) {
+            DecLaneV2 D;
+            const uint64_t off = io.bit_off[b];
+            D.init(io.in, io.in_bytes, off, ring);
+            uint32_t size = 0;
+            uint64_t used = 0;
+            uint32_t st = rans32_decode_lane_v2<NBO>(D, s_lut, c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+            if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+            io.sizes[b] = size;
+            io.consumed[b] = used;
+            io.status[b] = st;
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,6 +559,9 @@ struct scl_coder {
     AecHost *aec = nullptr;
     // device tables
     RansEnc32 *d_enc32 = nullptr;
+    RansEnc32 *d_enc32x8 = nullptr;  // [256][kEncTabCopies] bank-rotated replicas for the v2 encoder
+    int n_sm = 0;
+    bool v2_ok = false;              // parameter set eligible for the second-generation kernels
     RansDec32 *d_dec32 = nullptr;
     uint32_t dec32_bytes = 0;
     RansGeneric *d_gen = nullptr;
@@ -461,6 +601,7 @@ static const uint32_t kTansSmemTableMax = 160 * 1024;
 extern "C" void scl_coder_destroy(scl_coder *c) {
     if (!c) return;
     cudaFree(c->d_enc32);
+    cudaFree(c->d_enc32x8);
     cudaFree(c->d_dec32);
     cudaFree(c->d_gen);
     cudaFree(c->d_tsym);
@@ -491,6 +632,22 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         RansHost &r = *c->rans;
         rc = upload(&c->d_gen, &r.gen, sizeof(RansGeneric), sizeof(RansGeneric), s);
         if (!rc && r.enc32) rc = upload(&c->d_enc32, r.enc_tab.data(), sizeof(RansEnc32) * 256, sizeof(RansEnc32) * 256, s);
+        if (!rc && r.enc32) {
+            std::vector<RansEnc32> rep(256 * kEncTabCopies);
+            for (uint32_t sy = 0; sy < 256; ++sy)
+                for (uint32_t j = 0; j < kEncTabCopies; ++j) rep[sy * kEncTabCopies + j] = r.enc_tab[sy];
+            rc = upload(&c->d_enc32x8, rep.data(), rep.size() * sizeof(RansEnc32), rep.size() * sizeof(RansEnc32), s);
+            if (!rc) {
+                cudaError_t e = cudaStreamSynchronize(s);  // `rep` dies here
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+            }
+        }
+        if (!rc) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev);
+            c->v2_ok = r.max_bits_per_symbol <= kFastMaxBitsPerSym && (r.c.NBO == 1 || r.c.NBO == 8) && c->n_sm > 0;
+        }
         if (!rc && r.dec32) {
             c->dec32_bytes = (uint32_t)round16(r.dec_lut.size() * sizeof(RansDec32));
             rc = upload(&c->d_dec32, r.dec_lut.data(), r.dec_lut.size() * sizeof(RansDec32), c->dec32_bytes, s);
@@ -559,7 +716,7 @@ extern "C" uint64_t scl_coder_max_encoded_bytes(const scl_coder *c, uint64_t blo
     if (c->range) bits = c->range->max_encoded_bits(block_len);
     if (c->aec) bits = c->aec->max_encoded_bits(block_len);
     uint64_t bytes = (bits + 7) / 8 + 4;  // + one spare word: the last partial word is written whole
-    return (bytes + 15) & ~15ull;
+    return (bytes + 31) & ~31ull;         // whole 32-byte sectors (the v2 encoder drains sector-wise)
 }
 
 extern "C" int scl_coder_path(const scl_coder *c, int decode) {
@@ -571,6 +728,89 @@ static int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, what);
     return SCL_E_OK;
+}
+
+// ---- v2 launch helpers ---------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// Warps per CTA for a persistent one-CTA-per-SM launch: every warp runs ceil(tasks / (SMs*W))
+// whole tasks, so pick the W that wastes the least of the last round (ties: more warps).
+static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *grid, uint32_t *warps) {
+    if (n_tasks <= (uint32_t)n_sm * 8) {  // tiny batch: spread tasks over SMs, few warps each
+        uint32_t w = (n_tasks + n_sm - 1) / n_sm;
+        *warps = w ? w : 1;
+        *grid = (n_tasks + *warps - 1) / *warps;
+        return;
+    }
+    double best = -1;
+    uint32_t bw = max_w;
+    for (uint32_t w = 8; w <= max_w; ++w) {
+        uint64_t slots = (uint64_t)n_sm * w;
+        uint64_t rounds = (n_tasks + slots - 1) / slots;
+        double eff = (double)n_tasks / (double)(slots * rounds);
+        if (eff >= best - 1e-9) {
+            best = eff;
+            bw = w;
+        }
+    }
+    *warps = bw;
+    *grid = (uint32_t)n_sm;
+}
+
+static bool g_force_v1 = false;  // test hook: scl_debug_force_v1(1) routes the fast path to the first-generation kernels
+extern "C" void scl_debug_force_v1(int on) { g_force_v1 = on != 0; }
+
+template <uint32_t NBO>
+static int launch_encode_v2(const scl_coder *c, const BlockIo &io, cudaStream_t s) {
+    const RansHost &r = *c->rans;
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return -1;
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {io.block_len, io.n_blocks};
+    cuuint64_t gstr[1] = {io.sym_stride};
+    cuuint32_t box[2] = {kTileCols, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -1;
+    uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
+    pick_launch(n_tasks, c->n_sm, kMaxWarps, &grid, &warps);
+    size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + (warps * kTileStages + 1) * sizeof(uint64_t);
+    cudaError_t e;
+    if (r.c.check_sym) {
+        e = cudaFuncSetAttribute(rans32_encode_v2_kernel<NBO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        rans32_encode_v2_kernel<NBO, true><<<grid, warps * 32, smem, s>>>(tmap, c->d_enc32x8, r.c, io, n_tasks);
+    } else {
+        e = cudaFuncSetAttribute(rans32_encode_v2_kernel<NBO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        rans32_encode_v2_kernel<NBO, false><<<grid, warps * 32, smem, s>>>(tmap, c->d_enc32x8, r.c, io, n_tasks);
+    }
+    return check_launch("rans32_encode_v2_kernel");
+}
+
+template <uint32_t NBO>
+static int launch_decode_v2(const scl_coder *c, const DecodeIo &io, cudaStream_t s) {
+    const RansHost &r = *c->rans;
+    uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
+    pick_launch(n_tasks, c->n_sm, kMaxWarps, &grid, &warps);
+    size_t smem = (size_t)warps * kDecWarpSmem + c->dec32_bytes;
+    cudaError_t e = cudaFuncSetAttribute(rans32_decode_v2_kernel<NBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    rans32_decode_v2_kernel<NBO><<<grid, warps * 32, smem, s>>>(c->d_dec32, c->dec32_bytes, r.c, io, n_tasks);
+    return check_launch("rans32_decode_v2_kernel");
 }
 
 extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
@@ -585,6 +825,13 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     uint32_t grid = (uint32_t)((n_blocks + kThreads - 1) / kThreads);
     if (c->rans) {
         const RansHost &r = *c->rans;
+        // second-generation kernel: uniform block length, TMA-compatible input, sector-aligned output
+        if (r.enc32 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 &&
+            (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
+            (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
+            int rc2 = r.c.NBO == 1 ? launch_encode_v2<1>(c, io, s) : launch_encode_v2<8>(c, io, s);
+            if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
+        }
         if (r.enc32) {
             if (r.c.check_sym)
                 rans32_encode_kernel<true><<<grid, kThreads, 0, s>>>(c->d_enc32, r.c, io);
@@ -629,6 +876,9 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     uint32_t grid = (uint32_t)((n_blocks + kThreads - 1) / kThreads);
     if (c->rans) {
         const RansHost &r = *c->rans;
+        if (r.dec32 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+            n_blocks < (1ull << 36))
+            return r.c.NBO == 1 ? launch_decode_v2<1>(c, io, s) : launch_decode_v2<8>(c, io, s);
         if (r.dec32)
             rans32_decode_kernel<<<grid, kThreads, c->dec32_bytes, s>>>(c->d_dec32, c->dec32_bytes, r.c, io);
         else

@@ -198,8 +198,8 @@ class DeviceCoder:
             out, sizes, used, status = reuse.symbols, reuse.sizes, reuse.bits_consumed, reuse.status
             stride = out.stride(0)
         else:
-            stride = (int(max_block_len) + 15) // 16 * 16 if out is None else out.stride(0)
-            stride = max(stride, 16)
+            stride = (int(max_block_len) + 31) // 32 * 32 if out is None else out.stride(0)
+            stride = max(stride, 32)
             if out is None:
                 out = torch.empty((B, stride), dtype=torch.uint8, device=self.device)
             sizes = torch.empty(B, dtype=torch.int32, device=self.device)

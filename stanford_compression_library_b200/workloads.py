@@ -20,16 +20,22 @@ def zipf_frequencies(n_sym: int = 256, M: int = 4096, s: float = 1.0) -> Frequen
     return Frequencies({b: f for b, f in enumerate(zipf_freq_list(n_sym, M, s))})
 
 
-def sample_blocks(freq_list, n_blocks: int, block_len: int, seed: int, device, chunk_blocks: int = 16384) -> torch.Tensor:
-    """uint8 [n_blocks, block_len] of i.i.d. draws from freq_list by inverse CDF, generated on `device`."""
+def zipf_probabilities(n_sym: int = 256, s: float = 1.0):
+    """The source distribution of the benchmark data: p_b ~ 1/(b+1)^s (not the quantised table)."""
+    p = 1.0 / np.arange(1, n_sym + 1, dtype=np.float64) ** s
+    return (p / p.sum()).tolist()
+
+
+def sample_blocks(weights, n_blocks: int, block_len: int, seed: int, device, chunk_blocks: int = 16384) -> torch.Tensor:
+    """uint8 [n_blocks, block_len] of i.i.d. draws with P(b) ~ weights[b] by inverse CDF, generated on `device`."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    f = torch.tensor(freq_list, dtype=torch.float64, device=device)
+    f = torch.tensor(weights, dtype=torch.float64, device=device)
     cdf = torch.cumsum(f / f.sum(), 0).to(torch.float32)
     cdf[-1] = 2.0  # guard against u == 1.0 rounding
     out = torch.empty((n_blocks, block_len), dtype=torch.uint8, device=device)
     for b0 in range(0, n_blocks, chunk_blocks):
         b1 = min(n_blocks, b0 + chunk_blocks)
         u = torch.rand((b1 - b0, block_len), generator=g, device=device, dtype=torch.float32)
-        out[b0:b1] = torch.searchsorted(cdf, u, right=True).clamp_(max=len(freq_list) - 1).to(torch.uint8)
+        out[b0:b1] = torch.searchsorted(cdf, u, right=True).clamp_(max=len(weights) - 1).to(torch.uint8)
     return out

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
 _SO = os.path.join(_HERE, "host_emu", "libscl_emu.so")
 _CSRC = os.path.join(os.path.dirname(_HERE), "stanford_compression_library_b200", "csrc")
-_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("scl_lane.cuh", "scl_defs.h", "scl_tables.hpp")]
+_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("scl_lane.cuh", "scl_fast.cuh", "scl_defs.h", "scl_tables.hpp")]
 
 
 def build():
@@ -39,6 +39,9 @@ def lib():
         L.emu_tans_tables.argtypes = [vp, vp, vp, u64]
         L.emu_encode_blocks.argtypes = [vp, vp, u64, vp, u32, u64, vp, u64, vp, vp, vp, vp]
         L.emu_decode_blocks.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, vp]
+        L.emu_v2_eligible.argtypes = [vp]
+        L.emu_encode_blocks_v2.argtypes = [vp, vp, u64, u32, u64, vp, u64, vp, vp, vp]
+        L.emu_decode_blocks_v2.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -47,7 +50,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def aligned_zeros(n, dtype=np.uint8, align=16):
+def aligned_zeros(n, dtype=np.uint8, align=32):
     raw = np.zeros(n * np.dtype(dtype).itemsize + align, dtype=np.uint8)
     off = (-raw.ctypes.data) % align
     return raw[off : off + n * np.dtype(dtype).itemsize].view(dtype)
@@ -80,6 +83,39 @@ class EmuCoder:
         dec = np.zeros(L, dtype=np.uint32)
         assert lib().emu_tans_tables(self.h, _p(enc), _p(dec), L) == 0
         return enc, dec
+
+    def v2_eligible(self):
+        return bool(lib().emu_v2_eligible(self.h))
+
+    def encode_v2(self, sym2d, out_stride=None):
+        sym2d = np.ascontiguousarray(sym2d, dtype=np.uint8)
+        B, N = sym2d.shape
+        stride_in = max(16, (N + 15) // 16 * 16)
+        symbuf = aligned_zeros(B * stride_in)
+        symbuf.reshape(B, stride_in)[:, :N] = sym2d
+        stride = out_stride or int(lib().emu_max_encoded_bytes(self.h, N))
+        out = aligned_zeros(B * stride + 32)
+        off = np.zeros(B, dtype=np.uint64)
+        ln = np.zeros(B, dtype=np.uint64)
+        st = np.zeros(B, dtype=np.uint32)
+        rc = lib().emu_encode_blocks_v2(self.h, _p(symbuf), stride_in, N, B, _p(out), stride, _p(off), _p(ln), _p(st))
+        assert rc == 0, rc
+        return out, off, ln, st
+
+    def decode_v2(self, buf, bit_off, bit_len, max_len):
+        B = len(bit_off)
+        stride = max(32, (max_len + 31) // 32 * 32)
+        bufa = aligned_zeros(buf.size)
+        bufa[:] = buf
+        sym = aligned_zeros(B * stride).reshape(B, stride)
+        sizes = np.zeros(B, dtype=np.uint32)
+        used = np.zeros(B, dtype=np.uint64)
+        st = np.zeros(B, dtype=np.uint32)
+        bo = np.ascontiguousarray(bit_off, dtype=np.uint64)
+        bl = None if bit_len is None else np.ascontiguousarray(bit_len, dtype=np.uint64)
+        rc = lib().emu_decode_blocks_v2(self.h, _p(bufa), bufa.size, _p(bo), _p(bl), B, _p(sym), stride, _p(sizes), _p(used), _p(st))
+        assert rc == 0, rc
+        return sym, sizes, used, st
 
     def encode(self, sym2d, sizes=None, model=None, out_stride=None):
         sym2d = np.ascontiguousarray(sym2d, dtype=np.uint8)

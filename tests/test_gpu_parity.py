@@ -271,16 +271,16 @@ def test_rans_full_size_roundtrip_cfg2(kw):
     consumed == bits produced for every block, end state accepted, compressed size close to the
     table's cross-entropy; plus a strided sample of blocks bit-compared with the oracle."""
     from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
-    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
 
     fl = zipf_freq_list()
     params = rANSParams(zipf_frequencies(), **kw)
     B, N = 65536, 4096
-    data = sample_blocks(fl, B, N, seed=6, device="cuda:0")
+    data = sample_blocks(zipf_probabilities(), B, N, seed=6, device="cuda:0")  # true Zipf-1.0 source (SURVEY 8d)
     enc, dec = rANSEncoder(params), rANSDecoder(params)
     e, d = _compare_batch_with_oracle(enc, dec, so.Oracle.rans(fl, **kw), data, sample=range(0, B, 2048))
-    p = np.array(fl) / 4096.0
-    xent = float(-(p * np.log2(p)).sum())  # data drawn from the table itself
+    q = np.array(fl) / 4096.0
+    xent = float(-(np.array(zipf_probabilities()) * np.log2(q)).sum())  # 6.2296 bits/symbol
     bits_per_sym = float(e.bit_len.sum()) / (B * N)
     assert abs(bits_per_sym - xent) < 0.05, (bits_per_sym, xent)
 
@@ -309,3 +309,45 @@ def test_try_lossless_compression_harness_with_trailing_bits():
         block = get_random_data_block(freq.get_prob_dist(), 10000, seed=0)
         ok, nbits, _ = try_lossless_compression(block, rANSEncoder(params), rANSDecoder(params), add_extra_bits_to_encoder_output=True)
         assert ok
+
+
+@pytest.mark.parametrize("kw", [{}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)], ids=["default", "nbo8_rf12"])
+@pytest.mark.parametrize("shape", [(33, 64), (1000, 100), (4097, 4096), (96, 8200)], ids=lambda s: "%dx%d" % s)
+def test_rans_kernel_generations_agree(kw, shape):
+    """The TMA/ring kernels (v2, default for uniform batches) and the first-generation kernels must
+    produce identical streams and decode each other's output, for block counts that are not a
+    multiple of 32 and block lengths that are not a multiple of the 64-byte tile."""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    B, N = shape
+    params = rANSParams(zipf_frequencies(), **kw)
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=11, device="cuda:0")
+    data[0, :] = 255  # rarest symbol: worst-case bits per symbol
+    lib = _cabi.lib()
+    try:
+        lib.scl_debug_force_v1(1)
+        e1 = enc.encode_blocks(data).check()
+        p1 = e1.pack()
+        lib.scl_debug_force_v1(0)
+        e2 = enc.encode_blocks(data).check()
+        p2 = e2.pack()
+        assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
+        assert torch.equal(p1.buf, p2.buf)
+        d2 = dec.decode_blocks(e1, N).check()  # v2 decoder on v1 output
+        lib.scl_debug_force_v1(1)
+        d1 = dec.decode_blocks(e2, N).check()  # v1 decoder on v2 output
+    finally:
+        lib.scl_debug_force_v1(0)
+    for d in (d1, d2):
+        assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
+        assert int(d.sizes.min()) == N == int(d.sizes.max())
+    # and both against the oracle on a few blocks
+    oracle = so.Oracle.rans(zipf_freq_list(), **kw)
+    host = data.cpu().numpy()
+    for b in (0, 1, B - 1):
+        ref_bytes, ref_bits = oracle.encode_block(host[b])
+        got = e2.block(b)
+        assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()

@@ -205,3 +205,51 @@ def test_emu_status_words():
                      model=0, max_allowed_total_freq=0)
     out, off, ln, st = EmuCoder(prm2, None, freqs).encode(sym)
     assert st[0] == _cabi.ST_OVERFLOW
+
+
+# ---- second-generation lane structs (csrc/scl_fast.cuh: funnel-shift packing, sector ring I/O) ----
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "rans"], ids=case_id)
+def test_emu_v2_matches_golden(c):
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    if not coder.v2_eligible():
+        pytest.skip("parameter set not eligible for the v2 fast path")
+    n = c["n"]
+    out, off, ln, st = coder.encode_v2(c["data"].reshape(1, -1))
+    assert st[0] == 0 and int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    for lead in (0, 5, 250, 261):
+        bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
+        buf = np.concatenate([np.packbits(bits), np.zeros(7, dtype=np.uint8)])
+        sym, sizes, used, st = coder.decode_v2(buf, [lead], [total], max(n, 1))
+        assert st[0] == 0 and int(sizes[0]) == n and int(used[0]) == c["consumed"]
+        assert sym[0, :n].tolist() == c["data"].tolist()
+
+
+@pytest.mark.parametrize("kw", [dict(nbo=1, rf=1 << 16), dict(nbo=8, rf=1 << 12), dict(nbo=1, rf=1 << 4)], ids=["default", "nbo8_rf12", "nbo1_rf4"])
+def test_emu_v2_vs_oracle_zipf_lengths(kw):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+    from stanford_compression_library_b200.workloads import zipf_freq_list, zipf_probabilities
+
+    fl = zipf_freq_list()
+    rng = np.random.default_rng(3)
+    nsb = so.ref_get_bit_width(kw["rf"] * 4096 * (1 << kw["nbo"]) - 1)
+    prm = SclParams(coder=_cabi.CODER_RANS, data_block_size_bits=32, num_bits_out=kw["nbo"], range_factor=kw["rf"], num_state_bits=nsb,
+                    precision=0, model=0, max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, fl)
+    assert coder.v2_eligible()
+    oracle = so.Oracle.rans(fl, NUM_BITS_OUT=kw["nbo"], RANGE_FACTOR=kw["rf"])
+    for N in (0, 1, 15, 16, 17, 31, 32, 33, 64, 100, 511, 1024, 4096):
+        sym = rng.choice(256, size=(5, N), p=np.array(zipf_probabilities())).astype(np.uint8)
+        if N:
+            sym[0, :] = 255  # rarest symbol everywhere: the most bits per symbol the table can produce
+        out, off, ln, st = coder.encode_v2(sym)
+        assert (st == 0).all()
+        for b in range(5):
+            enc, nb = oracle.encode_block(sym[b])
+            assert nb == ln[b], (N, b)
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (N, b)
+        dsym, dsz, used, st = coder.decode_v2(out, off, ln, max(N, 1))
+        assert (st == 0).all() and (dsz == N).all() and (used == ln).all()
+        assert (dsym[:, :N] == sym).all()
