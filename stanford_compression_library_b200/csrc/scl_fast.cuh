@@ -44,6 +44,73 @@ SCL_HD uint32_t shr_fma(uint32_t x, uint32_t s) {
 #endif
 }
 
+
+// ---- shared-memory access through plain addresses --------------------------------------------
+// On the device `saddr_t` is a 32-bit shared-window address and every access is ONE explicit
+// ld/st.shared of the stated width (the compiler otherwise splits a 16-byte entry read into
+// LDS.128 + 2x LDS.32, and the extra scalar loads are 4-way bank conflicted: profiles/r1b).
+// On the host it is an ordinary pointer value.
+#ifdef __CUDA_ARCH__
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32x4 lds128(saddr_t a) {
+    u32x4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds32(saddr_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+#else
+typedef uintptr_t saddr_t;
+inline saddr_t saddr_of(const void *p) { return (uintptr_t)p; }
+inline u32x4 lds128(saddr_t a) { return *(const u32x4 *)a; }
+inline uint32_t lds32(saddr_t a) { return *(const uint32_t *)a; }
+inline void sts32(saddr_t a, uint32_t v) { *(uint32_t *)a = v; }
+#endif
+
+// byte `b` of w, zero-extended: one PRMT
+SCL_HD uint32_t byte_of(uint32_t w, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(w, 0, 0x4440u + b);
+#else
+    return (w >> (8 * b)) & 0xFFu;
+#endif
+}
+// a*b + c on the FMA pipe (IMAD)
+SCL_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a * b + c;
+#endif
+}
+// umulhi(x, m): with m = 2^(32-s) this is x >> s on the FMA pipe (IMAD.HI) instead of the ALU pipe
+SCL_HD uint32_t mulhi_fma(uint32_t x, uint32_t m) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(m));
+    return r;
+#else
+    return (uint32_t)(((uint64_t)x * m) >> 32);
+#endif
+}
+// replace byte `pos` of acc with byte 0 of e: one PRMT
+template <int POS>
+SCL_HD uint32_t put_byte(uint32_t acc, uint32_t e) {
+#ifdef __CUDA_ARCH__
+    constexpr uint32_t sel = POS == 0 ? 0x3214u : POS == 1 ? 0x3240u : POS == 2 ? 0x3410u : 0x4210u;
+    return __byte_perm(acc, e, sel);
+#else
+    return (acc & ~(0xFFu << (8 * POS))) | ((e & 0xFFu) << (8 * POS));
+#endif
+}
+
 struct u32x8 {
     uint32_t v[8];
 };
@@ -82,13 +149,13 @@ struct EncLaneV2 {
     uint32_t room;     // 64 - valid bits
     uint32_t wofs;     // words spilled so far * 128 (byte offset into the [word][lane] ring, unwrapped)
     uint32_t rofs;     // words drained so far * 128
-    uint32_t *ring;    // this lane's column of the ring: word i at ring[(i % kEncRingWords) * 32]
+    saddr_t ring;      // this lane's column of the ring: word i at ring + (i % kEncRingWords) * 128
     uint8_t *gend;     // slot end (32-byte aligned); drained word i lives at gend - 4*(i+1)
     uint8_t *gbegin;   // slot begin
     uint32_t ovf;
     uint32_t bad;
 
-    SCL_HD void init(uint32_t L, uint32_t *ring_, uint8_t *slot_begin, uint8_t *slot_end) {
+    SCL_HD void init(uint32_t L, saddr_t ring_, uint8_t *slot_begin, uint8_t *slot_end) {
         x = L;
         lo = hi = 0;
         room = 64;
@@ -98,21 +165,23 @@ struct EncLaneV2 {
         gbegin = slot_begin;
         ovf = bad = 0;
     }
+    SCL_HD saddr_t ring_slot(uint32_t ofs) const { return ring + (ofs & ((kEncRingWords - 1) * 128)); }
 
-    // one symbol: shrink_state + rans_base_encode_step (rANS.py:138-161), see scl_lane.cuh
+    // one symbol: shrink_state + rans_base_encode_step (rANS.py:138-161), see scl_lane.cuh.
+    // e = {thresh_m1, rcp, bias, cmpl << 16 | nb0 << 8 | shift}
     template <uint32_t NBO, bool CHECK>
-    SCL_HD void step(const RansEnc32 &e) {
-        if (CHECK && e.pack == kRansEncInvalid) {
+    SCL_HD void step(const u32x4 &e) {
+        if (CHECK && e.w == kRansEncInvalid) {
             bad = 1;
             return;
         }
-        uint32_t k = ((e.pack >> 8) & 0xFFu) + (x > e.thresh_m1 ? NBO : 0u);
+        uint32_t k = byte_of(e.w, 1) + (x > e.x ? NBO : 0u);
         lo = funnel_r(lo, hi, k);  // k <= 16 < 32
         hi = funnel_r(hi, x, k);
         room -= k;
         x >>= k;
-        uint32_t q = funnel_r(umulhi32(x, e.rcp), 0u, e.pack);
-        x = x + e.bias + q * (e.pack >> 16);
+        uint32_t q = funnel_r(umulhi32(x, e.y), 0u, e.w);  // >> (shift = e.w & 31)
+        x = mad32(q, mulhi_fma(e.w, 1u << 16), x + e.z);   // x + bias + q * cmpl
     }
 
     // after at most 2 symbols (<= 32 new bits): move one whole word to the ring if there is one
@@ -120,7 +189,7 @@ struct EncLaneV2 {
         bool full = room <= 32;
         uint32_t w = funnel_rc(lo, hi, room);  // oldest 32 bits when full
         if (full) {
-            ring[((wofs >> 7) & (kEncRingWords - 1)) * kRingStrideWords] = w;
+            sts32(ring_slot(wofs), w);
             wofs += 128;
             room += 32;
         }
@@ -130,11 +199,10 @@ struct EncLaneV2 {
     SCL_HD void drain_check() {
         if (wofs - rofs >= 8 * 128) {
             u32x8 s;
-            uint32_t base = rofs >> 7;
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j)  // word base+7-j goes to the lowest address first
-                s.v[j] = bswap32(ring[((base + 7 - j) & (kEncRingWords - 1)) * kRingStrideWords]);
-            uint8_t *dst = gend - 4 * (base + 8);
+                s.v[j] = bswap32(lds32(ring_slot(rofs + (7 - j) * 128)));
+            uint8_t *dst = gend - ((rofs >> 5) + 32);  // 4 * (words_drained + 8)
             if (dst >= gbegin)
                 st_sector32(dst, s);
             else
@@ -173,7 +241,7 @@ struct EncLaneV2 {
         for (uint32_t i = rofs >> 7; i < (uint32_t)words; ++i) {
             uint8_t *dst = gend - 4 * ((uint64_t)i + 1);
             if (dst >= gbegin)
-                st_word(dst, bswap32(ring[(i & (kEncRingWords - 1)) * kRingStrideWords]));
+                st_word(dst, bswap32(lds32(ring_slot(i * 128))));
             else
                 ovf = 1;
         }
@@ -189,23 +257,25 @@ struct EncLaneV2 {
     }
 };
 
-// Encode `cnt` (<= 16) symbols held in a 16-byte chunk.  The full-chunk path is fully unrolled
-// with the spill check after every second symbol.
+// Encode `cnt` (<= 16) symbols held in a 16-byte chunk.  `tab` = address of this lane's replica
+// of entry 0; entry s is `sym_stride` bytes further per symbol (128 on the device: 8 replicas of
+// 16 bytes, so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups).
+// The full-chunk path is fully unrolled with the spill check after every second symbol.
 template <uint32_t NBO, bool CHECK>
-SCL_HD void enc_chunk(EncLaneV2 &L, const RansEnc32 *tab, uint32_t tab_stride, const u32x4 &v, uint32_t cnt) {
+SCL_HD void enc_chunk(EncLaneV2 &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v, uint32_t cnt) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     if (cnt == 16) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                L.template step<NBO, CHECK>(tab[((wd[j] >> (8 * b)) & 0xFFu) * tab_stride]);
+                L.template step<NBO, CHECK>(lds128(tab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)));
                 if (b & 1) L.spill_check();
             }
         }
     } else {
         for (uint32_t i = 0; i < cnt; ++i) {
-            L.template step<NBO, CHECK>(tab[((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * tab_stride]);
+            L.template step<NBO, CHECK>(lds128(tab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)));
             L.spill_check();
         }
     }
@@ -222,7 +292,7 @@ struct DecLaneV2 {
     uint32_t x;
     uint32_t bp;       // bit position of the next unread bit
     uint32_t filled;   // bits stored in the ring so far (multiple of 256)
-    uint32_t *ring;    // word i at ring[(i % 32) * 32]; slot 32 duplicates slot 0 (wrap-free lookahead)
+    saddr_t ring;      // word i at ring + (i % 32) * 128; slot 32 duplicates slot 0 (wrap-free lookahead)
     const uint8_t *base;
     uint64_t in_bytes;
     uint64_t next_off;  // byte offset of the next sector to fetch
@@ -244,13 +314,13 @@ struct DecLaneV2 {
         return a;
     }
     SCL_HD void store_sector(const u32x8 &a) {
-        uint32_t w0 = (filled >> 5) & (kDecRingWords - 1);
+        uint32_t o = (filled << 2) & ((kDecRingWords - 1) * 128);  // (filled / 32 mod 32) * 128
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) ring[(w0 + j) * kRingStrideWords] = bswap32(a.v[j]);
-        if (w0 == 0) ring[kDecRingWords * kRingStrideWords] = bswap32(a.v[0]);
+        for (uint32_t j = 0; j < 8; ++j) sts32(ring + o + j * 128, bswap32(a.v[j]));
+        if (o == 0) sts32(ring + kDecRingWords * 128, bswap32(a.v[0]));
         filled += 256;
     }
-    SCL_HD void init(const uint8_t *base_, uint64_t in_bytes_, uint64_t bit_off, uint32_t *ring_) {
+    SCL_HD void init(const uint8_t *base_, uint64_t in_bytes_, uint64_t bit_off, saddr_t ring_) {
         base = base_;
         in_bytes = in_bytes_;
         ring = ring_;
@@ -267,8 +337,8 @@ struct DecLaneV2 {
     }
     // top 32 unread bits
     SCL_HD uint32_t peek32() const {
-        uint32_t wi = (bp >> 5) & (kDecRingWords - 1);
-        uint32_t w0 = ring[wi * kRingStrideWords], w1 = ring[(wi + 1) * kRingStrideWords];
+        saddr_t a = ring + ((bp << 2) & ((kDecRingWords - 1) * 128));
+        uint32_t w0 = lds32(a), w1 = lds32(a + 128);
         return funnel_l(w1, w0, bp);
     }
     SCL_HD uint32_t get(uint32_t k) {  // slow path (header fields), k <= 32
@@ -298,32 +368,56 @@ struct DecLaneV2 {
     }
 };
 
-// two symbols from one 32-bit peek (k1 + k2 <= 32 is guaranteed by kFastMaxBitsPerSym)
-#define SCL_DEC2_STEP(SYM)                                     \
-    {                                                          \
-        uint32_t e = lut[x & mmask];                           \
-        x = (e >> 20) * (x >> mlog) + ((e >> 8) & 0xFFFu);     \
-        SYM = e & 0xFFu;                                       \
-        uint32_t k = rans32_renorm_bits(x, llog, NBO);         \
-        x = funnel_l(bits, x, k);                              \
-        bits <<= k;                                            \
-        D.bp += k;                                             \
+// loop-invariant decode constants, precomputed so the inner loop is shifts-by-multiply on the FMA pipe
+struct DecConst {
+    saddr_t lut;      // address of LUT entry 0
+    uint32_t m4;      // (M - 1) * 4
+    uint32_t xq_mul;  // 2^(32 - log2 M): umulhi(x, xq_mul) = x >> log2 M
+    uint32_t kbase;   // clz(x) - kbase = bits missing to reach L   (kbase = 31 - log2 L)
+    uint32_t nbo;
+};
+
+// One decode step (rans_base_decode_step + expand_state, rANS.py:234-260) on lut entry
+// e = f << 20 | bias << 8 | byte.  k1 + k2 <= 32 for a pair is guaranteed by kFastMaxBitsPerSym.
+template <uint32_t NBO, int POS>
+SCL_HD void dec_step(const DecConst &c, uint32_t &x, uint32_t &bits, uint32_t &ksum, uint32_t &acc) {
+    uint32_t e = lds32(c.lut + (saddr_t)((x << 2) & c.m4));
+    uint32_t xq = mulhi_fma(x, c.xq_mul);
+    uint32_t f = mulhi_fma(e, 1u << 12);  // e >> 20
+    uint32_t bias = (e >> 8) & 0xFFFu;
+    x = mad32(f, xq, bias);
+    acc = put_byte<POS>(acc, e);
+    uint32_t d = clz32(x) - c.kbase;      // d >= 0 for NBO == 1 (x < 2^(l+1))
+    uint32_t k;
+    if (NBO == 1) {
+        k = d;
+    } else {
+        int32_t ds = (int32_t)d;
+        k = ds <= 0 ? 0u : (((uint32_t)ds + NBO - 1) / NBO) * NBO;
     }
+    x = funnel_l(bits, x, k);
+    bits <<= k;
+    ksum += k;
+}
 
 // decode 16 symbols, last first, into 4 words (byte 3 of w[3] is the first one decoded)
 template <uint32_t NBO>
-SCL_HD void dec_group16(DecLaneV2 &D, const RansDec32 *lut, uint32_t mmask, uint32_t mlog, uint32_t llog, uint32_t w[4]) {
+SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
     uint32_t x = D.x;
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
         uint32_t acc = 0;
-#pragma unroll
-        for (int h = 1; h >= 0; --h) {
-            uint32_t bits = D.peek32();
-            uint32_t s1, s0;
-            SCL_DEC2_STEP(s1);
-            SCL_DEC2_STEP(s0);
-            acc |= (s1 << (16 * h + 8)) | (s0 << (16 * h));
+        {
+            uint32_t bits = D.peek32(), ks = 0;
+            dec_step<NBO, 3>(c, x, bits, ks, acc);
+            dec_step<NBO, 2>(c, x, bits, ks, acc);
+            D.bp += ks;
+        }
+        {
+            uint32_t bits = D.peek32(), ks = 0;
+            dec_step<NBO, 1>(c, x, bits, ks, acc);
+            dec_step<NBO, 0>(c, x, bits, ks, acc);
+            D.bp += ks;
         }
         w[j] = acc;
     }
@@ -332,21 +426,43 @@ SCL_HD void dec_group16(DecLaneV2 &D, const RansDec32 *lut, uint32_t mmask, uint
 
 // rANSDecoder.decode_block (rANS.py:270-297) for one lane, v2 I/O.  `out` 32-byte aligned.
 template <uint32_t NBO>
-SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, const RansDec32 *lut, const RansConst &c, uint8_t *out, uint64_t out_cap,
+SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, saddr_t lut, const RansConst &c, uint8_t *out, uint64_t out_cap,
                                       uint32_t &size_out, uint64_t &bits_consumed) {
     uint64_t size64 = D.get64(c.DBSB);
     D.x = D.get(c.NSB);
     size_out = 0;
     if (size64 > out_cap) return SCL_ST_OVERFLOW;
     const uint32_t size = (uint32_t)size64;
-    const uint32_t mmask = (uint32_t)c.M - 1, mlog = c.m_log2, llog = c.l_log2;
+    DecConst dc;
+    dc.lut = lut;
+    dc.m4 = ((uint32_t)c.M - 1) << 2;
+    dc.xq_mul = c.m_log2 ? (1u << (32 - c.m_log2)) : 0u;  // M == 1: x >> 0 handled below
+    dc.kbase = 31 - c.l_log2;
+    dc.nbo = NBO;
     uint32_t p = size;
+    if (c.m_log2 == 0) {
+        // degenerate single-symbol table with M == 1 (x >> 0 is not a multiply-high): plain loop
+        while (p > 0) {
+            uint32_t e = lds32(lut);
+            uint32_t x = (e >> 20) * D.x + ((e >> 8) & 0xFFFu);
+            uint32_t k = rans32_renorm_bits(x, c.l_log2, NBO);
+            uint32_t b = D.peek32();
+            D.x = funnel_l(b, x, k);
+            D.bp += k;
+            out[--p] = (uint8_t)(e & 0xFFu);
+            if ((p & 15) == 0) {
+                D.prefetch_begin();
+                D.prefetch_end();
+            }
+        }
+    }
     // ragged head: bring p down to a multiple of 32 one symbol at a time
     while (p & 31) {
-        uint32_t x = D.x, bits = D.peek32(), s;
-        SCL_DEC2_STEP(s);
+        uint32_t x = D.x, bits = D.peek32(), ks = 0, acc = 0;
+        dec_step<NBO, 0>(dc, x, bits, ks, acc);
         D.x = x;
-        out[--p] = (uint8_t)s;
+        D.bp += ks;
+        out[--p] = (uint8_t)acc;
         if ((p & 15) == 0) {  // keep the ring topped up on the same cadence as the main loop
             D.prefetch_begin();
             D.prefetch_end();
@@ -355,10 +471,10 @@ SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, const RansDec32 *lut, const 
     while (p >= 32) {
         u32x8 o;
         D.prefetch_begin();
-        dec_group16<NBO>(D, lut, mmask, mlog, llog, &o.v[4]);
+        dec_group16<NBO>(D, dc, &o.v[4]);
         D.prefetch_end();
         D.prefetch_begin();
-        dec_group16<NBO>(D, lut, mmask, mlog, llog, &o.v[0]);
+        dec_group16<NBO>(D, dc, &o.v[0]);
         D.prefetch_end();
         p -= 32;
         st_sector32(out + p, o);

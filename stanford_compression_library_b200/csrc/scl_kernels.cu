@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
-    uint32_t *ring = (uint32_t *)(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane;
+    const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
     const RansEnc32 *s_tab = (const RansEnc32 *)(smem + W * kEncWarpSmem);
     uint64_t *mbars = (uint64_t *)(smem + W * kEncWarpSmem + kEncTabBytes);
     uint64_t *tab_bar = mbars + W * kTileStages;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     }
     mbar_wait(tab_bar, 0);
 
-    const RansEnc32 *my_tab = s_tab + (lane & (kEncTabCopies - 1));  // this lane's bank-rotated replica
+    const saddr_t my_tab = saddr_of(s_tab) + (lane & (kEncTabCopies - 1)) * 16;  // this lane's bank-rotated replica
     const uint32_t n = io.block_len;
     const uint32_t n_tiles = (n + kTileCols - 1) / kTileCols;
     const uint32_t total_warps = gridDim.x * W;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                 const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));  // 64-byte TMA swizzle: conflict-free LDS.128
                 if (active) {
                     u32x4 v = {q.x, q.y, q.z, q.w};
-                    enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies, v, cnt);
+                    enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v, cnt);
                 }
             }
             __syncwarp();
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *ring = (uint32_t *)(smem + warp * kDecWarpSmem) + lane;
+    const saddr_t ring = saddr_of(smem + warp * kDecWarpSmem) + lane * 4;
     const RansDec32 *s_lut = (const RansDec32 *)(smem + W * kDecWarpSmem);
     stage_table((void *)s_lut, g_lut, lut_bytes, &mbar);
     const uint32_t total_warps = gridDim.x * W;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             D.init(io.in, io.in_bytes, off, ring);
             uint32_t size = 0;
             uint64_t used = 0;
-            uint32_t st = rans32_decode_lane_v2<NBO>(D, s_lut, c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+            uint32_t st = rans32_decode_lane_v2<NBO>(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
             if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
             io.sizes[b] = size;
             io.consumed[b] = used;

@@ -219,7 +219,7 @@ static void enc_v2_block(const RansHost &r, const uint8_t *row, uint32_t n, uint
                          uint64_t *bit_off, uint64_t *bit_len, uint32_t *status) {
     static thread_local uint32_t ring[kEncRingWords * kRingStrideWords];
     EncLaneV2 L;
-    L.init((uint32_t)r.c.L, ring, slot, slot + out_stride);
+    L.init((uint32_t)r.c.L, saddr_of(ring), slot, slot + out_stride);
     for (uint32_t i = 0; i < n; i += 16) {
         uint32_t cnt = n - i >= 16 ? 16u : n - i;
         uint8_t tmp[16] = {0};
@@ -227,9 +227,9 @@ static void enc_v2_block(const RansHost &r, const uint8_t *row, uint32_t n, uint
         u32x4 v;
         memcpy(&v, tmp, 16);
         if (r.c.check_sym)
-            enc_chunk<NBO, true>(L, r.enc_tab.data(), 1, v, cnt);
+            enc_chunk<NBO, true>(L, saddr_of(r.enc_tab.data()), 16, v, cnt);
         else
-            enc_chunk<NBO, false>(L, r.enc_tab.data(), 1, v, cnt);
+            enc_chunk<NBO, false>(L, saddr_of(r.enc_tab.data()), 16, v, cnt);
     }
     L.put(L.x, r.c.NSB);
     uint32_t st = SCL_ST_OK;
@@ -266,11 +266,11 @@ int emu_decode_blocks_v2(void *h, const uint8_t *in, uint64_t in_bytes, const ui
     const RansHost &r = *e->rans;
     for (uint64_t b = 0; b < n_blocks; ++b) {
         DecLaneV2 D;
-        D.init(in, in_bytes, bit_off[b], ring);
+        D.init(in, in_bytes, bit_off[b], saddr_of(ring));
         uint32_t size = 0;
         uint64_t used = 0;
-        uint32_t st = r.c.NBO == 1 ? rans32_decode_lane_v2<1>(D, r.dec_lut.data(), r.c, sym + b * sym_stride, sym_stride, size, used)
-                                   : rans32_decode_lane_v2<8>(D, r.dec_lut.data(), r.c, sym + b * sym_stride, sym_stride, size, used);
+        uint32_t st = r.c.NBO == 1 ? rans32_decode_lane_v2<1>(D, saddr_of(r.dec_lut.data()), r.c, sym + b * sym_stride, sym_stride, size, used)
+                                   : rans32_decode_lane_v2<8>(D, saddr_of(r.dec_lut.data()), r.c, sym + b * sym_stride, sym_stride, size, used);
         uint64_t avail = bit_len ? bit_len[b] : (in_bytes * 8 > bit_off[b] ? in_bytes * 8 - bit_off[b] : 0);
         if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         sizes[b] = size;
