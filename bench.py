@@ -33,6 +33,15 @@ VARIANTS = {
 HEADLINE = "default"
 
 
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process is allowed on (torchrun exports
+    OMP_NUM_THREADS=1, so the OpenMP default is not a usable answer)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -122,7 +131,7 @@ def run_reference(args, rank, world):
 
     so.build()
     fl = zipf_freq_list()
-    threads = so.max_threads()
+    threads = host_threads()
     B = min(BLOCKS_PER_GPU, 1024 * threads)
     rng = np.random.default_rng(0)
     data = rng.choice(256, size=(B, BLOCK_LEN), p=np.array(zipf_probabilities())).astype(np.uint8)
@@ -181,6 +190,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         scl_build.build()
@@ -337,7 +347,7 @@ def main():
         from oracle import scl_oracle as so
 
         so.build()
-        threads = so.max_threads()
+        threads = host_threads()
         nb = min(B, 1024 * threads)
         cpu = cpu_baseline(fl, VARIANTS[HEADLINE], data[:nb].cpu().numpy(), threads, HEADLINE)
 
