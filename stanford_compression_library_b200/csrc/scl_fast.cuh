@@ -484,4 +484,126 @@ SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, saddr_t lut, const RansConst
     return D.x == (uint32_t)c.L ? SCL_ST_OK : SCL_ST_STATE_MISMATCH;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tANS on the same I/O machinery (tANS.py:126-157 / :239-250): the steps are pure table reads.
+//   symbol entry (16 B, 8 bank-rotated replicas) = {thresh, nb0, row - min_shrunk, pad}
+//   enc_table[row + x_shrunk] = next state        dec_packed[x - L] = x_shrunk << 8 | byte
+// ------------------------------------------------------------------------------------------------
+template <bool CHECK>
+SCL_HD void tans_enc_step(EncLaneV2 &L, const u32x4 &e, saddr_t enc_table) {
+    if (CHECK && e.y == 0xFFFFFFFFu) {
+        L.bad = 1;
+        return;
+    }
+    uint32_t k = e.y + (L.x >= e.x ? 1u : 0u);  // shrink_state_num_out_bits_base + threshold test
+    L.lo = funnel_r(L.lo, L.hi, k);
+    L.hi = funnel_r(L.hi, L.x, k);
+    L.room -= k;
+    L.x = lds32(enc_table + (saddr_t)(((L.x >> k) + e.z) << 2));  // base_encode_step_table[(s, x_shrunk)]
+}
+
+template <bool CHECK>
+SCL_HD void tans_enc_chunk(EncLaneV2 &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v, uint32_t cnt) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+    if (cnt == 16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                tans_enc_step<CHECK>(L, lds128(symtab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)), enc_table);
+                if (b & 1) L.spill_check();
+            }
+        }
+    } else {
+        for (uint32_t i = 0; i < cnt; ++i) {
+            tans_enc_step<CHECK>(L, lds128(symtab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)), enc_table);
+            L.spill_check();
+        }
+    }
+    L.drain_check();
+}
+
+struct TansDecConst {
+    saddr_t dec;      // address of dec_packed[0]
+    uint32_t L;       // table size (power of two)
+    uint32_t lmask4;  // (L - 1) * 4
+    uint32_t kbase;   // 32 - NUM_STATE_BITS: k = clz(x_shrunk) - kbase
+};
+
+template <int POS>
+SCL_HD void tans_dec_step(const TansDecConst &c, uint32_t &x, uint32_t &bits, uint32_t &ksum, uint32_t &acc) {
+    // a corrupt state (outside [L, 2L)) wraps inside the table instead of faulting; the final
+    // state check reports it (the reference raises KeyError from its dict)
+    uint32_t e = lds32(c.dec + (saddr_t)(((x - c.L) << 2) & c.lmask4));
+    uint32_t xs = e >> 8;
+    acc = put_byte<POS>(acc, e);
+    uint32_t k = clz32(xs) - c.kbase;  // expand_state_num_bits_table (tANS.py:225)
+    x = funnel_l(bits, xs, k);
+    bits <<= k;
+    ksum += k;
+}
+
+SCL_HD void tans_dec_group16(DecLaneV2 &D, const TansDecConst &c, uint32_t w[4]) {
+    uint32_t x = D.x;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+        uint32_t acc = 0;
+        {
+            uint32_t bits = D.peek32(), ks = 0;
+            tans_dec_step<3>(c, x, bits, ks, acc);
+            tans_dec_step<2>(c, x, bits, ks, acc);
+            D.bp += ks;
+        }
+        {
+            uint32_t bits = D.peek32(), ks = 0;
+            tans_dec_step<1>(c, x, bits, ks, acc);
+            tans_dec_step<0>(c, x, bits, ks, acc);
+            D.bp += ks;
+        }
+        w[j] = acc;
+    }
+    D.x = x;
+}
+
+// tANSDecoder.decode_block (tANS.py:252-279) for one lane, v2 I/O
+SCL_HD uint32_t tans_decode_lane_v2(DecLaneV2 &D, saddr_t dec, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
+                                    uint64_t &bits_consumed) {
+    uint64_t size64 = D.get64(c.DBSB);
+    D.x = D.get(c.NSB);
+    size_out = 0;
+    if (size64 > out_cap) return SCL_ST_OVERFLOW;
+    const uint32_t size = (uint32_t)size64;
+    TansDecConst tc;
+    tc.dec = dec;
+    tc.L = (uint32_t)c.L;
+    tc.lmask4 = ((uint32_t)c.L - 1) << 2;
+    tc.kbase = 32 - c.NSB;
+    uint32_t p = size;
+    while (p & 31) {
+        uint32_t x = D.x, bits = D.peek32(), ks = 0, acc = 0;
+        tans_dec_step<0>(tc, x, bits, ks, acc);
+        D.x = x;
+        D.bp += ks;
+        out[--p] = (uint8_t)acc;
+        if ((p & 15) == 0) {
+            D.prefetch_begin();
+            D.prefetch_end();
+        }
+    }
+    while (p >= 32) {
+        u32x8 o;
+        D.prefetch_begin();
+        tans_dec_group16(D, tc, &o.v[4]);
+        D.prefetch_end();
+        D.prefetch_begin();
+        tans_dec_group16(D, tc, &o.v[0]);
+        D.prefetch_end();
+        p -= 32;
+        st_sector32(out + p, o);
+    }
+    size_out = size;
+    bits_consumed = D.bp - D.start_bp;
+    return D.x == (uint32_t)c.L ? SCL_ST_OK : SCL_ST_STATE_MISMATCH;
+}
+
 }  // namespace scl

@@ -197,16 +197,19 @@ __device__ __forceinline__ void tma_tile_2d(void *smem_dst, const CUtensorMap *t
 }
 
 // smem layout: [tiles+rings per warp ...][table 32 KiB][mbarriers]
-template <uint32_t NBO, bool CHECK>
+// KIND 0 = rANS (arithmetic step), KIND 1 = tANS (table step; g_tab2 = enc_table, staged after the
+// replicated per-symbol table)
+template <int KIND, uint32_t NBO, bool CHECK>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
-    rans32_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const RansEnc32 *__restrict__ g_tab8, RansConst c, BlockIo io,
-                            uint32_t n_tasks) {
+    fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
+                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
     const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
-    const RansEnc32 *s_tab = (const RansEnc32 *)(smem + W * kEncWarpSmem);
-    uint64_t *mbars = (uint64_t *)(smem + W * kEncWarpSmem + kEncTabBytes);
+    const uint8_t *s_tab = smem + W * kEncWarpSmem;
+    const saddr_t s_tab2 = saddr_of(smem + W * kEncWarpSmem + kEncTabBytes);
+    uint64_t *mbars = (uint64_t *)(smem + W * kEncWarpSmem + kEncTabBytes + tab2_bytes);
     uint64_t *tab_bar = mbars + W * kTileStages;
     uint64_t *my_bar = mbars + warp * kTileStages;
 
@@ -217,8 +220,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        tma_expect(tab_bar, kEncTabBytes);
+        tma_expect(tab_bar, kEncTabBytes + tab2_bytes);
         tma_bulk_g2s((void *)s_tab, g_tab8, kEncTabBytes, tab_bar);
+        if (KIND == 1) tma_bulk_g2s(smem + W * kEncWarpSmem + kEncTabBytes, g_tab2, tab2_bytes, tab_bar);
     }
     mbar_wait(tab_bar, 0);
 
@@ -254,7 +258,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                 const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));  // 64-byte TMA swizzle: conflict-free LDS.128
                 if (active) {
                     u32x4 v = {q.x, q.y, q.z, q.w};
-                    enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v, cnt);
+                    if (KIND == 0)
+                        enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v, cnt);
+                    else
+                        tans_enc_chunk<CHECK>(L, my_tab, kEncTabCopies * 16, s_tab2, v, cnt);
                 }
             }
             __syncwarp();
@@ -279,9 +286,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     }
 }
 
-template <uint32_t NBO>
+template <int KIND, uint32_t NBO>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
-    rans32_decode_v2_kernel(const RansDec32 *__restrict__ g_lut, uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
+    fast_decode_v2_kernel(const uint32_t *__restrict__ g_lut, uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,7 +304,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             D.init(io.in, io.in_bytes, off, ring);
             uint32_t size = 0;
             uint64_t used = 0;
-            uint32_t st = rans32_decode_lane_v2<NBO>(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+            uint32_t st = KIND == 0 ? rans32_decode_lane_v2<NBO>(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used)
+                                    : tans_decode_lane_v2(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
             if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
             io.sizes[b] = size;
             io.consumed[b] = used;
@@ -566,6 +574,7 @@ struct scl_coder {
     uint32_t dec32_bytes = 0;
     RansGeneric *d_gen = nullptr;
     TansSym *d_tsym = nullptr;
+    TansSym *d_tsymx8 = nullptr;  // bank-rotated replicas for the v2 tANS encoder
     uint32_t *d_tenc = nullptr, *d_tdec = nullptr;
     uint32_t ttab_bytes = 0;
     RangeTab *d_range = nullptr;
@@ -605,6 +614,7 @@ extern "C" void scl_coder_destroy(scl_coder *c) {
     cudaFree(c->d_dec32);
     cudaFree(c->d_gen);
     cudaFree(c->d_tsym);
+    cudaFree(c->d_tsymx8);
     cudaFree(c->d_tenc);
     cudaFree(c->d_tdec);
     cudaFree(c->d_range);
@@ -663,7 +673,18 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         rc = upload(&c->d_gen, &t.r.gen, sizeof(RansGeneric), sizeof(RansGeneric), s);
         if (!rc) rc = upload(&c->d_tsym, t.sym_tab.data(), sizeof(TansSym) * 256, sizeof(TansSym) * 256, s);
         if (!rc) rc = upload(&d_rows, t.row_of_idx.data(), sizeof(uint32_t) * n_sym, sizeof(uint32_t) * n_sym, s);
+        std::vector<TansSym> trep(256 * kEncTabCopies);
+        for (uint32_t sy = 0; sy < 256; ++sy)
+            for (uint32_t j = 0; j < kEncTabCopies; ++j) trep[sy * kEncTabCopies + j] = t.sym_tab[sy];
+        if (!rc) rc = upload(&c->d_tsymx8, trep.data(), trep.size() * sizeof(TansSym), trep.size() * sizeof(TansSym), s);
         if (rc) break;
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev);
+            // v2 needs both L-entry tables in shared memory next to the per-warp buffers
+            c->v2_ok = t.r.max_bits_per_symbol <= kFastMaxBitsPerSym && t.r.c.L * 4 <= 64 * 1024 && c->n_sm > 0 && t.r.c.NSB <= 32;
+        }
         c->ttab_bytes = (uint32_t)round16(t.r.c.L * 4);
         cudaError_t e = cudaMalloc((void **)&c->d_tenc, c->ttab_bytes);
         if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_tdec, c->ttab_bytes);
@@ -772,9 +793,15 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
 static bool g_force_v1 = false;  // test hook: scl_debug_force_v1(1) routes the fast path to the first-generation kernels
 extern "C" void scl_debug_force_v1(int on) { g_force_v1 = on != 0; }
 
-template <uint32_t NBO>
-static int launch_encode_v2(const scl_coder *c, const BlockIo &io, cudaStream_t s) {
-    const RansHost &r = *c->rans;
+static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
+    size_t avail = 227 * 1024 - 1024 - fixed;  // 227 KiB per CTA minus slack for static smem / barriers
+    uint32_t w = (uint32_t)(avail / per_warp);
+    return w > kMaxWarps ? kMaxWarps : w;
+}
+
+template <int KIND, uint32_t NBO>
+static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void *tab8, const uint32_t *tab2, uint32_t tab2_bytes,
+                            const BlockIo &io, cudaStream_t s) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return -1;
     CUtensorMap tmap;
@@ -786,31 +813,32 @@ static int launch_encode_v2(const scl_coder *c, const BlockIo &io, cudaStream_t 
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -1;
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    pick_launch(n_tasks, c->n_sm, kMaxWarps, &grid, &warps);
-    size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + (warps * kTileStages + 1) * sizeof(uint64_t);
+    size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t);
+    pick_launch(n_tasks, c->n_sm, max_warps_for(kEncWarpSmem, fixed), &grid, &warps);
+    size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t);
     cudaError_t e;
-    if (r.c.check_sym) {
-        e = cudaFuncSetAttribute(rans32_encode_v2_kernel<NBO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc.check_sym) {
+        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        rans32_encode_v2_kernel<NBO, true><<<grid, warps * 32, smem, s>>>(tmap, c->d_enc32x8, r.c, io, n_tasks);
+        fast_encode_v2_kernel<KIND, NBO, true><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks);
     } else {
-        e = cudaFuncSetAttribute(rans32_encode_v2_kernel<NBO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        rans32_encode_v2_kernel<NBO, false><<<grid, warps * 32, smem, s>>>(tmap, c->d_enc32x8, r.c, io, n_tasks);
+        fast_encode_v2_kernel<KIND, NBO, false><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks);
     }
-    return check_launch("rans32_encode_v2_kernel");
+    return check_launch("fast_encode_v2_kernel");
 }
 
-template <uint32_t NBO>
-static int launch_decode_v2(const scl_coder *c, const DecodeIo &io, cudaStream_t s) {
-    const RansHost &r = *c->rans;
+template <int KIND, uint32_t NBO>
+static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint32_t *lut, uint32_t lut_bytes, const DecodeIo &io,
+                            cudaStream_t s) {
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    pick_launch(n_tasks, c->n_sm, kMaxWarps, &grid, &warps);
-    size_t smem = (size_t)warps * kDecWarpSmem + c->dec32_bytes;
-    cudaError_t e = cudaFuncSetAttribute(rans32_decode_v2_kernel<NBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem, lut_bytes), &grid, &warps);
+    size_t smem = (size_t)warps * kDecWarpSmem + lut_bytes;
+    cudaError_t e = cudaFuncSetAttribute(fast_decode_v2_kernel<KIND, NBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    rans32_decode_v2_kernel<NBO><<<grid, warps * 32, smem, s>>>(c->d_dec32, c->dec32_bytes, r.c, io, n_tasks);
-    return check_launch("rans32_decode_v2_kernel");
+    fast_decode_v2_kernel<KIND, NBO><<<grid, warps * 32, smem, s>>>(lut, lut_bytes, rc, io, n_tasks);
+    return check_launch("fast_decode_v2_kernel");
 }
 
 extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
@@ -829,7 +857,8 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         if (r.enc32 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 &&
             (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
             (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
-            int rc2 = r.c.NBO == 1 ? launch_encode_v2<1>(c, io, s) : launch_encode_v2<8>(c, io, s);
+            int rc2 = r.c.NBO == 1 ? launch_encode_v2<0, 1>(c, r.c, c->d_enc32x8, nullptr, 0, io, s)
+                                   : launch_encode_v2<0, 8>(c, r.c, c->d_enc32x8, nullptr, 0, io, s);
             if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
         }
         if (r.enc32) {
@@ -844,6 +873,12 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     }
     if (c->tans) {
         const TansHost &t = *c->tans;
+        if (c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
+            (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
+            (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
+            int rc2 = launch_encode_v2<1, 1>(c, t.r.c, c->d_tsymx8, c->d_tenc, c->ttab_bytes, io, s);
+            if (rc2 >= 0) return rc2;
+        }
         if (c->ttab_bytes <= kTansSmemTableMax) {
             SCL_CUDA(cudaFuncSetAttribute(tans_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
             tans_encode_kernel<true><<<grid, kThreads, c->ttab_bytes, s>>>(c->d_tsym, c->d_tenc, c->ttab_bytes, t.r.c, io);
@@ -878,7 +913,8 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         const RansHost &r = *c->rans;
         if (r.dec32 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
             n_blocks < (1ull << 36))
-            return r.c.NBO == 1 ? launch_decode_v2<1>(c, io, s) : launch_decode_v2<8>(c, io, s);
+            return r.c.NBO == 1 ? launch_decode_v2<0, 1>(c, r.c, c->d_dec32, c->dec32_bytes, io, s)
+                                : launch_decode_v2<0, 8>(c, r.c, c->d_dec32, c->dec32_bytes, io, s);
         if (r.dec32)
             rans32_decode_kernel<<<grid, kThreads, c->dec32_bytes, s>>>(c->d_dec32, c->dec32_bytes, r.c, io);
         else
@@ -887,6 +923,9 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     }
     if (c->tans) {
         const TansHost &t = *c->tans;
+        if (c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+            n_blocks < (1ull << 36))
+            return launch_decode_v2<1, 1>(c, t.r.c, c->d_tdec, c->ttab_bytes, io, s);
         if (c->ttab_bytes <= kTansSmemTableMax) {
             SCL_CUDA(cudaFuncSetAttribute(tans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
             tans_decode_kernel<true><<<grid, kThreads, c->ttab_bytes, s>>>(c->d_tdec, c->ttab_bytes, t.r.c, io);

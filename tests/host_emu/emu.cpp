@@ -207,6 +207,10 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
 // ---- second-generation lane structs (scl_fast.cuh), driven like the v2 kernels drive them ----
 int emu_v2_eligible(void *h) {
     Emu *e = (Emu *)h;
+    if (e->tans) {
+        const RansHost &r = e->tans->r;
+        return r.max_bits_per_symbol <= kFastMaxBitsPerSym && r.c.L * 4 <= 64 * 1024 && r.c.NSB <= 32;
+    }
     if (!e->rans) return 0;
     const RansHost &r = *e->rans;
     return r.enc32 && r.dec32 && r.max_bits_per_symbol <= kFastMaxBitsPerSym && (r.c.NBO == 1 || r.c.NBO == 8);
@@ -245,12 +249,43 @@ static void enc_v2_block(const RansHost &r, const uint8_t *row, uint32_t n, uint
 
 extern "C" {
 
+static void tans_enc_v2_block(const Emu &e, const uint8_t *row, uint32_t n, uint8_t *slot, uint64_t out_stride, uint64_t b, uint64_t *bit_off,
+                              uint64_t *bit_len, uint32_t *status) {
+    static thread_local uint32_t ring[kEncRingWords * kRingStrideWords];
+    const RansHost &r = e.tans->r;
+    EncLaneV2 L;
+    L.init((uint32_t)r.c.L, saddr_of(ring), slot, slot + out_stride);
+    for (uint32_t i = 0; i < n; i += 16) {
+        uint32_t cnt = n - i >= 16 ? 16u : n - i;
+        uint8_t tmp[16] = {0};
+        memcpy(tmp, row + i, cnt);
+        u32x4 v;
+        memcpy(&v, tmp, 16);
+        if (r.c.check_sym)
+            tans_enc_chunk<true>(L, saddr_of(e.tans->sym_tab.data()), 16, saddr_of(e.tenc.data()), v, cnt);
+        else
+            tans_enc_chunk<false>(L, saddr_of(e.tans->sym_tab.data()), 16, saddr_of(e.tenc.data()), v, cnt);
+    }
+    L.put(L.x, r.c.NSB);
+    uint32_t st = SCL_ST_OK;
+    if (r.c.DBSB < 32 && (n >> r.c.DBSB)) st = SCL_ST_OVERFLOW;
+    L.put64((uint64_t)n, r.c.DBSB);
+    uint64_t bits = L.finish();
+    if (L.bad) st = SCL_ST_BAD_SYMBOL;
+    if (L.ovf) st = SCL_ST_OVERFLOW;
+    bit_len[b] = bits;
+    bit_off[b] = (b + 1) * out_stride * 8 - bits;
+    status[b] = st;
+}
+
 int emu_encode_blocks_v2(void *h, const uint8_t *sym, uint64_t sym_stride, uint32_t block_len, uint64_t n_blocks, uint8_t *out,
                          uint64_t out_stride, uint64_t *bit_off, uint64_t *bit_len, uint32_t *status) {
     Emu *e = (Emu *)h;
     if (!emu_v2_eligible(h) || (out_stride & 31) || (((uintptr_t)out) & 31)) return SCL_E_INVALID;
     for (uint64_t b = 0; b < n_blocks; ++b) {
-        if (e->rans->c.NBO == 1)
+        if (e->tans)
+            tans_enc_v2_block(*e, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
+        else if (e->rans->c.NBO == 1)
             enc_v2_block<1>(*e->rans, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
         else
             enc_v2_block<8>(*e->rans, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
@@ -263,13 +298,14 @@ int emu_decode_blocks_v2(void *h, const uint8_t *in, uint64_t in_bytes, const ui
     Emu *e = (Emu *)h;
     if (!emu_v2_eligible(h) || (sym_stride & 31) || (((uintptr_t)sym) & 31) || (((uintptr_t)in) & 31)) return SCL_E_INVALID;
     static thread_local uint32_t ring[(kDecRingWords + 1) * kRingStrideWords];
-    const RansHost &r = *e->rans;
+    const RansHost &r = e->tans ? e->tans->r : *e->rans;
     for (uint64_t b = 0; b < n_blocks; ++b) {
         DecLaneV2 D;
         D.init(in, in_bytes, bit_off[b], saddr_of(ring));
         uint32_t size = 0;
         uint64_t used = 0;
-        uint32_t st = r.c.NBO == 1 ? rans32_decode_lane_v2<1>(D, saddr_of(r.dec_lut.data()), r.c, sym + b * sym_stride, sym_stride, size, used)
+        uint32_t st = e->tans ? tans_decode_lane_v2(D, saddr_of(e->tdec.data()), r.c, sym + b * sym_stride, sym_stride, size, used)
+                      : r.c.NBO == 1 ? rans32_decode_lane_v2<1>(D, saddr_of(r.dec_lut.data()), r.c, sym + b * sym_stride, sym_stride, size, used)
                                    : rans32_decode_lane_v2<8>(D, saddr_of(r.dec_lut.data()), r.c, sym + b * sym_stride, sym_stride, size, used);
         uint64_t avail = bit_len ? bit_len[b] : (in_bytes * 8 > bit_off[b] ? in_bytes * 8 - bit_off[b] : 0);
         if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;

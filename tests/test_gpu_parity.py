@@ -351,3 +351,37 @@ def test_rans_kernel_generations_agree(kw, shape):
         ref_bytes, ref_bits = oracle.encode_block(host[b])
         got = e2.block(b)
         assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()
+
+
+@pytest.mark.parametrize("rf", [1, 4], ids=["L4096", "L16384"])
+def test_tans_kernel_generations_agree(rf):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    B, N = 1000, 4100
+    params = tANSParams(zipf_frequencies(), RANGE_FACTOR=rf)
+    enc, dec = tANSEncoder(params), tANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=12, device="cuda:0")
+    data[0, :] = 255
+    lib = _cabi.lib()
+    try:
+        lib.scl_debug_force_v1(1)
+        e1 = enc.encode_blocks(data).check()
+        p1 = e1.pack()
+        lib.scl_debug_force_v1(0)
+        e2 = enc.encode_blocks(data).check()
+        assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(p1.buf, e2.pack().buf)
+        d2 = dec.decode_blocks(e1, N).check()
+        lib.scl_debug_force_v1(1)
+        d1 = dec.decode_blocks(e2, N).check()
+    finally:
+        lib.scl_debug_force_v1(0)
+    for d in (d1, d2):
+        assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
+    oracle = so.Oracle.tans(zipf_freq_list(), RANGE_FACTOR=rf)
+    host = data.cpu().numpy()
+    for b in (0, 1, B - 1):
+        ref_bytes, ref_bits = oracle.encode_block(host[b])
+        got = e2.block(b)
+        assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()

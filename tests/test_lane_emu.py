@@ -208,7 +208,7 @@ def test_emu_status_words():
 
 
 # ---- second-generation lane structs (csrc/scl_fast.cuh: funnel-shift packing, sector ring I/O) ----
-@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "rans"], ids=case_id)
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] in ("rans", "tans")], ids=case_id)
 def test_emu_v2_matches_golden(c):
     coder = EmuCoder(params_from_case(c), None, c["freqs"])
     if not coder.v2_eligible():
@@ -253,3 +253,30 @@ def test_emu_v2_vs_oracle_zipf_lengths(kw):
         dsym, dsz, used, st = coder.decode_v2(out, off, ln, max(N, 1))
         assert (st == 0).all() and (dsz == N).all() and (used == ln).all()
         assert (dsym[:, :N] == sym).all()
+
+
+@pytest.mark.parametrize("rf", [1, 4])
+def test_emu_tans_v2_vs_oracle_zipf_lengths(rf):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+    from stanford_compression_library_b200.workloads import zipf_freq_list, zipf_probabilities
+
+    fl = zipf_freq_list()
+    rng = np.random.default_rng(4)
+    nsb = so.ref_get_bit_width(rf * 4096 * 2 - 1)
+    prm = SclParams(coder=_cabi.CODER_TANS, data_block_size_bits=32, num_bits_out=1, range_factor=rf, num_state_bits=nsb, precision=0, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, fl)
+    assert coder.v2_eligible()
+    oracle = so.Oracle.tans(fl, RANGE_FACTOR=rf)
+    for N in (0, 1, 31, 32, 33, 100, 1024, 4096):
+        sym = rng.choice(256, size=(4, N), p=np.array(zipf_probabilities())).astype(np.uint8)
+        if N:
+            sym[0, :] = 255
+        out, off, ln, st = coder.encode_v2(sym)
+        assert (st == 0).all()
+        for b in range(4):
+            enc, nb = oracle.encode_block(sym[b])
+            assert nb == ln[b] and extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (N, b)
+        dsym, dsz, used, st = coder.decode_v2(out, off, ln, max(N, 1))
+        assert (st == 0).all() and (dsz == N).all() and (used == ln).all() and (dsym[:, :N] == sym).all()

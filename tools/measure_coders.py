@@ -1,0 +1,64 @@
+"""Throughput of every coder kernel on the BASELINE config shapes (informative; bench.py is the
+contract).  python tools/measure_coders.py [--blocks-scale 1.0]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stanford_compression_library_b200 import Frequencies  # noqa: E402
+from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder  # noqa: E402
+from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel  # noqa: E402
+from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams  # noqa: E402
+from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder  # noqa: E402
+from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams  # noqa: E402
+from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities  # noqa: E402
+
+
+def timeit(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return min(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+
+
+def run(name, enc, dec, data):
+    B, N = data.shape
+    e = enc.encode_blocks(data).check()
+    d = dec.decode_blocks(e, N).check()
+    assert torch.equal(d.symbols[:, :N], data)
+    te = timeit(lambda: enc.encode_blocks(data, reuse=e))
+    td = timeit(lambda: dec.decode_blocks(e, N, reuse=d))
+    raw, C = B * N, e.total_bytes()
+    res = dict(coder=name, blocks=B, block_len=N, bits_per_symbol=8 * C / raw, encode_ms=te, decode_ms=td, encode_GBps=raw / te / 1e6, decode_GBps=raw / td / 1e6,
+               encode_roofline_frac=(raw + C) / te / 1e6 / 6458.4, decode_roofline_frac=(raw + C) / td / 1e6 / 6458.4)
+    print(json.dumps(res))
+    return res
+
+
+def main():
+    torch.cuda.set_device(0)
+    fr = zipf_frequencies()
+    p = zipf_probabilities()
+    d4k = sample_blocks(p, 65536, 4096, seed=0, device="cuda:0")
+    d1k = sample_blocks(p, 262144, 1024, seed=1, device="cuda:0")
+    run("rANS default (cfg2)", rANSEncoder(rANSParams(fr)), rANSDecoder(rANSParams(fr)), d4k)
+    run("rANS nbo8 rf4096 (cfg2)", rANSEncoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), rANSDecoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), d4k)
+    tp = tANSParams(fr, RANGE_FACTOR=1)
+    run("tANS RF=1 L=4096 (cfg3)", tANSEncoder(tp), tANSDecoder(tp), d4k)
+    rp = RangeCoderParams()
+    run("range coder (cfg2 shape)", RangeEncoder(rp, fr), RangeDecoder(rp, fr), d4k)
+    ap = AECParams()
+    uni = Frequencies({b: 1 for b in range(256)})
+    run("arithmetic adaptive order-0, 262144 x 1 KiB (cfg4 shape / 4)", ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)),
+        ArithmeticDecoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)), d1k)
+
+
+if __name__ == "__main__":
+    main()
