@@ -417,14 +417,32 @@ __global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *
 // warp hits 32 distinct banks whatever the per-lane index).
 // ------------------------------------------------------------------------------------------------
 constexpr int kAecThreads = 32;
-struct SmemTree {
+struct SmemTree {  // 32-bit counters
     uint32_t *base;  // &smem[lane]
+    static constexpr uint32_t kBytes = 257 * kAecThreads * 4;
+    __device__ __forceinline__ explicit SmemTree(uint8_t *smem) : base((uint32_t *)smem + threadIdx.x) {}
     __device__ __forceinline__ uint32_t get(uint32_t i) const { return base[i * kAecThreads]; }
     __device__ __forceinline__ void set(uint32_t i, uint32_t v) { base[i * kAecThreads] = v; }
 };
-constexpr uint32_t kAecTreeBytes = 257 * kAecThreads * 4;
+// 16-bit counters, two tree nodes of the SAME lane per 32-bit word: still one bank per lane, half
+// the shared memory (twice the resident warps).  Usable when no count can reach 65536.
+struct SmemTree16 {
+    uint32_t *base;
+    static constexpr uint32_t kBytes = 129 * kAecThreads * 4;
+    __device__ __forceinline__ explicit SmemTree16(uint8_t *smem) : base((uint32_t *)smem + threadIdx.x) {}
+    __device__ __forceinline__ uint32_t get(uint32_t i) const {
+        uint32_t w = base[(i >> 1) * kAecThreads];
+        return (i & 1) ? (w >> 16) : (w & 0xFFFFu);
+    }
+    __device__ __forceinline__ void set(uint32_t i, uint32_t v) {
+        uint32_t *p = base + (i >> 1) * kAecThreads;
+        uint32_t w = *p;
+        *p = (i & 1) ? ((w & 0xFFFFu) | (v << 16)) : ((w & 0xFFFF0000u) | (v & 0xFFFFu));
+    }
+};
 
-__device__ __forceinline__ uint64_t aec_load_model(SmemTree &F, const AecTab &tab, const AecConst &c, const uint64_t *model) {
+template <typename Tree>
+__device__ __forceinline__ uint64_t aec_load_model(Tree &F, const AecTab &tab, const AecConst &c, const uint64_t *model) {
     uint64_t total = 0;
     F.set(0, 0);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -436,12 +454,14 @@ __device__ __forceinline__ uint64_t aec_load_model(SmemTree &F, const AecTab &ta
     fen_build(F);
     return total;
 }
-__device__ __forceinline__ void aec_store_model(SmemTree &F, const AecConst &c, uint64_t *model) {
+template <typename Tree>
+__device__ __forceinline__ void aec_store_model(Tree &F, const AecConst &c, uint64_t *model) {
     if (!model) return;
     fen_unbuild(F);
     for (uint32_t i = 0; i < c.n_sym; ++i) model[i] = F.get(i + 1);
 }
 
+template <typename Tree>
 __global__ void __launch_bounds__(kAecThreads) aec_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io, uint64_t *model) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ AecTab s_tab;
@@ -449,7 +469,7 @@ __global__ void __launch_bounds__(kAecThreads) aec_encode_kernel(const AecTab *_
     stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
     uint64_t b = (uint64_t)blockIdx.x * kAecThreads + threadIdx.x;
     if (b >= io.n_blocks) return;
-    SmemTree F{(uint32_t *)s_dyn + threadIdx.x};
+    Tree F(s_dyn);
     uint64_t *my_model = model ? model + b * c.n_sym : nullptr;
     uint64_t total = aec_load_model(F, s_tab, c, my_model);
     uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
@@ -464,6 +484,7 @@ __global__ void __launch_bounds__(kAecThreads) aec_encode_kernel(const AecTab *_
     io.status[b] = st;
 }
 
+template <typename Tree>
 __global__ void __launch_bounds__(kAecThreads) aec_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io, uint64_t *model) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ AecTab s_tab;
@@ -471,7 +492,7 @@ __global__ void __launch_bounds__(kAecThreads) aec_decode_kernel(const AecTab *_
     stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
     uint64_t b = (uint64_t)blockIdx.x * kAecThreads + threadIdx.x;
     if (b >= io.n_blocks) return;
-    SmemTree F{(uint32_t *)s_dyn + threadIdx.x};
+    Tree F(s_dyn);
     uint64_t *my_model = model ? model + b * c.n_sym : nullptr;
     uint64_t total = aec_load_model(F, s_tab, c, my_model);
     BitReader r;
@@ -893,7 +914,14 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     }
     if (c->aec) {
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
-        aec_encode_kernel<<<g, kAecThreads, kAecTreeBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        // 16-bit counters when no count can reach 65536: counts start at init_freq and grow by at most
+        // one per coded symbol (a caller-supplied d_model may hold anything, so it takes the 32-bit tree)
+        uint64_t max_init = 0;
+        for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
+        if (!d_model && max_init + block_len < 65536 && !g_force_v1)
+            aec_encode_kernel<SmemTree16><<<g, kAecThreads, SmemTree16::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        else
+            aec_encode_kernel<SmemTree><<<g, kAecThreads, SmemTree::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
         return check_launch("aec_encode_kernel");
     }
     return SCL_E_INVALID;
@@ -940,7 +968,12 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     }
     if (c->aec) {
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
-        aec_decode_kernel<<<g, kAecThreads, kAecTreeBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        uint64_t max_init = 0;
+        for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
+        if (!d_model && max_init + sym_stride < 65536 && !g_force_v1)  // decoded size <= sym_stride is enforced by the lane
+            aec_decode_kernel<SmemTree16><<<g, kAecThreads, SmemTree16::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
+        else
+            aec_decode_kernel<SmemTree><<<g, kAecThreads, SmemTree::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
         return check_launch("aec_decode_kernel");
     }
     return SCL_E_INVALID;

@@ -607,6 +607,20 @@ SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, BitRea
 // (1-based, F[0] unused) supplied by the caller through the accessor type `Tree`
 // (shared memory, lane-interleaved, on the device; a plain array in the host harness).
 // ------------------------------------------------------------------------------------------------
+// floor(a / d) for a < 2^62, 0 < d <= 2^32, given rcp = 1.0 / d: one FP64 multiply plus an exact
+// integer correction instead of a 64-bit integer division (~70 instructions on the GPU).  The FP64
+// estimate is within +-1 of the true quotient (quotients here are < 2^33, relative error of the
+// product < 2^-50), and the remainder test makes the result exact.
+SCL_HD uint64_t div_exact_rcp(uint64_t a, uint64_t d, double rcp) {
+    uint64_t q = (uint64_t)((double)a * rcp);
+    int64_t r = (int64_t)(a - q * d);
+    if (r < 0)
+        q -= 1;
+    else if ((uint64_t)r >= d)
+        q += 1;
+    return q;
+}
+
 template <typename Tree>
 SCL_HD uint32_t fen_prefix(const Tree &F, uint32_t i) {  // sum of counts[0 .. i)
     uint32_t s = 0;
@@ -694,8 +708,9 @@ SCL_HD uint32_t aec_encode_lane(Tree &F, const AecTab &tab, const AecConst &c, u
         // shrink_range (:58-78)
         uint64_t cc = fen_prefix(F, idx), dd = fen_prefix(F, idx + 1);
         uint64_t rng = high - low;
-        high = low + (rng * dd) / total;
-        low = low + (rng * cc) / total;
+        const double rcp_t = 1.0 / (double)total;
+        high = low + div_exact_rcp(rng * dd, total, rcp_t);
+        low = low + div_exact_rcp(rng * cc, total, rcp_t);
         aec_model_update(F, c, idx, total);  // :118
         while (high < HALF || low > HALF) {  // :126-143
             if (high < HALF) {
@@ -768,13 +783,14 @@ SCL_HD uint32_t aec_decode_lane(Tree &F, const AecTab &tab, const AecConst &c, u
             idx = c.n_sym - 1;  // searchsorted -> 0, alphabet[-1]
             cc = fen_prefix(F, idx);
         } else {
-            uint64_t v = ((state - low + 1) * total - 1) / rng;
+            uint64_t v = div_exact_rcp((state - low + 1) * total - 1, rng, 1.0 / (double)rng);
             if (v >= total) v = total - 1;
             idx = fen_find(F, (uint32_t)v, cc);
         }
         uint64_t dd = fen_prefix(F, idx + 1);
-        high = low + (rng * dd) / total;  // shrink_range
-        low = low + (rng * (uint64_t)cc) / total;
+        const double rcp_t = 1.0 / (double)total;
+        high = low + div_exact_rcp(rng * dd, total, rcp_t);  // shrink_range
+        low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
         out[i++] = tab.idx2sym[idx];
         aec_model_update(F, c, idx, total);
         if (i == size) break;  // :242-243, before renormalising
