@@ -165,7 +165,14 @@ struct EncLaneV2 {
         gbegin = slot_begin;
         ovf = bad = 0;
     }
-    SCL_HD saddr_t ring_slot(uint32_t ofs) const { return ring + (ofs & ((kEncRingWords - 1) * 128)); }
+    // the device ring is 2 KiB-aligned, so the wrapped offset can be OR-ed in (one LOP3, no add)
+    SCL_HD saddr_t ring_slot(uint32_t ofs) const {
+#ifdef __CUDA_ARCH__
+        return ring | (ofs & ((kEncRingWords - 1) * 128));
+#else
+        return ring + (ofs & ((kEncRingWords - 1) * 128));
+#endif
+    }
 
     // one symbol: shrink_state + rans_base_encode_step (rANS.py:138-161), see scl_lane.cuh.
     // e = {thresh_m1, rcp, bias, cmpl << 16 | nb0 << 8 | shift}
@@ -199,9 +206,12 @@ struct EncLaneV2 {
     SCL_HD void drain_check() {
         if (wofs - rofs >= 8 * 128) {
             u32x8 s;
+            // rofs is always a multiple of 8 words, so the group is the lower or upper half of the
+            // 16-word ring: one address, eight immediate offsets
+            const saddr_t g = ring_slot(rofs);
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j)  // word base+7-j goes to the lowest address first
-                s.v[j] = bswap32(lds32(ring_slot(rofs + (7 - j) * 128)));
+                s.v[j] = bswap32(lds32(g + (7 - j) * 128));
             uint8_t *dst = gend - ((rofs >> 5) + 32);  // 4 * (words_drained + 8)
             if (dst >= gbegin)
                 st_sector32(dst, s);
@@ -256,6 +266,21 @@ struct EncLaneV2 {
         return bits;
     }
 };
+
+// Encode one full 16-symbol chunk (the hot path: fully unrolled, spill check after every 2nd symbol).
+template <uint32_t NBO, bool CHECK>
+SCL_HD void enc_chunk16(EncLaneV2 &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            L.template step<NBO, CHECK>(lds128(tab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)));
+            if (b & 1) L.spill_check();
+        }
+    }
+    L.drain_check();
+}
 
 // Encode `cnt` (<= 16) symbols held in a 16-byte chunk.  `tab` = address of this lane's replica
 // of entry 0; entry s is `sym_stride` bytes further per symbol (128 on the device: 8 replicas of
@@ -500,6 +525,20 @@ SCL_HD void tans_enc_step(EncLaneV2 &L, const u32x4 &e, saddr_t enc_table) {
     L.hi = funnel_r(L.hi, L.x, k);
     L.room -= k;
     L.x = lds32(enc_table + (saddr_t)(((L.x >> k) + e.z) << 2));  // base_encode_step_table[(s, x_shrunk)]
+}
+
+template <bool CHECK>
+SCL_HD void tans_enc_chunk16(EncLaneV2 &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v) {
+    const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            tans_enc_step<CHECK>(L, lds128(symtab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)), enc_table);
+            if (b & 1) L.spill_check();
+        }
+    }
+    L.drain_check();
 }
 
 template <bool CHECK>

@@ -203,7 +203,9 @@ template <int KIND, uint32_t NBO, bool CHECK>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
                           uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // round the dynamic window up to 2 KiB so that ring addresses can be composed with OR
+    uint8_t *smem = smem_raw + ((2048u - (smem_u32(smem_raw) & 2047u)) & 2047u);
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
     const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
@@ -251,17 +253,32 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             mbar_wait(my_bar + st, (tile_seq / kTileStages) & 1);
             const uint8_t *row = tiles + st * kTileBytes + lane * kTileCols;
             const uint32_t left = n - t * kTileCols;
-#pragma unroll 1
-            for (uint32_t ch = 0; ch < kTileCols / 16; ++ch) {
-                if (ch * 16 >= left) break;
-                const uint32_t cnt = left - ch * 16 >= 16 ? 16u : left - ch * 16;
-                const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));  // 64-byte TMA swizzle: conflict-free LDS.128
+            if (left >= kTileCols) {
+                // full tile: four whole chunks, no per-chunk bookkeeping
                 if (active) {
-                    u32x4 v = {q.x, q.y, q.z, q.w};
-                    if (KIND == 0)
-                        enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v, cnt);
-                    else
-                        tans_enc_chunk<CHECK>(L, my_tab, kEncTabCopies * 16, s_tab2, v, cnt);
+#pragma unroll 1
+                    for (uint32_t ch = 0; ch < kTileCols / 16; ++ch) {
+                        const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));  // 64-byte TMA swizzle: conflict-free LDS.128
+                        const u32x4 v = {q.x, q.y, q.z, q.w};
+                        if (KIND == 0)
+                            enc_chunk16<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v);
+                        else
+                            tans_enc_chunk16<CHECK>(L, my_tab, kEncTabCopies * 16, s_tab2, v);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t ch = 0; ch < kTileCols / 16; ++ch) {
+                    if (ch * 16 >= left) break;
+                    const uint32_t cnt = left - ch * 16 >= 16 ? 16u : left - ch * 16;
+                    const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));
+                    if (active) {
+                        u32x4 v = {q.x, q.y, q.z, q.w};
+                        if (KIND == 0)
+                            enc_chunk<NBO, CHECK>(L, my_tab, kEncTabCopies * 16, v, cnt);
+                        else
+                            tans_enc_chunk<CHECK>(L, my_tab, kEncTabCopies * 16, s_tab2, v, cnt);
+                    }
                 }
             }
             __syncwarp();
@@ -834,9 +851,9 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -1;
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t);
+    size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048;
     pick_launch(n_tasks, c->n_sm, max_warps_for(kEncWarpSmem, fixed), &grid, &warps);
-    size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t);
+    size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t) + 2048;
     cudaError_t e;
     if (rc.check_sym) {
         e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
