@@ -65,7 +65,8 @@ class EncodedBlocks:
         return int(self.bit_len.numel())
 
     def check(self):
-        raise_for_status(self.status)
+        if self.status is not None:
+            raise_for_status(self.status)
         return self
 
     def total_bytes(self) -> int:

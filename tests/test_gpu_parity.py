@@ -385,3 +385,31 @@ def test_tans_kernel_generations_agree(rf):
         ref_bytes, ref_bits = oracle.encode_block(host[b])
         got = e2.block(b)
         assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()
+
+
+def test_host_pipeline_roundtrip_matches_direct_api():
+    """HostCodecPipeline (pinned host buffers, chunked over two streams) must produce exactly the
+    packed bytes of the direct device API, for a block count that is not a multiple of the chunk."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.pipeline import HostCodecPipeline
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities
+
+    B, N = 5000, 1024
+    params = rANSParams(zipf_frequencies())
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=21, device="cuda:0")
+    host_in = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
+    host_in.copy_(data)
+    pipe = HostCodecPipeline(enc, dec, N, B, chunk_blocks=1536)
+    host_c = torch.empty(pipe.max_packed_bytes(), dtype=torch.uint8, pin_memory=True)
+    host_out = torch.zeros((B, N), dtype=torch.uint8, pin_memory=True)
+    for _ in range(2):  # second pass reuses every staging buffer
+        total, lens = pipe.encode(host_in, host_c)
+        direct = enc.encode_blocks(data).check()
+        packed = direct.pack()
+        assert torch.equal(lens, direct.bit_len.cpu())
+        assert total == direct.total_bytes()
+        assert torch.equal(host_c[:total], packed.buf[:total].cpu())
+        host_out.zero_()
+        pipe.decode(host_c, lens, host_out)
+        assert torch.equal(host_out, host_in)
