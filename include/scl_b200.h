@@ -153,8 +153,9 @@ int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, con
 int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries,
                             void *stream);
 
-/* Test hook: route the 32-bit rANS fast path to the first-generation kernels (per-lane direct
- * global access) instead of the TMA/ring kernels, so both generations stay parity-tested. */
+/* Test hook: 1 = route the fast paths to the first-generation kernels (per-lane direct global
+ * access) instead of the TMA/ring kernels; 2 = second-generation decode with per-lane sector
+ * stores instead of TMA tile stores; 0 = default.  Keeps every code path parity-tested. */
 void scl_debug_force_v1(int on);
 
 const char *scl_last_cuda_error(void);

@@ -449,66 +449,6 @@ SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
     D.x = x;
 }
 
-// rANSDecoder.decode_block (rANS.py:270-297) for one lane, v2 I/O.  `out` 32-byte aligned.
-template <uint32_t NBO>
-SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, saddr_t lut, const RansConst &c, uint8_t *out, uint64_t out_cap,
-                                      uint32_t &size_out, uint64_t &bits_consumed) {
-    uint64_t size64 = D.get64(c.DBSB);
-    D.x = D.get(c.NSB);
-    size_out = 0;
-    if (size64 > out_cap) return SCL_ST_OVERFLOW;
-    const uint32_t size = (uint32_t)size64;
-    DecConst dc;
-    dc.lut = lut;
-    dc.m4 = ((uint32_t)c.M - 1) << 2;
-    dc.xq_mul = c.m_log2 ? (1u << (32 - c.m_log2)) : 0u;  // M == 1: x >> 0 handled below
-    dc.kbase = 31 - c.l_log2;
-    dc.nbo = NBO;
-    uint32_t p = size;
-    if (c.m_log2 == 0) {
-        // degenerate single-symbol table with M == 1 (x >> 0 is not a multiply-high): plain loop
-        while (p > 0) {
-            uint32_t e = lds32(lut);
-            uint32_t x = (e >> 20) * D.x + ((e >> 8) & 0xFFFu);
-            uint32_t k = rans32_renorm_bits(x, c.l_log2, NBO);
-            uint32_t b = D.peek32();
-            D.x = funnel_l(b, x, k);
-            D.bp += k;
-            out[--p] = (uint8_t)(e & 0xFFu);
-            if ((p & 15) == 0) {
-                D.prefetch_begin();
-                D.prefetch_end();
-            }
-        }
-    }
-    // ragged head: bring p down to a multiple of 32 one symbol at a time
-    while (p & 31) {
-        uint32_t x = D.x, bits = D.peek32(), ks = 0, acc = 0;
-        dec_step<NBO, 0>(dc, x, bits, ks, acc);
-        D.x = x;
-        D.bp += ks;
-        out[--p] = (uint8_t)acc;
-        if ((p & 15) == 0) {  // keep the ring topped up on the same cadence as the main loop
-            D.prefetch_begin();
-            D.prefetch_end();
-        }
-    }
-    while (p >= 32) {
-        u32x8 o;
-        D.prefetch_begin();
-        dec_group16<NBO>(D, dc, &o.v[4]);
-        D.prefetch_end();
-        D.prefetch_begin();
-        dec_group16<NBO>(D, dc, &o.v[0]);
-        D.prefetch_end();
-        p -= 32;
-        st_sector32(out + p, o);
-    }
-    size_out = size;
-    bits_consumed = D.bp - D.start_bp;
-    return D.x == (uint32_t)c.L ? SCL_ST_OK : SCL_ST_STATE_MISMATCH;
-}
-
 // ------------------------------------------------------------------------------------------------
 // tANS on the same I/O machinery (tANS.py:126-157 / :239-250): the steps are pure table reads.
 //   symbol entry (16 B, 8 bank-rotated replicas) = {thresh, nb0, row - min_shrunk, pad}
@@ -604,45 +544,134 @@ SCL_HD void tans_dec_group16(DecLaneV2 &D, const TansDecConst &c, uint32_t w[4])
     D.x = x;
 }
 
-// tANSDecoder.decode_block (tANS.py:252-279) for one lane, v2 I/O
-SCL_HD uint32_t tans_decode_lane_v2(DecLaneV2 &D, saddr_t dec, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
-                                    uint64_t &bits_consumed) {
-    uint64_t size64 = D.get64(c.DBSB);
-    D.x = D.get(c.NSB);
-    size_out = 0;
-    if (size64 > out_cap) return SCL_ST_OVERFLOW;
-    const uint32_t size = (uint32_t)size64;
+// ------------------------------------------------------------------------------------------------
+// Stepper policies: the same decode driver (header, ragged head, 16-symbol groups) serves rANS
+// and tANS, and the kernels reuse the pieces for their tile-store main loop.
+// ------------------------------------------------------------------------------------------------
+template <uint32_t NBO>
+struct RansStepper {
+    DecConst dc;
+    uint32_t l_log2, m_log2;
+    SCL_HD void init(saddr_t lut, const RansConst &c) {
+        dc.lut = lut;
+        dc.m4 = ((uint32_t)c.M - 1) << 2;
+        dc.xq_mul = c.m_log2 ? (1u << (32 - c.m_log2)) : 0u;
+        dc.kbase = 31 - c.l_log2;
+        dc.nbo = NBO;
+        l_log2 = c.l_log2;
+        m_log2 = c.m_log2;
+    }
+    SCL_HD bool degenerate() const { return m_log2 == 0; }  // M == 1: x >> 0 is not a multiply-high
+    SCL_HD uint32_t one(DecLaneV2 &D) const {               // one symbol, returned as a byte
+        if (degenerate()) {
+            uint32_t e = lds32(dc.lut);
+            uint32_t x = (e >> 20) * D.x + ((e >> 8) & 0xFFFu);
+            uint32_t k = rans32_renorm_bits(x, l_log2, NBO);
+            D.x = funnel_l(D.peek32(), x, k);
+            D.bp += k;
+            return e & 0xFFu;
+        }
+        uint32_t x = D.x, bits = D.peek32(), ks = 0, acc = 0;
+        dec_step<NBO, 0>(dc, x, bits, ks, acc);
+        D.x = x;
+        D.bp += ks;
+        return acc & 0xFFu;
+    }
+    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { dec_group16<NBO>(D, dc, w); }
+};
+
+struct TansStepper {
     TansDecConst tc;
-    tc.dec = dec;
-    tc.L = (uint32_t)c.L;
-    tc.lmask4 = ((uint32_t)c.L - 1) << 2;
-    tc.kbase = 32 - c.NSB;
-    uint32_t p = size;
-    while (p & 31) {
+    SCL_HD void init(saddr_t dec, const RansConst &c) {
+        tc.dec = dec;
+        tc.L = (uint32_t)c.L;
+        tc.lmask4 = ((uint32_t)c.L - 1) << 2;
+        tc.kbase = 32 - c.NSB;
+    }
+    SCL_HD bool degenerate() const { return false; }
+    SCL_HD uint32_t one(DecLaneV2 &D) const {
         uint32_t x = D.x, bits = D.peek32(), ks = 0, acc = 0;
         tans_dec_step<0>(tc, x, bits, ks, acc);
         D.x = x;
         D.bp += ks;
-        out[--p] = (uint8_t)acc;
-        if ((p & 15) == 0) {
+        return acc & 0xFFu;
+    }
+    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { tans_dec_group16(D, tc, w); }
+};
+
+// header: [size : DBSB][state : NSB]; returns false (with *st set) when the size does not fit
+SCL_HD bool dec_read_header(DecLaneV2 &D, const RansConst &c, uint64_t out_cap, uint32_t &size, uint32_t &st) {
+    uint64_t size64 = D.get64(c.DBSB);
+    D.x = D.get(c.NSB);
+    size = 0;
+    if (size64 > out_cap) {
+        st = SCL_ST_OVERFLOW;
+        return false;
+    }
+    size = (uint32_t)size64;
+    return true;
+}
+
+// decode single symbols (stored bytewise) until p is a multiple of `align` (16, 32 or 64)
+template <class S>
+SCL_HD void dec_head(DecLaneV2 &D, const S &s, uint8_t *out, uint32_t &p, uint32_t align) {
+    while (p & (align - 1)) {
+        out[--p] = (uint8_t)s.one(D);
+        if ((p & 15) == 0) {  // keep the ring topped up on the same cadence as the main loop
             D.prefetch_begin();
             D.prefetch_end();
         }
     }
+}
+
+// per-lane sector stores for the rest of the block (p a multiple of 32)
+template <class S>
+SCL_HD void dec_body_sectors(DecLaneV2 &D, const S &s, uint8_t *out, uint32_t &p) {
     while (p >= 32) {
         u32x8 o;
         D.prefetch_begin();
-        tans_dec_group16(D, tc, &o.v[4]);
+        s.group16(D, &o.v[4]);
         D.prefetch_end();
         D.prefetch_begin();
-        tans_dec_group16(D, tc, &o.v[0]);
+        s.group16(D, &o.v[0]);
         D.prefetch_end();
         p -= 32;
         st_sector32(out + p, o);
     }
+}
+
+template <class S>
+SCL_HD uint32_t decode_lane_generic(DecLaneV2 &D, const S &s, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
+                                    uint64_t &bits_consumed) {
+    uint32_t size, st = SCL_ST_OK;
+    size_out = 0;
+    if (!dec_read_header(D, c, out_cap, size, st)) return st;
+    uint32_t p = size;
+    if (s.degenerate()) {
+        dec_head(D, s, out, p, 1u << 31);  // everything symbol by symbol
+        while (p) out[--p] = (uint8_t)s.one(D);
+    }
+    dec_head(D, s, out, p, 32);
+    dec_body_sectors(D, s, out, p);
     size_out = size;
     bits_consumed = D.bp - D.start_bp;
     return D.x == (uint32_t)c.L ? SCL_ST_OK : SCL_ST_STATE_MISMATCH;
+}
+
+// rANSDecoder.decode_block (rANS.py:270-297) / tANSDecoder.decode_block (tANS.py:252-279) for one
+// lane with per-lane sector stores (`out` 32-byte aligned)
+template <uint32_t NBO>
+SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, saddr_t lut, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
+                                      uint64_t &bits_consumed) {
+    RansStepper<NBO> s;
+    s.init(lut, c);
+    return decode_lane_generic(D, s, c, out, out_cap, size_out, bits_consumed);
+}
+SCL_HD uint32_t tans_decode_lane_v2(DecLaneV2 &D, saddr_t dec, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
+                                    uint64_t &bits_consumed) {
+    TansStepper s;
+    s.init(dec, c);
+    return decode_lane_generic(D, s, c, out, out_cap, size_out, bits_consumed);
 }
 
 }  // namespace scl

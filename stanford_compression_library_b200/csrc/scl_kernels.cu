@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder entry point is fetched at run time)
@@ -303,27 +304,91 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     }
 }
 
+// Decode.  Output goes through a per-warp 32 x 64-byte tile in shared memory (64-byte swizzle, so
+// each lane's STS.128 into its own row is conflict-free) that one lane hands to the TMA
+// (cp.async.bulk.tensor store, UTMASTG): the scattered per-lane sector stores leave the L1 data
+// pipe, which is the decoder's tightest resource (profiles/r1c).  Needs every block of the warp to
+// have the same size (it is read from the stream headers, so this is checked per task with
+// __all_sync); otherwise the warp falls back to per-lane sector stores.
+constexpr uint32_t kDecTileBytes = 32 * kTileCols;
+
 template <int KIND, uint32_t NBO>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
-    fast_decode_v2_kernel(const uint32_t *__restrict__ g_lut, uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
+    fast_decode_v2_kernel(const __grid_constant__ CUtensorMap out_map, uint32_t use_tiles, const uint32_t *__restrict__ g_lut,
+                          uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const saddr_t ring = saddr_of(smem + warp * kDecWarpSmem) + lane * 4;
-    const RansDec32 *s_lut = (const RansDec32 *)(smem + W * kDecWarpSmem);
+    uint8_t *tile = smem + warp * kDecTileBytes;
+    const saddr_t ring = saddr_of(smem + W * kDecTileBytes + warp * kDecWarpSmem) + lane * 4;
+    const uint32_t *s_lut = (const uint32_t *)(smem + W * (kDecTileBytes + kDecWarpSmem));
     stage_table((void *)s_lut, g_lut, lut_bytes, &mbar);
     const uint32_t total_warps = gridDim.x * W;
+    const uint32_t swz = (lane >> 1) & 3;
+    const saddr_t my_row = saddr_of(tile) + lane * kTileCols;
+    typename std::conditional<KIND == 0, RansStepper<NBO>, TansStepper>::type S;
+    S.init(saddr_of(s_lut), c);
+
     for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
         const uint64_t b = (uint64_t)task * 32 + lane;
-        if (b < io.n_blocks) {
-            DecLaneV2 D;
-            const uint64_t off = io.bit_off[b];
+        const bool active = b < io.n_blocks;
+        DecLaneV2 D;
+        uint32_t size = 0, st = SCL_ST_OK, p = 0;
+        uint64_t off = 0;
+        uint8_t *out = io.sym + (active ? b : 0) * io.sym_stride;
+        bool ok = false;
+        if (active) {
+            off = io.bit_off[b];
             D.init(io.in, io.in_bytes, off, ring);
-            uint32_t size = 0;
+            ok = dec_read_header(D, c, io.sym_stride, size, st);
+            p = size;
+        }
+        // warp-uniform tile path?
+        const uint32_t size0 = __shfl_sync(0xffffffffu, size, 0);
+        const bool tiles = use_tiles && !S.degenerate() && __all_sync(0xffffffffu, !active || (ok && size == size0));
+        if (tiles) {
+            if (active) dec_head(D, S, out, p, 64);
+            const uint32_t n_it = (size0 & ~63u) >> 6;  // same for every lane
+            for (uint32_t it = 0; it < n_it; ++it) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store has read the tile
+                __syncwarp();
+                if (active) {
+#pragma unroll 1
+                    for (int g = 3; g >= 0; --g) {
+                        uint32_t w[4];
+                        D.prefetch_begin();
+                        S.group16(D, w);
+                        D.prefetch_end();
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + ((g ^ swz) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                                     : "memory");
+                    }
+                    p -= 64;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA
+                __syncwarp();
+                if (lane == 0) {
+                    const int32_t col = (int32_t)((size0 & ~63u) - 64 * (it + 1));
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&out_map), "r"(col),
+                                 "r"((int32_t)(task * 32)), "r"(saddr_of(tile))
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+        } else if (active && ok) {
+            if (S.degenerate())
+                while (p) out[--p] = (uint8_t)S.one(D);
+            dec_head(D, S, out, p, 32);
+            dec_body_sectors(D, S, out, p);
+        }
+        if (active) {
             uint64_t used = 0;
-            uint32_t st = KIND == 0 ? rans32_decode_lane_v2<NBO>(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used)
-                                    : tans_decode_lane_v2(D, saddr_of(s_lut), c, io.sym + b * io.sym_stride, io.sym_stride, size, used);
-            if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+            if (ok) {
+                used = D.bp - D.start_bp;
+                st = D.x == (uint32_t)c.L ? SCL_ST_OK : SCL_ST_STATE_MISMATCH;
+                if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+            }
             io.sizes[b] = size;
             io.consumed[b] = used;
             io.status[b] = st;
@@ -828,8 +893,12 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
     *grid = (uint32_t)n_sm;
 }
 
+static bool g_no_tile_store = false;  // test hook (scl_debug_force_v1(2)): v2 decode with per-lane sector stores
 static bool g_force_v1 = false;  // test hook: scl_debug_force_v1(1) routes the fast path to the first-generation kernels
-extern "C" void scl_debug_force_v1(int on) { g_force_v1 = on != 0; }
+extern "C" void scl_debug_force_v1(int on) {
+    g_force_v1 = on == 1;
+    g_no_tile_store = on == 2;
+}
 
 static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
     size_t avail = 227 * 1024 - 1024 - fixed;  // 227 KiB per CTA minus slack for static smem / barriers
@@ -871,11 +940,24 @@ template <int KIND, uint32_t NBO>
 static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint32_t *lut, uint32_t lut_bytes, const DecodeIo &io,
                             cudaStream_t s) {
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem, lut_bytes), &grid, &warps);
-    size_t smem = (size_t)warps * kDecWarpSmem + lut_bytes;
+    pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem + kDecTileBytes, lut_bytes), &grid, &warps);
+    size_t smem = (size_t)warps * (kDecWarpSmem + kDecTileBytes) + lut_bytes;
+    // output tensor map for the TMA tile stores: rows = blocks, inner = the row capacity
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    uint32_t use_tiles = 0;
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (enc && io.sym_stride >= kTileCols && !g_no_tile_store) {
+        cuuint64_t gdim[2] = {io.sym_stride, io.n_blocks};
+        cuuint64_t gstr[1] = {io.sym_stride};
+        cuuint32_t box[2] = {kTileCols, 32};
+        cuuint32_t estr[2] = {1, 1};
+        use_tiles = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
     cudaError_t e = cudaFuncSetAttribute(fast_decode_v2_kernel<KIND, NBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    fast_decode_v2_kernel<KIND, NBO><<<grid, warps * 32, smem, s>>>(lut, lut_bytes, rc, io, n_tasks);
+    fast_decode_v2_kernel<KIND, NBO><<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks);
     return check_launch("fast_decode_v2_kernel");
 }
 

@@ -336,12 +336,14 @@ def test_rans_kernel_generations_agree(kw, shape):
         p2 = e2.pack()
         assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
         assert torch.equal(p1.buf, p2.buf)
-        d2 = dec.decode_blocks(e1, N).check()  # v2 decoder on v1 output
+        d2 = dec.decode_blocks(e1, N).check()  # v2 decoder (TMA tile stores) on v1 output
+        lib.scl_debug_force_v1(2)
+        d3 = dec.decode_blocks(e1, N).check()  # v2 decoder with per-lane sector stores
         lib.scl_debug_force_v1(1)
         d1 = dec.decode_blocks(e2, N).check()  # v1 decoder on v2 output
     finally:
         lib.scl_debug_force_v1(0)
-    for d in (d1, d2):
+    for d in (d1, d2, d3):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
         assert int(d.sizes.min()) == N == int(d.sizes.max())
     # and both against the oracle on a few blocks
