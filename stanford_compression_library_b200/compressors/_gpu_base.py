@@ -94,3 +94,45 @@ class GpuCoderBase:
 
     def _size_bits(self) -> int:
         return int(self.params.DATA_BLOCK_SIZE_BITS)
+
+
+def encode_uint8_file(encoder, input_file_path: str, encoded_file_path: str, block_size: int = 10000, blocks_per_batch: int = 65536):
+    """Batched counterpart of `DataEncoder.encode_file` for byte files: reads the input in batches of
+    `blocks_per_batch` blocks, encodes each batch in one launch and writes the reference's framed
+    format (scl/core/encoded_stream.py:150-175).  The output file is byte-identical to what
+    `encoder.encode(Uint8FileDataStream(...), block_size, EncodedBlockWriter(...))` produces."""
+    import torch
+
+    from ..core.data_stream import Uint8FileDataStream
+    from ..core.encoded_stream import EncodedBlockWriter
+
+    with Uint8FileDataStream(input_file_path, "rb") as fds, EncodedBlockWriter(encoded_file_path) as writer:
+        while True:
+            got = fds.get_blocks(block_size, blocks_per_batch)
+            if got is None:
+                break
+            data, sizes = got
+            ragged = int(sizes[-1]) != block_size
+            enc = encoder.encode_blocks(torch.from_numpy(data), sizes=torch.from_numpy(sizes) if ragged else None).check()
+            writer.write_encoded_blocks(enc)
+
+
+def decode_uint8_file(decoder, encoded_file_path: str, output_file_path: str, block_size: int = 10000):
+    """Batched counterpart of `DataDecoder.decode_file` for byte files written by the reference's
+    `EncodedBlockWriter` (or by `encode_uint8_file`)."""
+    from ..core.encoded_stream import EncodedBlockReader
+
+    with EncodedBlockReader(encoded_file_path) as reader, open(output_file_path, "wb") as out:
+        enc = reader.get_encoded_blocks(device=decoder.device_coder().device)
+        if enc.n_blocks == 0:
+            return
+        dec = decoder.decode_blocks(enc, block_size).check()
+        if not bool((dec.bits_consumed == enc.bit_len).all()):
+            raise AssertionError("num_bits_consumed != len(encoded_block)")  # data_encoder_decoder.py:141
+        sym = dec.symbols.cpu().numpy()
+        sizes = dec.sizes.cpu().numpy()
+        if (sizes == sym.shape[1]).all():
+            out.write(sym.tobytes())
+        else:
+            for b in range(sym.shape[0]):
+                out.write(sym[b, : sizes[b]].tobytes())
