@@ -149,6 +149,13 @@ int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, cons
 int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len,
                      uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream);
 
+/* Byte counts of n_blocks blocks: DataBlock.get_counts (scl/core/data_block.py:37-64) in bulk -- the
+ * step before the coders (build a Frequencies table from the data).  d_counts [n_blocks][256]
+ * uint32 per-block counts and/or d_total [256] uint64 ACCUMULATED grid-wide totals (zero it first);
+ * either may be NULL. */
+int scl_histogram_blocks(const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
+                         uint64_t n_blocks, uint32_t *d_counts, uint64_t *d_total, void *stream);
+
 /* ---- introspection (tests pin the tANS tables against tANS.py:285-337) -------------------- */
 int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries,
                             void *stream);

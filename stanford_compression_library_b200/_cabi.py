@@ -67,6 +67,8 @@ def lib():
     L.scl_frame_blocks.argtypes = [vp, vp, vp, u64, vp, vp, vp]
     L.scl_tans_tables_to_host.restype = i32
     L.scl_tans_tables_to_host.argtypes = [vp, vp, vp, u64, vp]
+    L.scl_histogram_blocks.restype = i32
+    L.scl_histogram_blocks.argtypes = [vp, u64, vp, u32, u64, vp, vp, vp]
     L.scl_debug_force_v1.restype = None
     L.scl_debug_force_v1.argtypes = [i32]
     L.scl_last_cuda_error.restype = ctypes.c_char_p
@@ -77,7 +79,7 @@ def lib():
 
 EXPORTS = [
     "scl_coder_create", "scl_coder_destroy", "scl_coder_max_encoded_bytes", "scl_coder_path", "scl_encode_blocks",
-    "scl_decode_blocks", "scl_pack_blocks", "scl_frame_blocks", "scl_tans_tables_to_host", "scl_debug_force_v1", "scl_last_cuda_error", "scl_version",
+    "scl_decode_blocks", "scl_pack_blocks", "scl_frame_blocks", "scl_tans_tables_to_host", "scl_histogram_blocks", "scl_debug_force_v1", "scl_last_cuda_error", "scl_version",
 ]
 
 

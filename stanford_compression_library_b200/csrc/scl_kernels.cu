@@ -655,6 +655,59 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const uint8_t *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Byte histograms: DataBlock.get_counts (scl/core/data_block.py:37-64) for a batch of blocks, the
+// step before the coders.  One warp per block; each lane streams 16-byte
+// pieces of the row (coalesced 512 B per warp load) into one of 4 lane-interleaved sub-histograms
+// in shared memory (cuts same-bin atomic contention on skewed data), then the warp writes the
+// block's 256 counts and/or folds them into a grid-wide total.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHistWarps = 8;
+__global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(const uint8_t *__restrict__ sym, uint64_t sym_stride,
+                                                                    const uint32_t *__restrict__ sizes, uint32_t block_len, uint64_t n_blocks,
+                                                                    uint32_t *__restrict__ counts, unsigned long long *__restrict__ total) {
+    __shared__ uint32_t s_hist[kHistWarps][4][256];
+    __shared__ uint32_t s_total[256];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_total[i] = 0;
+    __syncthreads();
+    uint32_t(*h)[256] = s_hist[warp];
+    for (uint64_t b = (uint64_t)blockIdx.x * kHistWarps + warp; b < n_blocks; b += (uint64_t)gridDim.x * kHistWarps) {
+        for (uint32_t i = lane; i < 4 * 256; i += 32) (&h[0][0])[i] = 0;
+        __syncwarp();
+        const uint8_t *row = sym + b * sym_stride;
+        const uint32_t n = sizes ? sizes[b] : block_len;
+        uint32_t *mine = h[lane & 3];
+        uint32_t i = 0;
+        if ((((uintptr_t)row) & 15) == 0) {
+            for (uint32_t base = 0; base + 512 <= n; base += 512) {
+                const uint4 q = *(const uint4 *)(row + base + lane * 16);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    atomicAdd(&mine[w[j] & 0xFFu], 1u);
+                    atomicAdd(&mine[(w[j] >> 8) & 0xFFu], 1u);
+                    atomicAdd(&mine[(w[j] >> 16) & 0xFFu], 1u);
+                    atomicAdd(&mine[w[j] >> 24], 1u);
+                }
+                i = base + 512;
+            }
+        }
+        for (uint32_t k = i + lane; k < n; k += 32) atomicAdd(&mine[row[k]], 1u);
+        __syncwarp();
+        for (uint32_t v = lane; v < 256; v += 32) {
+            uint32_t c = h[0][v] + h[1][v] + h[2][v] + h[3][v];
+            if (counts) counts[b * 256 + v] = c;
+            if (total && c) atomicAdd(&s_total[v], c);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (total)
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+            if (s_total[i]) atomicAdd(&total[i], (unsigned long long)s_total[i]);
+}
+
 }  // namespace scl
 
 // ====================================================================================================
@@ -1105,4 +1158,20 @@ extern "C" int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, 
     SCL_CUDA(cudaMemcpyAsync(dec_packed, c->d_tdec, n_entries * 4, cudaMemcpyDeviceToHost, s));
     SCL_CUDA(cudaStreamSynchronize(s));
     return SCL_E_OK;
+}
+
+extern "C" int scl_histogram_blocks(const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len, uint64_t n_blocks,
+                                    uint32_t *d_counts, uint64_t *d_total, void *stream) {
+    if (!d_sym || (!d_counts && !d_total)) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t want = (n_blocks + kHistWarps - 1) / kHistWarps;
+    uint32_t grid = (uint32_t)(want < (uint64_t)n_sm * 4 ? want : (uint64_t)n_sm * 4);  // <= 4 CTAs per SM, grid-stride over blocks
+    // s_total is 32-bit per CTA: bound the bytes one CTA can see
+    if ((n_blocks / grid + 1) * kHistWarps * (uint64_t)block_len >= (1ull << 32)) return SCL_E_UNSUPPORTED;
+    histogram_kernel<<<grid, kHistWarps * 32, 0, (cudaStream_t)stream>>>(d_sym, sym_stride, d_sizes, block_len, n_blocks, d_counts,
+                                                                       (unsigned long long *)d_total);
+    return check_launch("histogram_kernel");
 }

@@ -455,3 +455,44 @@ def test_file_level_roundtrip_and_reference_file_format(tmp_path):
     rANSEncoder(tparams).encode_file(tsrc, tenc, block_size=500)
     rANSDecoder(tparams).decode_file(tenc, tback)
     assert open(tback).read() == text
+
+
+def test_histogram_blocks_vs_numpy_and_end_to_end_model():
+    """§8(f) row 2: device histogram == DataBlock.get_counts semantics (numpy restatement), and a table
+    built from the data itself (normalised to 2^12) codes that data bit-exactly like the oracle."""
+    from stanford_compression_library_b200 import DataBlock
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.stats import empirical_frequencies, histogram_blocks
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    B, N = 777, 4096 + 48
+    data = sample_blocks(zipf_probabilities(), B, N, seed=31, device="cuda:0")
+    data[:, ::7] = 0  # extra contention on one bin
+    sizes = torch.randint(0, N + 1, (B,), device="cuda:0", dtype=torch.int32)
+    host = data.cpu().numpy()
+    for sz in (None, sizes):
+        counts, tot = histogram_blocks(data, sizes=sz)
+        hs = np.full(B, N) if sz is None else sz.cpu().numpy()
+        ref = np.stack([np.bincount(host[b, : hs[b]], minlength=256) for b in range(B)])
+        assert np.array_equal(counts.cpu().numpy(), ref)
+        assert np.array_equal(tot.cpu().numpy(), ref.sum(0))
+    # same numbers as the reference-style host method on one block
+    blk = DataBlock(host[3].tolist())
+    gc = blk.get_counts()
+    assert all(gc.get(v, 0) == int(ref_v) for v, ref_v in enumerate(np.bincount(host[3], minlength=256)))
+    # model from data -> code the data
+    freqs = empirical_frequencies(data, total_freq=4096)
+    assert int(freqs.total_freq) == 4096
+    params = rANSParams(freqs)
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    e = enc.encode_blocks(data).check()
+    d = dec.decode_blocks(e, N).check()
+    assert torch.equal(d.symbols[:, :N], data)
+    alpha = list(freqs.freq_dict)
+    oracle = so.Oracle.rans([freqs.freq_dict[a] for a in alpha])
+    idx_of = np.full(256, 255, dtype=np.uint8)
+    idx_of[alpha] = np.arange(len(alpha), dtype=np.uint8)
+    for b in (0, B - 1):
+        ref_bytes, ref_bits = oracle.encode_block(idx_of[host[b]])
+        got = e.block(b)
+        assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()

@@ -118,3 +118,26 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "scl_oracle" not in src, fn
+
+
+def test_normalize_frequencies_properties():
+    from stanford_compression_library_b200.stats import normalize_frequencies
+
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        n = int(rng.integers(1, 257))
+        c = np.zeros(256, dtype=np.int64)
+        idx = rng.choice(256, size=n, replace=False)
+        c[idx] = rng.integers(1, 10 ** int(rng.integers(1, 7)), size=n)
+        M = int(rng.choice([256, 1024, 4096, 1 << 16]))
+        if n > M:
+            continue
+        f = normalize_frequencies(c, M)
+        assert sum(f.freq_dict.values()) == M and min(f.freq_dict.values()) >= 1
+        assert list(f.freq_dict) == sorted(int(i) for i in idx)  # ascending byte order, only symbols that occur
+    # the benchmark table: Zipf-1.0 expected counts reproduce SURVEY 8(d)'s quantiser exactly
+    from stanford_compression_library_b200.workloads import zipf_freq_list, zipf_probabilities
+
+    p = np.array(zipf_probabilities())
+    f = normalize_frequencies(np.round(p * 1e9).astype(np.int64), 4096)
+    assert [f.freq_dict[b] for b in range(256)] == zipf_freq_list()

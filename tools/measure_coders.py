@@ -48,6 +48,13 @@ def main():
     p = zipf_probabilities()
     d4k = sample_blocks(p, 65536, 4096, seed=0, device="cuda:0")
     d1k = sample_blocks(p, 262144, 1024, seed=1, device="cuda:0")
+    from stanford_compression_library_b200.stats import histogram_blocks
+    big = sample_blocks(p, 262144, 4096, seed=2, device="cuda:0")
+    th = timeit(lambda: histogram_blocks(big, per_block=False))
+    tb = timeit(lambda: histogram_blocks(big, total=False))
+    print(json.dumps(dict(coder="histogram 262144 x 4 KiB", total_only_ms=th, total_only_GBps=big.numel() / th / 1e6, roofline_frac=big.numel() / th / 1e6 / 6458.4,
+                          per_block_ms=tb, per_block_GBps=big.numel() / tb / 1e6)))
+    del big
     run("rANS default (cfg2)", rANSEncoder(rANSParams(fr)), rANSDecoder(rANSParams(fr)), d4k)
     run("rANS nbo8 rf4096 (cfg2)", rANSEncoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), rANSDecoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), d4k)
     tp = tANSParams(fr, RANGE_FACTOR=1)
