@@ -1,0 +1,369 @@
+// scl_aec.cuh -- second-generation arithmetic-coder lanes (arithmetic_coding.py:58-161,177-287 with
+// FixedFreqModel / AdaptiveIIDFreqModel, probability_models.py:57-92).
+//
+// The first-generation lanes (scl_lane.cuh) follow the reference loop by loop; on the GPU that means
+// data-dependent trip counts everywhere (Fenwick walks, one renormalisation iteration per bit) and
+// the profile shows it: 1146 warp-instructions per symbol with 15 of 32 lanes active
+// (profiles/r1e).  Here every per-symbol step has a fixed instruction sequence:
+//   * the 256 counters live in a two-level radix-16 structure of packed 16-bit pairs
+//     (8 words of group totals + 128 words of counts per lane, lane-interleaved in shared memory);
+//     cumulative counts are masked dot products (dp2a) over 8 words per level;
+//   * the E1/E2 loop (":126-143") and the E3 loop (":146-150") are evaluated in closed form from
+//     leading/trailing bit counts, including the reference's strict `<` / `>` boundary cases;
+//   * x // T is one FP64 multiply with an exact integer correction (div_exact_rcp).
+// Usable when every counter and group total stays below 65536 (host-checked); otherwise the
+// first-generation kernel runs.  __host__ __device__ throughout: tests/host_emu checks these
+// against the oracle on the CPU.
+#pragma once
+#include "scl_fast.cuh"
+
+namespace scl {
+
+constexpr uint32_t kAecModelWords = 8 + 128;  // G[16] + C[256] as u16 pairs
+
+SCL_HD uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {  // c + a.u16[0]*b.u8[0] + a.u16[1]*b.u8[1]
+#ifdef __CUDA_ARCH__
+    return __dp2a_lo(a, b, c);
+#else
+    return c + (a & 0xFFFFu) * (b & 0xFFu) + (a >> 16) * ((b >> 8) & 0xFFu);
+#endif
+}
+SCL_HD uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {  // c + a.u16[0]*b.u8[2] + a.u16[1]*b.u8[3]
+#ifdef __CUDA_ARCH__
+    return __dp2a_hi(a, b, c);
+#else
+    return c + (a & 0xFFFFu) * ((b >> 16) & 0xFFu) + (a >> 16) * (b >> 24);
+#endif
+}
+SCL_HD uint32_t ctz32(uint32_t x) {  // 32 for x == 0
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)__brev(x));
+#else
+    return x ? (uint32_t)__builtin_ctz(x) : 32u;
+#endif
+}
+
+// The model of one lane.  `w` = address of word 0 of this lane; word i is `stride` bytes further
+// (128 on the device: [word][lane] interleave, one bank per lane; 4 on the host).
+// `masks` = address of this lane's replica of the prefix-mask table: entry t (0..16) is 16 bytes
+// whose first t bytes are 1 (entry stride `mstride`: 128 on the device = 8 replicas x 16 B).
+struct AecModel {
+    saddr_t w;
+    uint32_t stride;
+    saddr_t masks;
+    uint32_t mstride;
+    SCL_HD uint32_t word(uint32_t i) const { return lds32(w + (saddr_t)(i * stride)); }
+    SCL_HD void set_word(uint32_t i, uint32_t v) const { sts32(w + (saddr_t)(i * stride), v); }
+
+    // sum of the first t (0..16) of the 16 packed values in words [first, first+8)
+    SCL_HD uint32_t masked_sum(uint32_t first, uint32_t t) const {
+        const u32x4 m = lds128(masks + (saddr_t)(t * mstride));
+        const saddr_t a = w + (saddr_t)(first * stride);
+        uint32_t s = 0;
+        s = dp2a_lo(lds32(a), m.x, s);
+        s = dp2a_hi(lds32(a + (saddr_t)(1 * stride)), m.x, s);
+        s = dp2a_lo(lds32(a + (saddr_t)(2 * stride)), m.y, s);
+        s = dp2a_hi(lds32(a + (saddr_t)(3 * stride)), m.y, s);
+        s = dp2a_lo(lds32(a + (saddr_t)(4 * stride)), m.z, s);
+        s = dp2a_hi(lds32(a + (saddr_t)(5 * stride)), m.z, s);
+        s = dp2a_lo(lds32(a + (saddr_t)(6 * stride)), m.w, s);
+        s = dp2a_hi(lds32(a + (saddr_t)(7 * stride)), m.w, s);
+        return s;
+    }
+    SCL_HD uint32_t count(uint32_t idx) const {  // freq of alphabet index idx
+        uint32_t wv = word(8 + (idx >> 1));
+        return (idx & 1) ? (wv >> 16) : (wv & 0xFFFFu);
+    }
+    // cumulative count below idx (cumulative_freq_dict, prob_dist.py:193-205) and the count itself
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const {
+        const uint32_t hi = idx >> 4, lo = idx & 15;
+        cum = masked_sum(0, hi) + masked_sum(8 + hi * 8, lo);
+        f = count(idx);
+    }
+    SCL_HD void add1(uint32_t idx) const {  // freq_dict[s] += 1
+        const uint32_t cw = 8 + (idx >> 1), gw = idx >> 5;
+        set_word(cw, word(cw) + ((idx & 1) ? 0x10000u : 1u));
+        set_word(gw, word(gw) + (((idx >> 4) & 1) ? 0x10000u : 1u));
+    }
+    // last index whose cumulative count is <= v (numpy.searchsorted(side="right") - 1); v < total
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        uint32_t pre = 0, hi = 0, base = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            uint32_t wv = word(j);
+            uint32_t t1 = pre + (wv & 0xFFFFu), t2 = t1 + (wv >> 16);
+            bool c1 = t1 <= v, c2 = t2 <= v;  // inclusive prefixes are non-decreasing: true..true false..false
+            hi += (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+            base = c2 ? t2 : (c1 ? t1 : base);
+            pre = t2;
+        }
+        hi = hi > 15 ? 15 : hi;
+        uint32_t lo = 0, b2 = base;
+        pre = base;
+        const uint32_t first = 8 + hi * 8;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            uint32_t wv = word(first + j);
+            uint32_t t1 = pre + (wv & 0xFFFFu), t2 = t1 + (wv >> 16);
+            bool c1 = t1 <= v, c2 = t2 <= v;
+            lo += (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+            b2 = c2 ? t2 : (c1 ? t1 : b2);
+            pre = t2;
+        }
+        lo = lo > 15 ? 15 : lo;
+        const uint32_t idx = hi * 16 + lo;
+        cum = b2;
+        f = count(idx);
+        return idx;
+    }
+    SCL_HD void load(const uint32_t *init_freq, const uint64_t *model, uint32_t n_sym, uint64_t &total) const {
+        total = 0;
+        for (uint32_t g = 0; g < 16; g += 2) {
+            uint32_t gs[2] = {0, 0};
+            for (uint32_t h = 0; h < 2; ++h)
+                for (uint32_t j = 0; j < 16; j += 2) {
+                    uint32_t i0 = (g + h) * 16 + j;
+                    uint32_t f0 = i0 < n_sym ? (model ? (uint32_t)model[i0] : init_freq[i0]) : 0u;
+                    uint32_t f1 = i0 + 1 < n_sym ? (model ? (uint32_t)model[i0 + 1] : init_freq[i0 + 1]) : 0u;
+                    set_word(8 + (i0 >> 1), f0 | (f1 << 16));
+                    gs[h] += f0 + f1;
+                }
+            set_word(g >> 1, gs[0] | (gs[1] << 16));
+            total += gs[0] + gs[1];
+        }
+    }
+    SCL_HD void store(uint64_t *model, uint32_t n_sym) const {
+        for (uint32_t i = 0; i < n_sym; ++i) model[i] = count(i);
+    }
+    // AdaptiveIIDFreqModel's halving (probability_models.py:90-92): f = max(f // 2, 1) for every symbol
+    SCL_HD void halve(uint32_t n_sym, uint64_t &total) const {
+        total = 0;
+        for (uint32_t g = 0; g < 16; ++g) {
+            uint32_t gsum = 0;
+            for (uint32_t j = 0; j < 16; ++j) {
+                uint32_t i = g * 16 + j;
+                if (i < n_sym) {
+                    uint32_t h = count(i) >> 1;
+                    h = h > 1 ? h : 1;
+                    uint32_t cw = 8 + (i >> 1), wv = word(cw);
+                    set_word(cw, (i & 1) ? ((wv & 0xFFFFu) | (h << 16)) : ((wv & 0xFFFF0000u) | h));
+                    gsum += h;
+                }
+            }
+            uint32_t gw = g >> 1, wv = word(gw);
+            set_word(gw, (g & 1) ? ((wv & 0xFFFFu) | (gsum << 16)) : ((wv & 0xFFFF0000u) | gsum));
+            total += gsum;
+        }
+    }
+};
+
+// ---- closed-form renormalisation ------------------------------------------------------------
+// State: low in [0, 2^P), high in (low, 2^P].  Let hm = high - 1.
+// E1/E2 loop (:126-143): every iteration drops a COMMON leading bit of low and hm.  The reference's
+// strict tests stop one iteration early in two boundary cases: high == HALF (hm == 0111..1, reached
+// at iteration j_A = P-1-cto(hm)) and low == HALF (1000..0, at j_B = P-1-ctz(low)).  So
+//   n = min(leading common bits of (low, hm), j_A, j_B).
+SCL_HD uint32_t aec_e12_count(uint64_t low, uint64_t high, uint32_t P) {
+    const uint32_t lo = (uint32_t)low, hm = (uint32_t)(high - 1);
+    const uint32_t sh = 32 - P;
+    uint32_t x = (lo ^ hm) << sh;  // P-bit view aligned to bit 31
+    uint32_t n = x ? clz32(x) : P;
+    const uint32_t full = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u);
+    if (hm != full) {
+        uint32_t jA = P - 1 - ctz32(~hm);  // ctz(~hm) = number of trailing ones
+        n = jA < n ? jA : n;
+    }
+    if (lo != 0) {
+        uint32_t jB = P - 1 - ctz32(lo);
+        n = jB < n ? jB : n;
+    }
+    return n;
+}
+// E3 loop (:146-150): every iteration deletes bit P-2 of low and hm (keeping the top bits).  It runs
+// while low > QTR and high < 3*QTR, i.e. (top bit of low set, or low = 01.. and not exactly QTR) and
+// (top bit of hm clear, or hm = 10.. and not exactly 3*QTR-1): runs of ones / zeros below the top bit,
+// shortened by one when the run ends at the lowest set bit of low / lowest clear bit of hm.
+SCL_HD uint32_t aec_e3_count(uint64_t low, uint64_t high, uint32_t P) {
+    const uint32_t lo = (uint32_t)low, hm = (uint32_t)(high - 1);
+    const uint32_t top = 1u << (P - 1);
+    uint32_t m = 0xFFFFFFFFu;
+    const uint32_t sh = 33 - P;  // drops the top bit, aligns bit P-2 to bit 31 (P >= 2; sh == 32 handled for P == 1 never)
+    if (!(lo & top)) {
+        uint32_t body = sh >= 32 ? 0u : (lo << sh);
+        uint32_t r1 = clz32(~body);  // leading ones
+        r1 = r1 > P - 1 ? P - 1 : r1;
+        if (r1 > 0 && ctz32(lo) == P - 1 - r1) r1 -= 1;
+        m = r1;
+    }
+    if (hm & top) {
+        uint32_t body = sh >= 32 ? 0u : (hm << sh);
+        uint32_t r0 = clz32(body);  // leading zeros
+        r0 = r0 > P - 1 ? P - 1 : r0;
+        if (r0 > 0 && ctz32(~hm) == P - 1 - r0) r0 -= 1;
+        m = r0 < m ? r0 : m;
+    }
+    return m == 0xFFFFFFFFu ? 0u : m;
+}
+// n E1/E2 steps: v -> 2^n v - prefix * 2^P  (prefix = top n bits of low); exact in 64-bit integers
+SCL_HD void aec_apply_e12(uint64_t &low, uint64_t &high, uint32_t n, uint32_t P, uint32_t &prefix) {
+    prefix = n ? (uint32_t)(low >> (P - n)) : 0u;
+    const uint64_t sub = (uint64_t)prefix << P;
+    low = (low << n) - sub;
+    high = (high << n) - sub;
+}
+// m E3 steps: v -> 2^m (v - HALF) + HALF
+SCL_HD uint64_t aec_apply_e3(uint64_t v, uint32_t m, uint32_t P) {
+    const uint64_t half = 1ull << (P - 1);
+    return ((v - half) << m) + half;  // unsigned wrap-around == the signed identity (results are in [0, 2^P])
+}
+
+// ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
+SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, const uint8_t *sym, uint32_t n,
+                                 FwdBitWriter &w, uint64_t &bits_out, uint64_t &total_out) {
+    const uint32_t P = c.P;
+    const uint64_t FULL = 1ull << P, QTR = 1ull << (P - 2);
+    uint64_t low = 0, high = FULL, num_mid = 0;
+    uint32_t st = SCL_ST_OK;
+    if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
+    w.put64((uint64_t)n, c.DBSB);
+    for (uint32_t i = 0; i < n && st == SCL_ST_OK; ++i) {
+        const uint32_t idx = tab.sym2idx[sym[i]];
+        if (idx == 0xFFFFu) {
+            st = SCL_ST_BAD_SYMBOL;
+            break;
+        }
+        if (!(total < QTR)) {  // :110-112
+            st = SCL_ST_TOTAL_FREQ;
+            break;
+        }
+        uint32_t cc, f;
+        M.query(idx, cc, f);
+        const uint64_t rng = high - low;
+        const double rcp_t = 1.0 / (double)total;
+        high = low + div_exact_rcp(rng * (uint64_t)(cc + f), total, rcp_t);  // shrink_range (:58-78)
+        low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
+        if (c.model == SCL_MODEL_ADAPTIVE_IID) {  // update_model (:118)
+            M.add1(idx);
+            total += 1;
+            if (total >= c.max_total) M.halve(c.n_sym, total);
+        }
+        const uint32_t ne = aec_e12_count(low, high, P);
+        if (ne) {
+            uint32_t prefix;
+            aec_apply_e12(low, high, ne, P, prefix);
+            const uint32_t b0 = (prefix >> (ne - 1)) & 1u;  // first released bit, then the pending opposite bits
+            w.put(b0, 1);
+            w.put_run(b0 ^ 1u, num_mid);
+            num_mid = 0;
+            if (ne > 1) w.put(prefix & mask32(ne - 1), ne - 1);
+        }
+        const uint32_t me = aec_e3_count(low, high, P);
+        if (me) {
+            num_mid += me;
+            low = aec_apply_e3(low, me, P);
+            high = aec_apply_e3(high, me, P);
+        }
+        if (w.ovf) break;
+    }
+    num_mid += 1;  // :153-159
+    if (low <= QTR) {
+        w.put(0, 1);
+        w.put_run(1, num_mid);
+    } else {
+        w.put(1, 1);
+        w.put_run(0, num_mid);
+    }
+    bits_out = w.finish();
+    total_out = total;
+    if (w.ovf) st = SCL_ST_OVERFLOW;
+    return st;
+}
+
+// next k (<= 32) bits of the arithmetic stream with zero fill past its end (`A` bits, :258-261)
+SCL_HD uint32_t aec_get_bits(BitReader &r, uint64_t &nbc, uint64_t A, uint32_t k) {
+    uint32_t v = 0;
+    if (k) {
+        if (nbc + k <= A) {
+            v = r.get(k);
+        } else {
+            uint32_t have = nbc < A ? (uint32_t)(A - nbc) : 0u;  // < k
+            v = have ? (r.get(have) << (k - have)) : 0u;
+        }
+    }
+    nbc += k;
+    return v;
+}
+
+// ArithmeticDecoder.decode_block (arithmetic_coding.py:203-287)
+SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, BitReader &r,
+                                 uint64_t avail_bits, uint8_t *out, uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed,
+                                 uint64_t &total_out) {
+    const uint32_t P = c.P;
+    const uint64_t FULL = 1ull << P, QTR = 1ull << (P - 2);
+    uint64_t size64 = r.get64(c.DBSB);
+    size_out = 0;
+    total_out = total;
+    if (size64 > out_cap) return SCL_ST_OVERFLOW;
+    if (size64 == 0) return SCL_ST_EMPTY_BLOCK;
+    const uint32_t size = (uint32_t)size64;
+    const uint64_t A = avail_bits > c.DBSB ? avail_bits - c.DBSB : 0;
+    uint64_t nbc = 0, low = 0, high = FULL;
+    uint64_t state = aec_get_bits(r, nbc, A, P);  // :222-229 (MSB first, zero fill)
+    uint32_t st = SCL_ST_OK;
+    for (uint32_t i = 0;;) {
+        if (!(total < QTR)) {
+            st = SCL_ST_TOTAL_FREQ;
+            break;
+        }
+        const uint64_t rng = high - low;
+        uint32_t idx, cc, f;
+        if (state < low) {
+            idx = c.n_sym - 1;  // searchsorted -> 0, alphabet[-1]
+            M.query(idx, cc, f);
+        } else {
+            uint64_t v = div_exact_rcp((state - low + 1) * total - 1, rng, 1.0 / (double)rng);  // decode_step_core (:177-201)
+            if (v >= total) v = total - 1;
+            idx = M.find((uint32_t)v, cc, f);
+            if (idx >= c.n_sym) {
+                idx = c.n_sym - 1;
+                M.query(idx, cc, f);
+            }
+        }
+        const double rcp_t = 1.0 / (double)total;
+        high = low + div_exact_rcp(rng * (uint64_t)(cc + f), total, rcp_t);
+        low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
+        out[i++] = tab.idx2sym[idx];
+        if (c.model == SCL_MODEL_ADAPTIVE_IID) {
+            M.add1(idx);
+            total += 1;
+            if (total >= c.max_total) M.halve(c.n_sym, total);
+        }
+        if (i == size) break;  // :242-243
+        const uint32_t ne = aec_e12_count(low, high, P);
+        if (ne) {
+            uint32_t prefix;
+            aec_apply_e12(low, high, ne, P, prefix);
+            // the reference subtracts HALF from `state` exactly when it does so for low/high (:252-256)
+            state = (state << ne) - ((uint64_t)prefix << P) + aec_get_bits(r, nbc, A, ne);
+        }
+        const uint32_t me = aec_e3_count(low, high, P);
+        if (me) {
+            low = aec_apply_e3(low, me, P);
+            high = aec_apply_e3(high, me, P);
+            state = aec_apply_e3(state, me, P) + aec_get_bits(r, nbc, A, me);
+        }
+    }
+    uint32_t extra = 0;  // :277-282
+    for (extra = 0; extra < P; ++extra) {
+        uint64_t state_low = (state >> extra) << extra;
+        uint64_t state_high = state_low + (1ull << extra);
+        if (state_low < low || state_high > high) break;
+    }
+    if (extra == P) extra = P - 1;
+    size_out = size;
+    total_out = total;
+    bits_consumed = (uint64_t)((int64_t)nbc - ((int64_t)extra - 1) + (int64_t)c.DBSB);
+    return st;
+}
+
+}  // namespace scl

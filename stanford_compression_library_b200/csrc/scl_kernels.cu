@@ -15,6 +15,7 @@
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder entry point is fetched at run time)
 
+#include "scl_aec.cuh"
 #include "scl_fast.cuh"
 #include "scl_lane.cuh"
 #include "scl_tables.hpp"
@@ -591,6 +592,74 @@ __global__ void __launch_bounds__(kAecThreads) aec_decode_kernel(const AecTab *_
 }
 
 // ------------------------------------------------------------------------------------------------
+// arithmetic coder, second generation (scl_aec.cuh): 4 warps per CTA, per-lane two-level count
+// structure in shared memory ([word][lane] interleave), prefix-mask table in 8 bank-rotated replicas.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kAec2Warps = 4;
+constexpr uint32_t kAec2ModelBytes = kAecModelWords * 128;      // per warp
+constexpr uint32_t kAec2MaskBytes = 17 * kEncTabCopies * 16;    // 17 entries x 8 replicas x 16 B
+
+struct Aec2Smem {
+    AecModel M;
+};
+__device__ __forceinline__ AecModel aec2_setup(uint8_t *smem, const AecTab *g_tab, AecTab *s_tab, uint64_t *mbar) {
+    // smem: [mask table][models per warp]
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *masks = smem;
+    for (uint32_t i = threadIdx.x; i < 17 * kEncTabCopies * 16; i += blockDim.x) {
+        uint32_t t = i / (kEncTabCopies * 16), k = i % 16;
+        masks[i] = k < t ? 1 : 0;
+    }
+    stage_table(s_tab, g_tab, sizeof(AecTab), mbar);  // includes a __syncthreads
+    __syncthreads();
+    AecModel M;
+    M.w = saddr_of(smem + kAec2MaskBytes + warp * kAec2ModelBytes) + lane * 4;
+    M.stride = 128;
+    M.masks = saddr_of(masks) + (lane & (kEncTabCopies - 1)) * 16;
+    M.mstride = kEncTabCopies * 16;
+    return M;
+}
+
+__global__ void __launch_bounds__(kAec2Warps * 32) aec2_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    const AecModel M = aec2_setup(s_dyn, g_tab, &s_tab, &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint64_t total = 0, total_out = 0, bits = 0;
+    M.load(s_tab.init_freq, nullptr, c.n_sym, total);
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint32_t st = aec2_encode_lane(M, s_tab, c, total, io.sym + b * io.sym_stride, n, w, bits, total_out);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kAec2Warps * 32) aec2_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    const AecModel M = aec2_setup(s_dyn, g_tab, &s_tab, &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint64_t total = 0, total_out = 0, used = 0;
+    M.load(s_tab.init_freq, nullptr, c.n_sym, total);
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint32_t st = aec2_decode_lane(M, s_tab, c, total, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used,
+                                   total_out);
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stream packing: bit-granular copy of each block's stream to a byte-aligned destination
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t src_byte_at_bit(const uint8_t *src, uint64_t pos) {  // 8 bits starting at bit `pos`
@@ -1070,7 +1139,15 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         // one per coded symbol (a caller-supplied d_model may hold anything, so it takes the 32-bit tree)
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
-        if (!d_model && max_init + block_len < 65536 && !g_force_v1)
+        // second generation: every counter and group total must stay below 65536
+        if (!d_model && 16 * max_init + block_len < 65536 && !g_force_v1) {
+            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
+            size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;
+            SCL_CUDA(cudaFuncSetAttribute(aec2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            aec2_encode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            return check_launch("aec2_encode_kernel");
+        }
+        if (!d_model && max_init + block_len < 65536)
             aec_encode_kernel<SmemTree16><<<g, kAecThreads, SmemTree16::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
         else
             aec_encode_kernel<SmemTree><<<g, kAecThreads, SmemTree::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
@@ -1122,7 +1199,14 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
-        if (!d_model && max_init + sym_stride < 65536 && !g_force_v1)  // decoded size <= sym_stride is enforced by the lane
+        if (!d_model && 16 * max_init + sym_stride < 65536 && !g_force_v1) {  // decoded size <= sym_stride is enforced by the lane
+            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
+            size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;
+            SCL_CUDA(cudaFuncSetAttribute(aec2_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            aec2_decode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            return check_launch("aec2_decode_kernel");
+        }
+        if (!d_model && max_init + sym_stride < 65536)
             aec_decode_kernel<SmemTree16><<<g, kAecThreads, SmemTree16::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);
         else
             aec_decode_kernel<SmemTree><<<g, kAecThreads, SmemTree::kBytes, s>>>(c->d_aec, c->aec->c, io, d_model);

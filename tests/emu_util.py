@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
 _SO = os.path.join(_HERE, "host_emu", "libscl_emu.so")
 _CSRC = os.path.join(os.path.dirname(_HERE), "stanford_compression_library_b200", "csrc")
-_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("scl_lane.cuh", "scl_fast.cuh", "scl_defs.h", "scl_tables.hpp")]
+_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("scl_lane.cuh", "scl_fast.cuh", "scl_aec.cuh", "scl_defs.h", "scl_tables.hpp")]
 
 
 def build():
@@ -39,6 +39,8 @@ def lib():
         L.emu_tans_tables.argtypes = [vp, vp, vp, u64]
         L.emu_encode_blocks.argtypes = [vp, vp, u64, vp, u32, u64, vp, u64, vp, vp, vp, vp]
         L.emu_decode_blocks.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, vp]
+        L.emu_set_aec2.argtypes = [vp, ctypes.c_int]
+        L.emu_aec_renorm_counts.argtypes = [u32, u64, u64, vp, vp, vp, vp]
         L.emu_v2_eligible.argtypes = [vp]
         L.emu_encode_blocks_v2.argtypes = [vp, vp, u64, u32, u64, vp, u64, vp, vp, vp]
         L.emu_decode_blocks_v2.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp]
@@ -83,6 +85,9 @@ class EmuCoder:
         dec = np.zeros(L, dtype=np.uint32)
         assert lib().emu_tans_tables(self.h, _p(enc), _p(dec), L) == 0
         return enc, dec
+
+    def set_aec2(self, on=True):
+        lib().emu_set_aec2(self.h, int(on))
 
     def v2_eligible(self):
         return bool(lib().emu_v2_eligible(self.h))

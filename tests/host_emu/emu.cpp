@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../stanford_compression_library_b200/csrc/scl_aec.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_fast.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_lane.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_tables.hpp"
@@ -28,6 +29,7 @@ struct Emu {
     RangeHost *range = nullptr;
     AecHost *aec = nullptr;
     std::vector<uint32_t> tenc, tdec;
+    bool aec2 = false;  // use the second-generation arithmetic-coder lanes
     ~Emu() {
         delete rans;
         delete tans;
@@ -52,9 +54,33 @@ void store_model(HostTree &F, const AecConst &c, uint64_t *model) {
     fen_unbuild(F);
     for (uint32_t i = 0; i < c.n_sym; ++i) model[i] = F.get(i + 1);
 }
+struct MaskTable {
+    alignas(16) uint8_t m[17][16];
+    MaskTable() {
+        for (int t = 0; t <= 16; ++t)
+            for (int k = 0; k < 16; ++k) m[t][k] = k < t ? 1 : 0;
+    }
+};
+const MaskTable g_mask_table;
+const uint8_t *g_aec_masks = &g_mask_table.m[0][0];
 }  // namespace
 
 extern "C" {
+
+void emu_set_aec2(void *h, int on) { ((Emu *)h)->aec2 = on != 0; }
+
+// closed-form renormalisation counts, exposed for a direct check against the literal loops
+void emu_aec_renorm_counts(uint32_t P, uint64_t low, uint64_t high, uint32_t *n_e12, uint32_t *m_e3, uint64_t *low_out, uint64_t *high_out) {
+    uint32_t n = aec_e12_count(low, high, P), prefix;
+    aec_apply_e12(low, high, n, P, prefix);
+    uint32_t m = aec_e3_count(low, high, P);
+    low = aec_apply_e3(low, m, P);
+    high = aec_apply_e3(high, m, P);
+    *n_e12 = n;
+    *m_e3 = m;
+    *low_out = low;
+    *high_out = high;
+}
 
 int emu_create(const scl_params *params, const uint8_t *alphabet, const uint64_t *freq, uint32_t n_sym, void **out) {
     Emu *e = new Emu();
@@ -154,6 +180,14 @@ int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const ui
             w.init(slot, slot + out_stride);
             if (e->range) {
                 st = range_encode_lane(e->range->t, e->range->c, row, n, w, bits);
+            } else if (e->aec2) {
+                alignas(16) uint32_t words[kAecModelWords];
+                AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
+                uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
+                uint64_t total = 0, tout = 0;
+                M.load(e->aec->t.init_freq, mm, e->aec->c.n_sym, total);
+                st = aec2_encode_lane(M, e->aec->t, e->aec->c, total, row, n, w, bits, tout);
+                if (mm) M.store(mm, e->aec->c.n_sym);
             } else {
                 HostTree F;
                 uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
@@ -190,6 +224,14 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
             if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         } else if (e->range) {
             st = range_decode_lane(e->range->t, e->range->c, r, avail, row, sym_stride, size, used);
+        } else if (e->aec2) {
+            alignas(16) uint32_t words[kAecModelWords];
+            AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
+            uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
+            uint64_t total = 0, tout = 0;
+            M.load(e->aec->t.init_freq, mm, e->aec->c.n_sym, total);
+            st = aec2_decode_lane(M, e->aec->t, e->aec->c, total, r, avail, row, sym_stride, size, used, tout);
+            if (mm) M.store(mm, e->aec->c.n_sym);
         } else {
             HostTree F;
             uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;

@@ -280,3 +280,113 @@ def test_emu_tans_v2_vs_oracle_zipf_lengths(rf):
             assert nb == ln[b] and extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (N, b)
         dsym, dsz, used, st = coder.decode_v2(out, off, ln, max(N, 1))
         assert (st == 0).all() and (dsz == N).all() and (used == ln).all() and (dsym[:, :N] == sym).all()
+
+
+# ---- second-generation arithmetic-coder lanes (csrc/scl_aec.cuh) -------------------------------
+def _renorm_literal(P, low, high):
+    """the reference's two loops (arithmetic_coding.py:126-150), literally"""
+    HALF, QTR = 1 << (P - 1), 1 << (P - 2)
+    n = m = 0
+    while high < HALF or low > HALF:
+        if high < HALF:
+            low, high = low << 1, high << 1
+        else:
+            low, high = (low - HALF) << 1, (high - HALF) << 1
+        n += 1
+    while low > QTR and high < 3 * QTR:
+        low, high = (low - QTR) << 1, (high - QTR) << 1
+        m += 1
+    return n, m, low, high
+
+
+@pytest.mark.parametrize("P", [32, 16, 8, 5])
+def test_aec_closed_form_renormalisation_matches_literal_loops(P):
+    import ctypes
+
+    from tests.emu_util import lib
+
+    rng = np.random.default_rng(P)
+    FULL = 1 << P
+    cases = []
+    for _ in range(20000):
+        a, b = sorted(int(x) for x in rng.integers(0, FULL + 1, size=2))
+        if a == b:
+            continue
+        cases.append((a, b))
+    # boundary-heavy cases: powers of two, all-ones patterns, tiny ranges
+    specials = sorted({v for k in range(P + 1) for v in ((1 << k) - 1, 1 << k, (1 << k) + 1, FULL - (1 << k), FULL - (1 << k) - 1, FULL - (1 << k) + 1) if 0 <= v <= FULL})
+    for a in specials:
+        for b in specials:
+            if a < b and a < FULL:
+                cases.append((a, b))
+    if P <= 8:
+        cases = [(a, b) for a in range(FULL) for b in range(a + 1, FULL + 1)]  # exhaustive
+    n_ = ctypes.c_uint32()
+    m_ = ctypes.c_uint32()
+    lo_ = ctypes.c_uint64()
+    hi_ = ctypes.c_uint64()
+    for low, high in cases:
+        n, m, lo2, hi2 = _renorm_literal(P, low, high)
+        lib().emu_aec_renorm_counts(P, low, high, ctypes.byref(n_), ctypes.byref(m_), ctypes.byref(lo_), ctypes.byref(hi_))
+        assert (n_.value, m_.value, lo_.value, hi_.value) == (n, m, lo2, hi2), (P, low, high)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "aec"], ids=case_id)
+def test_emu_aec2_matches_golden(c):
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    coder.set_aec2(True)
+    n = c["n"]
+    model = np.array([c["freqs"]], dtype=np.uint64)
+    out, off, ln, st = coder.encode(c["data"].reshape(1, -1), model=model)
+    assert st[0] == 0 and int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    assert model[0].tolist() == c["model"]["final_freqs"]
+    if n == 0:
+        return
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    lead = 3
+    bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
+    buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
+    model = np.array([c["freqs"]], dtype=np.uint64)
+    sym, sizes, used, st = coder.decode(buf, [lead], [total], n, model=model)
+    assert st[0] == 0 and int(sizes[0]) == n and int(used[0]) == c["consumed"]
+    assert sym[0, :n].tolist() == c["data"].tolist()
+    assert model[0].tolist() == c["model"]["final_freqs"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_emu_aec2_vs_oracle_random(seed):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(500 + seed)
+    n_sym = int(rng.choice([1, 2, 5, 17, 64, 256]))
+    init = [int(x) for x in rng.integers(1, 30, size=n_sym)] if seed % 2 else [1] * n_sym
+    B, N = 5, int(rng.integers(1, 600))
+    skew = rng.dirichlet(np.ones(n_sym) * 0.3)
+    sym = rng.choice(n_sym, size=(B, N), p=skew).astype(np.uint8)
+    sizes = rng.integers(1, N + 1, size=B).astype(np.uint32)
+    for P, max_total, model in ((32, 1 << 30, _cabi.MODEL_ADAPTIVE_IID), (16, 1 << 14, _cabi.MODEL_ADAPTIVE_IID), (32, sum(init) + 40, _cabi.MODEL_ADAPTIVE_IID),
+                                (32, 1 << 30, _cabi.MODEL_FIXED), (12, 1 << 10, _cabi.MODEL_ADAPTIVE_IID)):
+        if sum(init) >= (1 << (P - 2)) or max_total <= sum(init) and model == _cabi.MODEL_ADAPTIVE_IID and max_total < n_sym:
+            continue
+        oracle = so.Oracle.aec(init, PRECISION=P, max_allowed_total_freq=max_total, model=so.MODEL_ADAPTIVE_IID if model == _cabi.MODEL_ADAPTIVE_IID else so.MODEL_FIXED)
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=P, model=model,
+                        max_allowed_total_freq=max_total)
+        coder = EmuCoder(prm, None, init)
+        coder.set_aec2(True)
+        out, off, ln, st = coder.encode(sym, sizes=sizes)
+        ok = st == 0
+        for b in range(B):
+            try:
+                enc, nb = oracle.encode_block(sym[b, : sizes[b]])
+            except so.OracleError as e:
+                assert st[b] == e.code, (P, max_total, b, st[b], e.code)
+                continue
+            assert st[b] == 0 and nb == ln[b], (P, max_total, b)
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (P, max_total, b)
+        dsym, dsz, used, st2 = coder.decode(out, off, ln, N)
+        for b in range(B):
+            if ok[b]:
+                assert st2[b] == 0 and dsz[b] == sizes[b] and used[b] == ln[b], (P, max_total, b)
+                assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
