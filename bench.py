@@ -272,14 +272,16 @@ def main():
     alg_bytes = head["raw"] + head["C"]  # N + C per launch: enc reads N writes C, dec reads C writes N
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None
+    kernel_name = "fast_%s_v2_kernel" % dom
     tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tp):
         try:
-            tj = json.load(open(tp))
-            traffic = tj.get("rans32_%s_kernel" % dom, {}).get("dram_bytes_per_launch_at_%d_blocks" % B)
+            tj = json.load(open(tp)).get("rans32_%s_kernel" % dom, {})
+            traffic = tj.get("dram_bytes_per_launch_at_%d_blocks" % B)
+            kernel_name = tj.get("kernel", kernel_name)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "rans32_%s_kernel" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": dom_ms, "encode_frac": hs["roofline_encode_frac"], "decode_frac": hs["roofline_decode_frac"],
                 "hbm_read_only_frac": hs["hbm_read_only_frac"]}

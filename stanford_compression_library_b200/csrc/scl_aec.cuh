@@ -218,8 +218,10 @@ SCL_HD uint64_t aec_apply_e3(uint64_t v, uint32_t m, uint32_t P) {
 }
 
 // ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
-SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, const uint8_t *sym, uint32_t n,
-                                 FwdBitWriter &w, uint64_t &bits_out, uint64_t &total_out) {
+SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, const uint8_t *sym, uint64_t sym_cap,
+                                 uint32_t n, FwdBitWriter &w, uint64_t &bits_out, uint64_t &total_out) {
+    SymWindow sw;
+    sw.init(sym, sym_cap);
     const uint32_t P = c.P;
     const uint64_t FULL = 1ull << P, QTR = 1ull << (P - 2);
     uint64_t low = 0, high = FULL, num_mid = 0;
@@ -227,7 +229,7 @@ SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const Aec
     if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
     w.put64((uint64_t)n, c.DBSB);
     for (uint32_t i = 0; i < n && st == SCL_ST_OK; ++i) {
-        const uint32_t idx = tab.sym2idx[sym[i]];
+        const uint32_t idx = tab.sym2idx[sw.next(i)];
         if (idx == 0xFFFFu) {
             st = SCL_ST_BAD_SYMBOL;
             break;
@@ -310,6 +312,8 @@ SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const Aec
     uint64_t nbc = 0, low = 0, high = FULL;
     uint64_t state = aec_get_bits(r, nbc, A, P);  // :222-229 (MSB first, zero fill)
     uint32_t st = SCL_ST_OK;
+    OutWindow ow;
+    ow.init(out);
     for (uint32_t i = 0;;) {
         if (!(total < QTR)) {
             st = SCL_ST_TOTAL_FREQ;
@@ -332,7 +336,8 @@ SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const Aec
         const double rcp_t = 1.0 / (double)total;
         high = low + div_exact_rcp(rng * (uint64_t)(cc + f), total, rcp_t);
         low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
-        out[i++] = tab.idx2sym[idx];
+        ow.push(i, tab.idx2sym[idx]);
+        ++i;
         if (c.model == SCL_MODEL_ADAPTIVE_IID) {
             M.add1(idx);
             total += 1;
@@ -353,6 +358,7 @@ SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const Aec
             state = aec_apply_e3(state, me, P) + aec_get_bits(r, nbc, A, me);
         }
     }
+    ow.flush(st == SCL_ST_OK ? size : 0);
     uint32_t extra = 0;  // :277-282
     for (extra = 0; extra < P; ++extra) {
         uint64_t state_low = (state >> extra) << extra;

@@ -67,6 +67,7 @@ struct alignas(16) RangeTab {
 };
 struct RangeConst {
     uint32_t P, DBSB, n_sym, T;
+    uint32_t t_shift;  // log2 T when T is a power of two (range // T is then a shift), else 0xFFFFFFFF
 };
 
 // ---- arithmetic coder (arithmetic_coding.py), PRECISION <= 32 ------------------------------

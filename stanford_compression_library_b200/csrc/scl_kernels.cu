@@ -471,16 +471,24 @@ __global__ void __launch_bounds__(kThreads) range_encode_kernel(const RangeTab *
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
     uint64_t bits = 0;
-    uint32_t st = range_encode_lane(s_tab, c, io.sym + b * io.sym_stride, n, w, bits);
+    uint32_t st = range_encode_lane(s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
     io.status[b] = st;
 }
 
-__global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *__restrict__ g_tab, RangeConst c, DecodeIo io) {
+__global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *__restrict__ g_tab, const uint8_t *__restrict__ g_lut,
+                                                                uint32_t lut_bytes, RangeConst c, DecodeIo io) {
+    extern __shared__ __align__(16) uint8_t s_lut[];
     __shared__ RangeTab s_tab;
     __shared__ uint64_t mbar;
-    stage_table(&s_tab, g_tab, sizeof(RangeTab), &mbar);
+    mbar_init(&mbar);
+    if (threadIdx.x == 0) {
+        tma_expect(&mbar, (uint32_t)sizeof(RangeTab) + lut_bytes);
+        tma_bulk_g2s(&s_tab, g_tab, sizeof(RangeTab), &mbar);
+        if (lut_bytes) tma_bulk_g2s(s_lut, g_lut, lut_bytes, &mbar);
+    }
+    mbar_wait(&mbar, 0);
     uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     if (b >= io.n_blocks) return;
     BitReader r;
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
     uint64_t used = 0;
-    uint32_t st = range_decode_lane(s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    uint32_t st = range_decode_lane(s_tab, c, lut_bytes ? s_lut : nullptr, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_encode_kernel(const AecT
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(M, s_tab, c, total, io.sym + b * io.sym_stride, n, w, bits, total_out);
+    uint32_t st = aec2_encode_lane(M, s_tab, c, total, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits, total_out);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
     io.status[b] = st;
@@ -803,6 +811,8 @@ struct scl_coder {
     uint32_t *d_tenc = nullptr, *d_tdec = nullptr;
     uint32_t ttab_bytes = 0;
     RangeTab *d_range = nullptr;
+    uint8_t *d_range_lut = nullptr;
+    uint32_t range_lut_bytes = 0;
     AecTab *d_aec = nullptr;
 };
 
@@ -843,6 +853,7 @@ extern "C" void scl_coder_destroy(scl_coder *c) {
     cudaFree(c->d_tenc);
     cudaFree(c->d_tdec);
     cudaFree(c->d_range);
+    cudaFree(c->d_range_lut);
     cudaFree(c->d_aec);
     delete c->rans;
     delete c->tans;
@@ -932,6 +943,10 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         c->range = new RangeHost();
         rc = c->range->init(*params, alphabet, freq, n_sym);
         if (!rc) rc = upload(&c->d_range, &c->range->t, sizeof(RangeTab), sizeof(RangeTab), s);
+        if (!rc) {
+            c->range_lut_bytes = (uint32_t)round16(c->range->lut.size());
+            rc = upload(&c->d_range_lut, c->range->lut.data(), c->range->lut.size(), c->range_lut_bytes, s);
+        }
         break;
     }
     case SCL_CODER_AEC: {
@@ -1192,7 +1207,8 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         return check_launch("tans_decode_kernel");
     }
     if (c->range) {
-        range_decode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
+        SCL_CUDA(cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->range_lut_bytes));
+        range_decode_kernel<<<grid, kThreads, c->range_lut_bytes, s>>>(c->d_range, c->d_range_lut, c->range_lut_bytes, c->range->c, io);
         return check_launch("range_decode_kernel");
     }
     if (c->aec) {

@@ -518,11 +518,98 @@ SCL_HD uint32_t tans_decode_lane(const uint32_t *dec_packed, const RansConst &c,
 }
 
 // ------------------------------------------------------------------------------------------------
+// 16-byte register windows for a lane's own symbol row: one vector access per 16 symbols instead of
+// a byte access per symbol (a per-lane byte load costs a whole 32-byte sector and a wavefront per lane).
+// ------------------------------------------------------------------------------------------------
+struct SymWindow {  // sequential reader
+    const uint8_t *row;
+    uint64_t cap;  // bytes that may be read from `row` (the row stride)
+    uint32_t w0, w1, w2, w3;
+    SCL_HD void init(const uint8_t *row_, uint64_t cap_) {
+        row = row_;
+        cap = cap_;
+        w0 = w1 = w2 = w3 = 0;
+    }
+    SCL_HD uint32_t next(uint32_t i) {  // symbol i; must be called for i = 0, 1, 2, ... in order
+        if ((i & 15) == 0) {
+            if (((((uintptr_t)row) & 15) == 0) && (uint64_t)i + 16 <= cap) {
+                u32x4 v = ld_stream16(row + i);
+                w0 = v.x;
+                w1 = v.y;
+                w2 = v.z;
+                w3 = v.w;
+            } else {
+                uint32_t t[4] = {0, 0, 0, 0};
+                for (uint32_t k = 0; k < 16 && (uint64_t)i + k < cap; ++k) t[k >> 2] |= (uint32_t)row[i + k] << (8 * (k & 3));
+                w0 = t[0];
+                w1 = t[1];
+                w2 = t[2];
+                w3 = t[3];
+            }
+        }
+        uint32_t s = w0 & 0xFFu;
+        w0 = funnel_r(w0, w1, 8);
+        w1 = funnel_r(w1, w2, 8);
+        w2 = funnel_r(w2, w3, 8);
+        w3 >>= 8;
+        return s;
+    }
+};
+struct OutWindow {  // sequential writer
+    uint8_t *row;
+    uint32_t w0, w1, w2, w3;
+    SCL_HD void init(uint8_t *row_) {
+        row = row_;
+        w0 = w1 = w2 = w3 = 0;
+    }
+    SCL_HD void push(uint32_t i, uint32_t s) {  // symbol i; in order from 0
+        w0 = funnel_r(w0, w1, 8);
+        w1 = funnel_r(w1, w2, 8);
+        w2 = funnel_r(w2, w3, 8);
+        w3 = (w3 >> 8) | (s << 24);
+        if ((i & 15) == 15) {
+            if ((((uintptr_t)row) & 15) == 0) {
+                u32x4 v = {w0, w1, w2, w3};
+                st_stream16(row + (i - 15), v);
+            } else {
+                uint32_t t[4] = {w0, w1, w2, w3};
+                for (uint32_t k = 0; k < 16; ++k) row[i - 15 + k] = (uint8_t)(t[k >> 2] >> (8 * (k & 3)));
+            }
+        }
+    }
+    SCL_HD void flush(uint32_t n) {  // after the last push: write the n % 16 pending symbols
+        uint32_t rem = n & 15;
+        if (!rem) return;
+        uint32_t t[4] = {w0, w1, w2, w3};  // the pending bytes are the TOP `rem` bytes of the 16-byte window
+        for (uint32_t k = 0; k < rem; ++k) {
+            uint32_t pos = 16 - rem + k;
+            row[n - rem + k] = (uint8_t)(t[pos >> 2] >> (8 * (pos & 3)));
+        }
+    }
+};
+
+// floor(a / d) for a < 2^62, 0 < d <= 2^32, given rcp = 1.0 / d: one FP64 multiply plus an exact
+// integer correction instead of a 64-bit integer division (~70 instructions on the GPU).  The FP64
+// estimate is within +-1 of the true quotient (quotients here are < 2^33, relative error of the
+// product < 2^-50), and the remainder test makes the result exact.
+SCL_HD uint64_t div_exact_rcp(uint64_t a, uint64_t d, double rcp) {
+    uint64_t q = (uint64_t)((double)a * rcp);
+    int64_t r = (int64_t)(a - q * d);
+    if (r < 0)
+        q -= 1;
+    else if ((uint64_t)r >= d)
+        q += 1;
+    return q;
+}
+
+// ------------------------------------------------------------------------------------------------
 // range coder (range_coder.py), PRECISION in {24, 32}: low/range held in 64 bits so that
 // low + range == 2^P is representable (the reference works in unbounded ints)
 // ------------------------------------------------------------------------------------------------
-SCL_HD uint32_t range_encode_lane(const RangeTab &t, const RangeConst &c, const uint8_t *sym, uint32_t n,
+SCL_HD uint32_t range_encode_lane(const RangeTab &t, const RangeConst &c, const uint8_t *sym, uint64_t sym_cap, uint32_t n,
                                   FwdBitWriter &w, uint64_t &bits_out) {
+    SymWindow sw;
+    sw.init(sym, sym_cap);
     const uint32_t P = c.P;
     const uint64_t TOP = 1ull << (P - 8), BOTTOM = 1ull << (P - 16), MASK = (1ull << P) - 1;
     uint64_t low = 0, range = MASK;  // range_coder.py:191-192
@@ -530,13 +617,13 @@ SCL_HD uint32_t range_encode_lane(const RangeTab &t, const RangeConst &c, const 
     w.put64((uint64_t)n, c.DBSB);
     if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
     for (uint32_t i = 0; i < n; ++i) {
-        uint32_t idx = t.sym2idx[sym[i]];
+        uint32_t idx = t.sym2idx[sw.next(i)];
         if (idx == 0xFFFFu) {
             st = SCL_ST_BAD_SYMBOL;
             break;
         }
-        // shrink_range (range_coder.py:88-105); values fit 32 bits here, so use 32-bit division
-        uint32_t r = (uint32_t)range / c.T;
+        // shrink_range (range_coder.py:88-105); values fit 32 bits here: shift or 32-bit division
+        uint32_t r = c.t_shift != 0xFFFFFFFFu ? ((uint32_t)range >> c.t_shift) : ((uint32_t)range / c.T);
         low += (uint64_t)t.cum[idx] * r;
         range = (uint64_t)r * t.freq[idx];
         // normalize (range_coder.py:107-179)
@@ -561,7 +648,8 @@ SCL_HD uint32_t range_encode_lane(const RangeTab &t, const RangeConst &c, const 
     return st;
 }
 
-SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, BitReader &r, uint64_t avail_bits,
+// `lut` (may be null) maps v in [0, T) to the alphabet index whose [cum, cum+f) contains v
+SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, const uint8_t *lut, BitReader &r, uint64_t avail_bits,
                                   uint8_t *out, uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed) {
     const uint32_t P = c.P;
     const uint64_t TOP = 1ull << (P - 8), BOTTOM = 1ull << (P - 16), MASK = (1ull << P) - 1;
@@ -571,17 +659,22 @@ SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, BitRea
     const uint32_t size = (uint32_t)size64;
     uint64_t low = 0, range = MASK, state = 0;
     for (uint32_t k = 0; k < P / 8; ++k) state = (state << 8) | r.get(8);  // range_coder.py:289-291
+    OutWindow ow;
+    ow.init(out);
     for (uint32_t i = 0; i < size; ++i) {
         // decode_symbol (range_coder.py:225-238): last i with low + cum_i * (range // T) <= state
-        uint32_t rr = (uint32_t)range / c.T;
+        uint32_t rr = c.t_shift != 0xFFFFFFFFu ? ((uint32_t)range >> c.t_shift) : ((uint32_t)range / c.T);
         uint32_t idx;
         if (state < low || rr == 0) {
             idx = c.n_sym - 1;  // searchsorted gives 0 -> alphabet[-1]
         } else {
-            uint64_t v = (state - low) / rr;
-            idx = find_bin<uint32_t>(t.cum, c.n_sym, v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v);
+            uint64_t v = div_exact_rcp(state - low, rr, 1.0 / (double)rr);
+            if (v >= c.T)
+                idx = c.n_sym - 1;  // beyond the last cumulative value: searchsorted returns the last index
+            else
+                idx = lut ? lut[v] : find_bin<uint32_t>(t.cum, c.n_sym, (uint32_t)v);
         }
-        out[i] = t.idx2sym[idx];
+        ow.push(i, t.idx2sym[idx]);
         low += (uint64_t)t.cum[idx] * rr;
         range = (uint64_t)rr * t.freq[idx];
         for (;;) {  // normalize (range_coder.py:240-267)
@@ -593,9 +686,13 @@ SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, BitRea
             state = ((state << 8) | r.get(8)) & MASK;
             low = (low << 8) & MASK;
             range <<= 8;
-            if (r.used > avail_bits) return SCL_ST_TRUNCATED;
+            if (r.used > avail_bits) {
+                ow.flush(i + 1);
+                return SCL_ST_TRUNCATED;
+            }
         }
     }
+    ow.flush(size);
     size_out = size;
     bits_consumed = r.used;
     return r.used > avail_bits ? SCL_ST_TRUNCATED : SCL_ST_OK;
@@ -607,20 +704,6 @@ SCL_HD uint32_t range_decode_lane(const RangeTab &t, const RangeConst &c, BitRea
 // (1-based, F[0] unused) supplied by the caller through the accessor type `Tree`
 // (shared memory, lane-interleaved, on the device; a plain array in the host harness).
 // ------------------------------------------------------------------------------------------------
-// floor(a / d) for a < 2^62, 0 < d <= 2^32, given rcp = 1.0 / d: one FP64 multiply plus an exact
-// integer correction instead of a 64-bit integer division (~70 instructions on the GPU).  The FP64
-// estimate is within +-1 of the true quotient (quotients here are < 2^33, relative error of the
-// product < 2^-50), and the remainder test makes the result exact.
-SCL_HD uint64_t div_exact_rcp(uint64_t a, uint64_t d, double rcp) {
-    uint64_t q = (uint64_t)((double)a * rcp);
-    int64_t r = (int64_t)(a - q * d);
-    if (r < 0)
-        q -= 1;
-    else if ((uint64_t)r >= d)
-        q += 1;
-    return q;
-}
-
 template <typename Tree>
 SCL_HD uint32_t fen_prefix(const Tree &F, uint32_t i) {  // sum of counts[0 .. i)
     uint32_t s = 0;

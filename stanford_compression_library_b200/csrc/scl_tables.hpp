@@ -256,8 +256,14 @@ struct RangeHost {
         c.DBSB = p.data_block_size_bits;
         c.n_sym = n_sym;
         c.T = (uint32_t)tot;
+        c.t_shift = is_pow2_u64(tot) ? log2_u64(tot) : 0xFFFFFFFFu;
+        // v -> alphabet index for the decoder's symbol search (replaces an 8-step binary search)
+        lut.assign((size_t)tot, 0);
+        for (uint32_t i = 0; i < n_sym; ++i)
+            for (uint64_t v = t.cum[i]; v < (uint64_t)t.cum[i] + t.freq[i]; ++v) lut[v] = (uint8_t)i;
         return SCL_E_OK;
     }
+    std::vector<uint8_t> lut;
     // every symbol can release at most ceil(P/8) bytes... bound: normalise emits a byte only while
     // range < 2^(P-8) effectively; one symbol shrinks range by at most T <= 2^(P-16) => <= 3 bytes
     uint64_t max_encoded_bits(uint64_t n) const { return (uint64_t)c.DBSB + 8ull * (3 * n + c.P / 8); }

@@ -179,14 +179,14 @@ int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const ui
             FwdBitWriter w;
             w.init(slot, slot + out_stride);
             if (e->range) {
-                st = range_encode_lane(e->range->t, e->range->c, row, n, w, bits);
+                st = range_encode_lane(e->range->t, e->range->c, row, sym_stride, n, w, bits);
             } else if (e->aec2) {
                 alignas(16) uint32_t words[kAecModelWords];
                 AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
                 uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
                 uint64_t total = 0, tout = 0;
                 M.load(e->aec->t.init_freq, mm, e->aec->c.n_sym, total);
-                st = aec2_encode_lane(M, e->aec->t, e->aec->c, total, row, n, w, bits, tout);
+                st = aec2_encode_lane(M, e->aec->t, e->aec->c, total, row, sym_stride, n, w, bits, tout);
                 if (mm) M.store(mm, e->aec->c.n_sym);
             } else {
                 HostTree F;
@@ -223,7 +223,7 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
             st = tans_decode_lane(e->tdec.data(), e->tans->r.c, r, row, sym_stride, size, used);
             if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         } else if (e->range) {
-            st = range_decode_lane(e->range->t, e->range->c, r, avail, row, sym_stride, size, used);
+            st = range_decode_lane(e->range->t, e->range->c, e->range->lut.data(), r, avail, row, sym_stride, size, used);
         } else if (e->aec2) {
             alignas(16) uint32_t words[kAecModelWords];
             AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
