@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -234,7 +234,7 @@ def main():
             dec.decode_blocks(e, N, reuse=d)
             ev[i][2].record()
         barrier()
-        clocks = sampler.stop() if sample_clocks else None
+        clocks = None
         total_ms = ev[0][0].elapsed_time(ev[-1][2])
         enc_ms = sorted(ev[i][0].elapsed_time(ev[i][1]) for i in range(steps))
         dec_ms = sorted(ev[i][1].elapsed_time(ev[i][2]) for i in range(steps))
@@ -262,8 +262,12 @@ def main():
         }
         return out
 
+    # clocks / throttle reasons are sampled over every timed loop of this run (headline + variants)
     head = bench_variant(HEADLINE, data, args.steps, args.warmup, sample_clocks=True)
     others = {k: bench_variant(k, data, max(5, args.steps // 2), 3) for k in VARIANTS if k != HEADLINE}
+    if args.steps < 100:  # short runs: keep the GPU under the same load a little longer so nvidia-smi gets samples
+        bench_variant(HEADLINE, data, 100, 0)
+    head["clocks"] = sampler.stop()
     hs = summarize(head, world)
 
     # ---- roofline of the dominant kernel (the longer of the two launches of a step) ----------
