@@ -412,10 +412,12 @@ SCL_HD void dec_step(const DecConst &c, uint32_t &x, uint32_t &bits, uint32_t &k
     uint32_t bias = (e >> 8) & 0xFFFu;
     x = mad32(f, xq, bias);
     acc = put_byte<POS>(acc, e);
-    uint32_t d = clz32(x) - c.kbase;      // d >= 0 for NBO == 1 (x < 2^(l+1))
+    uint32_t d = clz32(x) - c.kbase;      // bits missing to reach L; d >= 1 - NBO because x < 2^(l+NBO)
     uint32_t k;
     if (NBO == 1) {
         k = d;
+    } else if ((NBO & (NBO - 1)) == 0) {
+        k = (d + (NBO - 1)) & ~(NBO - 1);  // NBO * ceil(d / NBO), and 0 for d <= 0 (d + NBO - 1 >= 0)
     } else {
         int32_t ds = (int32_t)d;
         k = ds <= 0 ? 0u : (((uint32_t)ds + NBO - 1) / NBO) * NBO;

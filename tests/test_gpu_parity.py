@@ -562,3 +562,36 @@ def test_aec_kernel_generations_agree():
         for b in (0, 1, 2, B - 1):
             got = e2.block(b)
             assert got.tobytes() == ref_out[b, : (int(ref_bits[b]) + 7) // 8].tobytes()
+
+
+def test_tans_full_size_roundtrip_cfg3():
+    """BASELINE cfg3 at full size: tANS, 4096-state tables (RANGE_FACTOR=1), 65536 blocks x 4 KiB."""
+    from stanford_compression_library_b200.compressors.rANS import rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    B, N = 65536, 4096
+    params = tANSParams(zipf_frequencies(), RANGE_FACTOR=1)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=61, device="cuda:0")
+    enc, dec = tANSEncoder(params), tANSDecoder(params)
+    e, d = _compare_batch_with_oracle(enc, dec, so.Oracle.tans(zipf_freq_list(), RANGE_FACTOR=1), data, sample=range(0, B, 4096))
+    r = rANSEncoder(rANSParams(zipf_frequencies(), RANGE_FACTOR=1)).encode_blocks(data).check()
+    assert torch.equal(r.bit_len, e.bit_len) and torch.equal(r.pack().buf, e.pack().buf)  # tANS == rANS bit for bit
+
+
+def test_aec_full_size_roundtrip_cfg4():
+    """BASELINE cfg4 at full size: adaptive order-0 arithmetic coder, 1 048 576 blocks x 1 KiB, fresh
+    uniform model per block.  Exact round trip for every block, oracle bits + consumed on a sample."""
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    B, N = 1048576, 1024
+    params = AECParams()
+    uni = [1] * 256
+    data = sample_blocks(zipf_probabilities(), B, N, seed=62, device="cuda:0")
+    enc = ArithmeticEncoder(params, AdaptiveIIDFreqModel(_F(uni), params.MAX_ALLOWED_TOTAL_FREQ))
+    dec = ArithmeticDecoder(params, AdaptiveIIDFreqModel(_F(uni), params.MAX_ALLOWED_TOTAL_FREQ))
+    e, d = _compare_batch_with_oracle(enc, dec, so.Oracle.aec(uni), data, sample=range(0, B, 65536), consumed_equals_length=False)
+    bits_per_sym = float(e.bit_len.sum()) / (B * N)
+    assert 6.2 < bits_per_sym < 7.0  # Zipf-1.0 entropy 6.22 b/sym + the adaptive model's learning cost over 1 KiB
