@@ -10,7 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libscl_b200.so")
 SOURCES = ["scl_kernels.cu"]
-DEPS = ["scl_kernels.cu", "scl_lane.cuh", "scl_defs.h", "scl_tables.hpp", os.path.join("..", "..", "include", "scl_b200.h")]
+
+
+def _deps():
+    """every source the library is built from: all of csrc/ plus the public header"""
+    files = [f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".hpp"))]
+    return files + [os.path.join("..", "..", "include", "scl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
               "-ccbin", "/usr/bin/g++"]
 
@@ -19,7 +24,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in _deps())
 
 
 def build(force=False, verbose=False):

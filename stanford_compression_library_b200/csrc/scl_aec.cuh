@@ -15,6 +15,8 @@
 // first-generation kernel runs.  __host__ __device__ throughout: tests/host_emu checks these
 // against the oracle on the CPU.
 #pragma once
+#include <math.h>
+
 #include "scl_fast.cuh"
 
 namespace scl {
@@ -217,14 +219,41 @@ SCL_HD uint64_t aec_apply_e3(uint64_t v, uint32_t m, uint32_t P) {
     return ((v - half) << m) + half;  // unsigned wrap-around == the signed identity (results are in [0, 2^P])
 }
 
+// ---- 32-bit state form ------------------------------------------------------------------------
+// The lanes keep low and hm = high - 1 as 32-bit words (high itself can be 2^32).  With P-bit
+// precision every update is taken modulo 2^P (`pm` = 2^P - 1): an E1/E2 step drops the common top
+// bit (low shifts in 0, hm shifts in 1), an E3 step maps v -> 2(v - QTR), i.e. after m steps
+// v -> 2^m (v - HALF) + HALF, and for hm the "+1" of high carries through as + (2^m - 1).
+SCL_HD void aec_shift_e12(uint32_t &low, uint32_t &hm, uint32_t n, uint32_t pm) {
+    low = (low << n) & pm;
+    hm = ((hm << n) | ((1u << n) - 1u)) & pm;
+}
+SCL_HD void aec_shift_e3(uint32_t &low, uint32_t &hm, uint32_t m, uint32_t half, uint32_t pm) {
+    low = (((low - half) << m) + half) & pm;
+    hm = (((hm - half) << m) + half + ((1u << m) - 1u)) & pm;
+}
+// floor(a / t) for integer-valued doubles a < 2^53, t >= 1, rcp = 1 / t: the product estimate is
+// within 1 of the quotient and the fused remainder a - q t is exact, so one correction suffices.
+SCL_HD double aec_floor_div(double a, double t, double rcp) {
+    double q = floor(a * rcp);
+    double r = fma(-q, t, a);
+    if (r < 0.0)
+        q -= 1.0;
+    else if (r >= t)
+        q += 1.0;
+    return q;
+}
+
 // ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
-SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, const uint8_t *sym, uint64_t sym_cap,
+SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total64, const uint8_t *sym, uint64_t sym_cap,
                                  uint32_t n, FwdBitWriter &w, uint64_t &bits_out, uint64_t &total_out) {
     SymWindow sw;
     sw.init(sym, sym_cap);
     const uint32_t P = c.P;
-    const uint64_t FULL = 1ull << P, QTR = 1ull << (P - 2);
-    uint64_t low = 0, high = FULL, num_mid = 0;
+    const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
+    const uint32_t max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    uint32_t low = 0, hm = pm, num_mid = 0;  // high = FULL
+    uint32_t total = (uint32_t)total64;      // < 2^20 (16 group totals below 2^16)
     uint32_t st = SCL_ST_OK;
     if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
     w.put64((uint64_t)n, c.DBSB);
@@ -240,30 +269,40 @@ SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const Aec
         }
         uint32_t cc, f;
         M.query(idx, cc, f);
-        const uint64_t rng = high - low;
-        const double rcp_t = 1.0 / (double)total;
-        high = low + div_exact_rcp(rng * (uint64_t)(cc + f), total, rcp_t);  // shrink_range (:58-78)
-        low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
+        // shrink_range (:58-78): rng * d < 2^33 * 2^20, exact in FP64
+        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
+        const double rng_d = (double)hm - low_d + 1.0;
+        hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
+        low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
         if (c.model == SCL_MODEL_ADAPTIVE_IID) {  // update_model (:118)
             M.add1(idx);
             total += 1;
-            if (total >= c.max_total) M.halve(c.n_sym, total);
+            if (total >= max_total) {
+                uint64_t t64 = total;
+                M.halve(c.n_sym, t64);
+                total = (uint32_t)t64;
+            }
         }
-        const uint32_t ne = aec_e12_count(low, high, P);
+        const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
         if (ne) {
-            uint32_t prefix;
-            aec_apply_e12(low, high, ne, P, prefix);
-            const uint32_t b0 = (prefix >> (ne - 1)) & 1u;  // first released bit, then the pending opposite bits
-            w.put(b0, 1);
-            w.put_run(b0 ^ 1u, num_mid);
+            const uint32_t prefix = low >> (P - ne);
+            aec_shift_e12(low, hm, ne, pm);
+            // released bits: first prefix bit, then num_mid copies of its complement, then the rest
+            const uint32_t b0 = (prefix >> (ne - 1)) & 1u;
+            if (num_mid + ne <= 32) {
+                const uint32_t run = b0 ? 0u : mask32(num_mid);
+                w.put((b0 << (num_mid + ne - 1)) | (run << (ne - 1)) | (prefix & mask32(ne - 1)), num_mid + ne);
+            } else {
+                w.put(b0, 1);
+                w.put_run(b0 ^ 1u, num_mid);
+                if (ne > 1) w.put(prefix & mask32(ne - 1), ne - 1);
+            }
             num_mid = 0;
-            if (ne > 1) w.put(prefix & mask32(ne - 1), ne - 1);
         }
-        const uint32_t me = aec_e3_count(low, high, P);
+        const uint32_t me = aec_e3_count(low, (uint64_t)hm + 1, P);
         if (me) {
             num_mid += me;
-            low = aec_apply_e3(low, me, P);
-            high = aec_apply_e3(high, me, P);
+            aec_shift_e3(low, hm, me, HALF, pm);
         }
         if (w.ovf) break;
     }
@@ -297,20 +336,22 @@ SCL_HD uint32_t aec_get_bits(BitReader &r, uint64_t &nbc, uint64_t A, uint32_t k
 }
 
 // ArithmeticDecoder.decode_block (arithmetic_coding.py:203-287)
-SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total, BitReader &r,
+SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total64, BitReader &r,
                                  uint64_t avail_bits, uint8_t *out, uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed,
                                  uint64_t &total_out) {
     const uint32_t P = c.P;
-    const uint64_t FULL = 1ull << P, QTR = 1ull << (P - 2);
+    const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
+    const uint32_t max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
     uint64_t size64 = r.get64(c.DBSB);
     size_out = 0;
-    total_out = total;
+    total_out = total64;
     if (size64 > out_cap) return SCL_ST_OVERFLOW;
     if (size64 == 0) return SCL_ST_EMPTY_BLOCK;
     const uint32_t size = (uint32_t)size64;
     const uint64_t A = avail_bits > c.DBSB ? avail_bits - c.DBSB : 0;
-    uint64_t nbc = 0, low = 0, high = FULL;
-    uint64_t state = aec_get_bits(r, nbc, A, P);  // :222-229 (MSB first, zero fill)
+    uint64_t nbc = 0;
+    uint32_t low = 0, hm = pm, total = (uint32_t)total64;
+    uint32_t state = aec_get_bits(r, nbc, A, P);  // :222-229 (MSB first, zero fill)
     uint32_t st = SCL_ST_OK;
     OutWindow ow;
     ow.init(out);
@@ -319,51 +360,55 @@ SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const Aec
             st = SCL_ST_TOTAL_FREQ;
             break;
         }
-        const uint64_t rng = high - low;
+        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
+        const double rng_d = (double)hm - low_d + 1.0;
         uint32_t idx, cc, f;
         if (state < low) {
             idx = c.n_sym - 1;  // searchsorted -> 0, alphabet[-1]
             M.query(idx, cc, f);
         } else {
-            uint64_t v = div_exact_rcp((state - low + 1) * total - 1, rng, 1.0 / (double)rng);  // decode_step_core (:177-201)
+            // decode_step_core (:177-201): last idx with cum <= ((state - low + 1) * T - 1) // rng ; product < 2^52
+            double v_d = aec_floor_div(((double)state - low_d + 1.0) * t_d - 1.0, rng_d, 1.0 / rng_d);
+            uint32_t v = (uint32_t)v_d;
             if (v >= total) v = total - 1;
-            idx = M.find((uint32_t)v, cc, f);
+            idx = M.find(v, cc, f);
             if (idx >= c.n_sym) {
                 idx = c.n_sym - 1;
                 M.query(idx, cc, f);
             }
         }
-        const double rcp_t = 1.0 / (double)total;
-        high = low + div_exact_rcp(rng * (uint64_t)(cc + f), total, rcp_t);
-        low = low + div_exact_rcp(rng * (uint64_t)cc, total, rcp_t);
+        hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
+        low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
         ow.push(i, tab.idx2sym[idx]);
         ++i;
         if (c.model == SCL_MODEL_ADAPTIVE_IID) {
             M.add1(idx);
             total += 1;
-            if (total >= c.max_total) M.halve(c.n_sym, total);
+            if (total >= max_total) {
+                uint64_t t64 = total;
+                M.halve(c.n_sym, t64);
+                total = (uint32_t)t64;
+            }
         }
         if (i == size) break;  // :242-243
-        const uint32_t ne = aec_e12_count(low, high, P);
+        const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
         if (ne) {
-            uint32_t prefix;
-            aec_apply_e12(low, high, ne, P, prefix);
-            // the reference subtracts HALF from `state` exactly when it does so for low/high (:252-256)
-            state = (state << ne) - ((uint64_t)prefix << P) + aec_get_bits(r, nbc, A, ne);
+            aec_shift_e12(low, hm, ne, pm);
+            state = ((state << ne) & pm) | aec_get_bits(r, nbc, A, ne);  // the dropped top bits are the common prefix (:252-256)
         }
-        const uint32_t me = aec_e3_count(low, high, P);
+        const uint32_t me = aec_e3_count(low, (uint64_t)hm + 1, P);
         if (me) {
-            low = aec_apply_e3(low, me, P);
-            high = aec_apply_e3(high, me, P);
-            state = aec_apply_e3(state, me, P) + aec_get_bits(r, nbc, A, me);
+            aec_shift_e3(low, hm, me, HALF, pm);
+            state = ((((state - HALF) << me) + HALF) & pm) + aec_get_bits(r, nbc, A, me);
         }
     }
     ow.flush(st == SCL_ST_OK ? size : 0);
+    const uint64_t low64 = low, high64 = (uint64_t)hm + 1, state64 = state;
     uint32_t extra = 0;  // :277-282
     for (extra = 0; extra < P; ++extra) {
-        uint64_t state_low = (state >> extra) << extra;
+        uint64_t state_low = (state64 >> extra) << extra;
         uint64_t state_high = state_low + (1ull << extra);
-        if (state_low < low || state_high > high) break;
+        if (state_low < low64 || state_high > high64) break;
     }
     if (extra == P) extra = P - 1;
     size_out = size;
