@@ -56,7 +56,8 @@ extern "C" {
 #define SCL_ST_STATE_MISMATCH 2 /* AssertionError: rANS.py:295 / tANS.py:277 end state != INITIAL_STATE */
 #define SCL_ST_OVERFLOW 3       /* OverflowError: size does not fit DATA_BLOCK_SIZE_BITS (rANS.py:206), or slot too small */
 #define SCL_ST_TRUNCATED 4      /* ValueError: stream ended inside a block */
-#define SCL_ST_TOTAL_FREQ 6     /* AssertionError: arithmetic_coding.py:110-112 */
+#define SCL_ST_TOTAL_FREQ 6     /* AssertionError: arithmetic_coding.py:110-112; or an order-k count reached
+                                   max_allowed_total_freq (the reference raises, probability_models.py:164-168) */
 #define SCL_ST_EMPTY_BLOCK 7    /* arithmetic decoder given size 0: the reference loops forever (arithmetic_coding.py:232-243) */
 
 /* coder kinds */
@@ -68,6 +69,9 @@ extern "C" {
 /* frequency models for the arithmetic coder (scl/compressors/probability_models.py) */
 #define SCL_MODEL_FIXED 0        /* FixedFreqModel        :57-67 */
 #define SCL_MODEL_ADAPTIVE_IID 1 /* AdaptiveIIDFreqModel  :70-92 */
+#define SCL_MODEL_ORDER_K 2      /* AdaptiveOrderKFreqModel :95-168, order = scl_params.model_order; this backend
+                                    keeps the table in shared memory: n_sym^k * (n_sym + 1) <= 1600 words
+                                    (else SCL_E_UNSUPPORTED) */
 
 typedef struct scl_coder scl_coder; /* opaque: parameters + device tables */
 
@@ -84,6 +88,7 @@ typedef struct scl_params {
     uint32_t precision; /* PRECISION */
     /* FreqModelBase (probability_models.py:39-44) -- arithmetic coder only */
     int32_t model;                   /* SCL_MODEL_* */
+    uint32_t model_order;            /* k of AdaptiveOrderKFreqModel (:104-107); 0 for the other models */
     uint64_t max_allowed_total_freq; /* halving threshold of AdaptiveIIDFreqModel (:90-92) */
 } scl_params;
 
@@ -101,6 +106,12 @@ void scl_coder_destroy(scl_coder *c);
  * sector size (32).  Use it as out_stride. */
 uint64_t scl_coder_max_encoded_bytes(const scl_coder *c, uint64_t block_len);
 
+/* Length, in uint64 words, of ONE block's model table as passed in d_model: n_sym for the fixed / IID
+ * models (freqs_current in alphabet order); n_sym^(k+1) + 1 for the order-k model (freqs_kplus1_tuple
+ * flattened row-major, then the context index = past_k read as a base-n_sym number).  0 = not an
+ * arithmetic coder. */
+uint64_t scl_coder_model_words(const scl_coder *c);
+
 /* Which kernel family the handle selected: 0 = 32-bit-state fast path, 1 = generic 64-bit. */
 int scl_coder_path(const scl_coder *c, int decode);
 
@@ -110,8 +121,8 @@ int scl_coder_path(const scl_coder *c, int decode);
  *   d_sym      [n_blocks][sym_stride] bytes; block b has d_sizes[b] symbols (d_sizes NULL: block_len each)
  *   d_out      n_blocks slots of out_stride bytes (out_stride % 16 == 0, base 16-byte aligned)
  *   d_out_bit_offset / d_out_bit_len  [n_blocks]  where block b's stream lies (bits)
- *   d_model    arithmetic coder only: [n_blocks][n_sym] uint64 model tables, read as the initial
- *              freqs_current and overwritten with the final one (the reference mutates its model in
+ *   d_model    arithmetic coder only: [n_blocks][scl_coder_model_words()] uint64 model tables, read as the
+ *              initial model state and overwritten with the final one (the reference mutates its model in
  *              place, arithmetic_coding.py:118); NULL = every block starts from the creation-time table
  * Replaces rANSEncoder.encode_block (rANS.py:186-210), tANSEncoder.encode_block (tANS.py:159-193),
  * ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161), RangeEncoder.encode_block

@@ -23,7 +23,7 @@ from oracle.ref_loader import import_reference  # noqa: E402
 
 import_reference()
 from scl.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder  # noqa: E402
-from scl.compressors.probability_models import AdaptiveIIDFreqModel, FixedFreqModel  # noqa: E402
+from scl.compressors.probability_models import AdaptiveIIDFreqModel, AdaptiveOrderKFreqModel, FixedFreqModel  # noqa: E402
 from scl.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams  # noqa: E402
 from scl.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder  # noqa: E402
 from scl.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams  # noqa: E402
@@ -113,6 +113,33 @@ def run_aec(freqs_initial, data, model="adaptive_iid", note="", max_total=None, 
            dec.data_list, used, g, note, model=dict(kind=model, max_total=int(mt), final_freqs=final))
 
 
+def run_aec_order_k(n_alpha, k, data, note="", **kw):
+    """AdaptiveOrderKFreqModel (probability_models.py:95-160) over alphabet 0..n_alpha-1."""
+    params = AECParams(**kw)
+    m_enc = AdaptiveOrderKFreqModel(list(range(n_alpha)), k, params.MAX_ALLOWED_TOTAL_FREQ)
+    m_dec = copy.deepcopy(m_enc)
+    enc = ArithmeticEncoder(params, m_enc).encode_block(DataBlock([int(x) for x in data]))
+    g = garbage(len(cases))
+    dec, used = ArithmeticDecoder(params, m_dec).decode_block(enc + BitArray(g))
+    final = [int(x) for x in np.ravel(m_enc.freqs_kplus1_tuple)]
+    ctx = 0
+    for p in m_enc.past_k:
+        ctx = ctx * n_alpha + int(p)
+    record("aec", dict(DATA_BLOCK_SIZE_BITS=params.DATA_BLOCK_SIZE_BITS, PRECISION=params.PRECISION), [1] * n_alpha, data, enc, dec.data_list, used, g, note,
+           model=dict(kind="order_k", k=k, max_total=int(params.MAX_ALLOWED_TOTAL_FREQ), final_freqs=final, final_ctx=ctx))
+
+
+def markov2(n, seed):
+    """the reference's 2nd-order Markov test source (arithmetic_coding.py:384-402)"""
+    rng = np.random.default_rng(seed)
+    bits = rng.choice(2, size=n - 2)
+    x = np.zeros(n, dtype=np.uint8)
+    x[0], x[1] = rng.choice(3), rng.choice(3)
+    for i in range(2, n):
+        x[i] = (x[i - 1] + x[i - 2] + bits[i - 2]) % 3
+    return x
+
+
 def main():
     # ---- the reference's literal known-answer vector (rANS.py:303-360 / tANS.py:340-415) ----
     run_rans([3, 3, 2], [0, 2, 1], note="KAT rANS.py:303-360 expects 00011 1011 10 01 0", DATA_BLOCK_SIZE_BITS=5, NUM_BITS_OUT=1, RANGE_FACTOR=1)
@@ -190,6 +217,14 @@ def main():
     run_aec([1] * 256, z[:1024], note="cfg4: 1 KiB zipf block, uniform init over 256 symbols")
     run_aec([1] * 256, z[:1], note="single symbol block")
     run_aec([1] * 256, [], note="AEC empty block: encode only (reference decoder does not terminate)") if False else None
+
+    # ---- order-k adaptive context model (arithmetic_coding.py:404-447, probability_models.py:95-160) ----
+    mk = markov2(400, seed=0)
+    for k in (0, 1, 2, 3):
+        run_aec_order_k(3, k, mk, note="order-%d model on the reference's 2nd-order Markov source" % k, DATA_BLOCK_SIZE_BITS=12)
+    run_aec_order_k(2, 4, draw([3, 1], 300, 70), note="binary alphabet, order 4", DATA_BLOCK_SIZE_BITS=12)
+    run_aec_order_k(4, 2, draw([5, 1, 1, 3], 300, 71), note="4 symbols, order 2", DATA_BLOCK_SIZE_BITS=12, PRECISION=16)
+    run_aec_order_k(5, 3, draw([4, 3, 2, 1, 1], 600, 72), note="5 symbols, order 3 (750 counters)", DATA_BLOCK_SIZE_BITS=12)
 
     meta = json.dumps(dict(version=1, reference_commit="5e9a699db81d7452cdf4f34b5b7023bac39f5dd5", cases=cases))
     np.savez_compressed(OUT, meta=np.frombuffer(meta.encode(), dtype=np.uint8), **arrays)

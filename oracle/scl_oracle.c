@@ -436,9 +436,36 @@ static int tans_decode_block(const tans_tables *t, const uint8_t *in, uint64_t n
 
 #define SCL_MODEL_FIXED 0        /* FixedFreqModel (:57-67) */
 #define SCL_MODEL_ADAPTIVE_IID 1 /* AdaptiveIIDFreqModel (:70-92) */
+#define SCL_MODEL_ORDER_K 2      /* AdaptiveOrderKFreqModel (:95-160), k in bits 8.. of the kind word */
 
-static void model_update(int kind, uint64_t *freq, uint32_t n_sym, uint32_t s, uint64_t max_total) {
-    if (kind != SCL_MODEL_ADAPTIVE_IID) return;
+/* Order-k state: `freq` is then the whole count array freqs_kplus1_tuple flattened as
+ * [context][symbol] (n_ctx = n_sym^k rows) FOLLOWED by one word holding the current context index
+ * (past_k read as a base-n_sym number, oldest symbol most significant; :114-126,146-148). */
+static uint64_t ipow_u64(uint64_t a, uint32_t k) {
+    uint64_t r = 1;
+    while (k--) r *= a;
+    return r;
+}
+static uint64_t *model_row(int kind, uint64_t *freq, uint32_t n_sym) {
+    if ((kind & 0xFF) != SCL_MODEL_ORDER_K) return freq;
+    uint64_t n_ctx = ipow_u64(n_sym, (uint32_t)kind >> 8);
+    return freq + freq[n_ctx * n_sym] * n_sym; /* freqs_current (:128-140) */
+}
+
+static int model_update(int kind, uint64_t *freq, uint32_t n_sym, uint32_t s, uint64_t max_total) {
+    if ((kind & 0xFF) == SCL_MODEL_ORDER_K) { /* update_model (:142-160) */
+        uint32_t k = (uint32_t)kind >> 8;
+        uint64_t n_ctx = ipow_u64(n_sym, k);
+        uint64_t *ctx = &freq[n_ctx * n_sym];
+        uint64_t *cnt = &freq[*ctx * n_sym + s];
+        *cnt += 1;
+        if (k > 0) *ctx = (*ctx * n_sym + s) % n_ctx; /* past_k = past_k[1:] + [idx] */
+        /* :156-160 tests ONE count against max_allowed_total_freq and then calls np.max(x // 2, 1),
+         * which raises (axis 1 of a scalar): report it instead of guessing */
+        if (*cnt >= max_total) return SCL_ERR_TOTAL_FREQ;
+        return SCL_OK;
+    }
+    if (kind != SCL_MODEL_ADAPTIVE_IID) return SCL_OK;
     freq[s] += 1; /* :86 */
     uint64_t tot = 0;
     for (uint32_t i = 0; i < n_sym; ++i) tot += freq[i];
@@ -447,6 +474,7 @@ static void model_update(int kind, uint64_t *freq, uint32_t n_sym, uint32_t s, u
             uint64_t h = freq[i] / 2;
             freq[i] = h > 1 ? h : 1;
         }
+    return SCL_OK;
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -469,17 +497,18 @@ static int aec_encode_block(uint32_t dbsb, uint32_t P, int model, uint64_t *freq
     for (uint64_t i = 0; i < n; ++i) {
         uint32_t s = sym[i];
         if (s >= n_sym) return SCL_ERR_BAD_SYMBOL;
+        const uint64_t *row = model_row(model, freq, n_sym);
         u128 T = 0, c = 0;
         for (uint32_t j = 0; j < n_sym; ++j) {
             if (j == s) c = T;
-            T += freq[j];
+            T += row[j];
         }
         if (!(T < MAX_TOTAL)) return SCL_ERR_TOTAL_FREQ; /* :110-112 */
         /* shrink_range (:58-78) */
-        u128 rng = high - low, d = c + freq[s];
+        u128 rng = high - low, d = c + row[s];
         high = low + (rng * d) / T;
         low = low + (rng * c) / T;
-        model_update(model, freq, n_sym, s, max_total); /* :118 */
+        if (model_update(model, freq, n_sym, s, max_total)) return SCL_ERR_TOTAL_FREQ; /* :118 */
         while (high < HALF || low > HALF) { /* :126 (strict tests) */
             if (high < HALF) {
                 if (bv_push(out, 0)) return SCL_ERR_OVERFLOW;
@@ -543,23 +572,27 @@ static int aec_decode_block(uint32_t dbsb, uint32_t P, int model, uint64_t *freq
     uint64_t count = 0;
     int rc = SCL_OK;
     for (;;) {
+        const uint64_t *row = model_row(model, freq, n_sym);
         u128 T = 0;
-        for (uint32_t j = 0; j < n_sym; ++j) T += freq[j];
+        for (uint32_t j = 0; j < n_sym; ++j) T += row[j];
         u128 rng = high - low, c = 0;
         for (uint32_t j = 0; j < n_sym; ++j) { /* search_list (:196-198) */
             search[j] = low + (c * rng) / T;
-            c += freq[j];
+            c += row[j];
         }
         int64_t idx = searchsorted_right_minus1(search, n_sym, state);
         if (idx < 0) idx = (int64_t)n_sym - 1; /* Python alphabet[-1] */
         uint32_t s = (uint32_t)idx;
         c = 0;
-        for (uint32_t j = 0; j < s; ++j) c += freq[j];
-        u128 d = c + freq[s];
+        for (uint32_t j = 0; j < s; ++j) c += row[j];
+        u128 d = c + row[s];
         high = low + (rng * d) / T; /* shrink_range */
         low = low + (rng * c) / T;
         out[count++] = (uint8_t)s;
-        model_update(model, freq, n_sym, s, max_total);
+        if (model_update(model, freq, n_sym, s, max_total)) {
+            rc = SCL_ERR_TOTAL_FREQ;
+            break;
+        }
         if (count == size) break; /* :242-243 -- before renormalisation */
         while (high < HALF || low > HALF) {
             if (high < HALF) {
@@ -816,6 +849,21 @@ void scl_oracle_destroy(void *h) {
     free(c);
 }
 
+/* a private model for one block: the creation-time table, or all-ones + context 0 for order-k */
+static uint64_t *fresh_model(const oracle_ctx *c) {
+    int kind = (int)c->cfg.p2;
+    if ((kind & 0xFF) == SCL_MODEL_ORDER_K) {
+        uint64_t n = ipow_u64(c->n_sym, (uint32_t)kind >> 8) * c->n_sym;
+        uint64_t *m = (uint64_t *)malloc(sizeof(uint64_t) * (n + 1));
+        for (uint64_t i = 0; i < n; ++i) m[i] = 1; /* np.ones (:106) */
+        m[n] = 0;                                  /* past_k = [0] * k (:112) */
+        return m;
+    }
+    uint64_t *m = (uint64_t *)malloc(sizeof(uint64_t) * c->n_sym);
+    memcpy(m, c->freq, sizeof(uint64_t) * c->n_sym);
+    return m;
+}
+
 /* Encode one block.  `model_freq` (AEC only; may be NULL -> use a private copy of the
  * creation-time table) is the model's current table, updated in place like the reference's
  * freq_model.  Returns status; *out_bits = stream length in bits. */
@@ -836,11 +884,7 @@ int scl_oracle_encode_block(void *h, const uint8_t *sym, uint64_t n, uint64_t *m
         rc = range_encode_block(&c->gp, sym, n, &bv);
         break;
     default:
-        if (!model_freq) {
-            tmp = (uint64_t *)malloc(sizeof(uint64_t) * c->n_sym);
-            memcpy(tmp, c->freq, sizeof(uint64_t) * c->n_sym);
-            model_freq = tmp;
-        }
+        if (!model_freq) model_freq = tmp = fresh_model(c);
         rc = aec_encode_block((uint32_t)c->cfg.p0, (uint32_t)c->cfg.p1, (int)c->cfg.p2, model_freq, c->n_sym,
                               c->cfg.p3, sym, n, &bv);
         free(tmp);
@@ -880,11 +924,7 @@ int scl_oracle_decode_block(void *h, const uint8_t *in, uint64_t bit_offset, uin
         rc = range_decode_block(&c->gp, src, nbits, out, out_cap, n_out, bits_consumed);
         break;
     default:
-        if (!model_freq) {
-            tmp = (uint64_t *)malloc(sizeof(uint64_t) * c->n_sym);
-            memcpy(tmp, c->freq, sizeof(uint64_t) * c->n_sym);
-            model_freq = tmp;
-        }
+        if (!model_freq) model_freq = tmp = fresh_model(c);
         rc = aec_decode_block((uint32_t)c->cfg.p0, (uint32_t)c->cfg.p1, (int)c->cfg.p2, model_freq, c->n_sym,
                               c->cfg.p3, src, nbits, out, out_cap, n_out, bits_consumed);
         free(tmp);

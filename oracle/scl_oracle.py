@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libscl_oracle.so")
 
 CODER_RANS, CODER_TANS, CODER_RANGE, CODER_AEC = 0, 1, 2, 3
-MODEL_FIXED, MODEL_ADAPTIVE_IID = 0, 1
+MODEL_FIXED, MODEL_ADAPTIVE_IID, MODEL_ORDER_K = 0, 1, 2
 
 STATUS = {
     0: "ok",
@@ -102,10 +102,12 @@ class Oracle:
         return cls(CODER_RANGE, freqs, DATA_BLOCK_SIZE_BITS, PRECISION)
 
     @classmethod
-    def aec(cls, freqs_initial, DATA_BLOCK_SIZE_BITS=32, PRECISION=32, model=MODEL_ADAPTIVE_IID, max_allowed_total_freq=None):
+    def aec(cls, freqs_initial, DATA_BLOCK_SIZE_BITS=32, PRECISION=32, model=MODEL_ADAPTIVE_IID, max_allowed_total_freq=None, k=0):
+        """model=MODEL_ORDER_K: `freqs_initial` only gives the alphabet size; the model table passed to
+        encode_block/decode_block is [n_sym**k * n_sym counts][context index] (uint64)."""
         if max_allowed_total_freq is None:
             max_allowed_total_freq = 1 << (PRECISION - 2)
-        return cls(CODER_AEC, freqs_initial, DATA_BLOCK_SIZE_BITS, PRECISION, model, max_allowed_total_freq)
+        return cls(CODER_AEC, freqs_initial, DATA_BLOCK_SIZE_BITS, PRECISION, model | (k << 8), max_allowed_total_freq)
 
     def __del__(self):
         try:
@@ -162,12 +164,6 @@ class Oracle:
         status = np.zeros(nb, dtype=np.int32)
         lib().scl_oracle_decode_batch(self.h, _p(buf, ctypes.c_uint8), _p(bit_offsets, ctypes.c_uint64), _p(bit_lens, ctypes.c_uint64), nb, _p(out, ctypes.c_uint8), out_stride, _p(sizes, ctypes.c_uint32), _p(used, ctypes.c_uint64), _p(status, ctypes.c_int32), n_threads)
         return out, sizes, used, status
-
-    def tans_tables(self):
-        assert self.coder == CODER_TANS
-        M = int(self.freq.sum())
-        # L = RF*M is not stored on the python side; ask for the maximum the C side allows
-        raise NotImplementedError("use tans_tables_for(L)")
 
     def tans_tables_for(self, L):
         enc = np.zeros(L, dtype=np.uint64)

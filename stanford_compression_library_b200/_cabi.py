@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libscl_b200.so")
 E_OK, E_INVALID, E_CUDA, E_UNSUPPORTED = 0, 1, 2, 3
 ST_OK, ST_BAD_SYMBOL, ST_STATE_MISMATCH, ST_OVERFLOW, ST_TRUNCATED, ST_TOTAL_FREQ, ST_EMPTY_BLOCK = 0, 1, 2, 3, 4, 6, 7
 CODER_RANS, CODER_TANS, CODER_RANGE, CODER_AEC = 0, 1, 2, 3
-MODEL_FIXED, MODEL_ADAPTIVE_IID = 0, 1
+MODEL_FIXED, MODEL_ADAPTIVE_IID, MODEL_ORDER_K = 0, 1, 2
 
 
 class SclParams(ctypes.Structure):
@@ -26,6 +26,7 @@ class SclParams(ctypes.Structure):
         ("num_state_bits", ctypes.c_uint32),
         ("precision", ctypes.c_uint32),
         ("model", ctypes.c_int32),
+        ("model_order", ctypes.c_uint32),
         ("max_allowed_total_freq", ctypes.c_uint64),
     ]
 
@@ -55,6 +56,8 @@ def lib():
     L.scl_coder_destroy.argtypes = [vp]
     L.scl_coder_max_encoded_bytes.restype = u64
     L.scl_coder_max_encoded_bytes.argtypes = [vp, u64]
+    L.scl_coder_model_words.restype = u64
+    L.scl_coder_model_words.argtypes = [vp]
     L.scl_coder_path.restype = i32
     L.scl_coder_path.argtypes = [vp, i32]
     L.scl_encode_blocks.restype = i32
@@ -78,7 +81,7 @@ def lib():
 
 
 EXPORTS = [
-    "scl_coder_create", "scl_coder_destroy", "scl_coder_max_encoded_bytes", "scl_coder_path", "scl_encode_blocks",
+    "scl_coder_create", "scl_coder_destroy", "scl_coder_max_encoded_bytes", "scl_coder_model_words", "scl_coder_path", "scl_encode_blocks",
     "scl_decode_blocks", "scl_pack_blocks", "scl_frame_blocks", "scl_tans_tables_to_host", "scl_histogram_blocks", "scl_debug_force_v1", "scl_last_cuda_error", "scl_version",
 ]
 

@@ -39,20 +39,40 @@ class _AecCoder(GpuCoderBase):
     def _freqs(self):
         return self.freq_model.freqs_current
 
+    def _cache_key(self):
+        m = self.freq_model
+        if m.CABI_MODEL == _cabi.MODEL_ORDER_K:  # the handle only depends on the alphabet and k
+            return ("order_k", tuple(m.alphabet), m.k, int(m.max_allowed_total_freq))
+        return super()._cache_key()
+
     def _make_cabi_params(self):
         if self.freq_model.CABI_MODEL is None:
             raise NotImplementedError("frequency model %s has no device implementation" % type(self.freq_model).__name__)
         return _cabi.SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=int(self.params.DATA_BLOCK_SIZE_BITS), num_bits_out=0,
                                range_factor=0, num_state_bits=0, precision=int(self.params.PRECISION), model=self.freq_model.CABI_MODEL,
+                               model_order=int(getattr(self.freq_model, "k", 0)) if self.freq_model.CABI_MODEL == _cabi.MODEL_ORDER_K else 0,
                                max_allowed_total_freq=int(self.freq_model.max_allowed_total_freq))
 
-    def _model_tensor(self):
+    def _model_tensor(self, n_blocks=1):
         dev = self.device_coder()
-        counts = [int(f) for f in self.freq_model.freqs_current.freq_list]
-        return torch.tensor([counts], dtype=torch.int64, device=dev.device)
+        return torch.tensor([self.freq_model._to_table()], dtype=torch.int64, device=dev.device).repeat(n_blocks, 1)
 
     def _writeback(self, model_t):
-        self.freq_model._set_counts(model_t[0].tolist())
+        self.freq_model._from_table(model_t[0].tolist())
+
+    # batched API: every block starts from a copy of the model's CURRENT state.  For the fixed / IID
+    # models that is the creation-time table of the handle (re-created when the table changes); the
+    # order-k table is passed explicitly.
+    def encode_blocks(self, data, sizes=None, reuse=None):
+        if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:
+            return super().encode_blocks(data, sizes=sizes, reuse=reuse)
+        n_blocks = int(data.shape[0])
+        return self.device_coder().encode_blocks(data, sizes=sizes, model=self._model_tensor(n_blocks), reuse=reuse)
+
+    def decode_blocks(self, enc, max_block_len, out=None, reuse=None):
+        if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:
+            return super().decode_blocks(enc, max_block_len, out=out, reuse=reuse)
+        return self.device_coder().decode_blocks(enc, max_block_len, model=self._model_tensor(enc.n_blocks), out=out, reuse=reuse)
 
 
 class ArithmeticEncoder(_AecCoder, DataEncoder):

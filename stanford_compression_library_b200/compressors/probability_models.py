@@ -3,8 +3,8 @@
 The model objects live on the host and keep the reference's semantics -- in particular the
 table is MUTATED as symbols are coded and is never reset between blocks
 (probability_models.py:39-44, data_encoder_decoder.py:23-27).  On the device each block's model
-is a 256-counter Fenwick tree in shared memory (csrc/scl_lane.cuh aec_model_update); after a
-single-block call the final counts are copied back into `freqs_current`.
+lives in shared memory (csrc/scl_aec.cuh; first-generation Fenwick tree in csrc/scl_lane.cuh);
+after a single-block call the final table is copied back into the model object.
 """
 import abc
 import copy
@@ -26,8 +26,12 @@ class FreqModelBase(abc.ABC):
     def update_model(self, s):
         raise NotImplementedError
 
-    def _set_counts(self, counts):
-        for k, v in zip(list(self.freqs_current.freq_dict), counts):
+    # ---- device table: freqs_current in alphabet order (include/scl_b200.h scl_coder_model_words) ----
+    def _to_table(self):
+        return [int(f) for f in self.freqs_current.freq_list]
+
+    def _from_table(self, table):
+        for k, v in zip(list(self.freqs_current.freq_dict), table):
             self.freqs_current.freq_dict[k] = int(v)
 
 
@@ -52,19 +56,56 @@ class AdaptiveIIDFreqModel(FreqModelBase):
 
 
 class AdaptiveOrderKFreqModel(FreqModelBase):
-    """Order-k context model (probability_models.py:95-160).  k = 0 is exactly the adaptive IID
-    model started from all-ones (arithmetic_coding.py:449-463) and runs on the device; k > 0 is
-    listed as "next" in SURVEY.md 8(f) and is not implemented by this backend."""
+    """Order-k context model (probability_models.py:95-168): counts of (k+1)-tuples, all ones at
+    the start, the past k symbols (as alphabet indices, initially all 0) select the row used for the
+    next symbol.  Same attributes as the reference (`freqs_kplus1_tuple`, `past_k`, `freqs_current`).
+    On the device the whole table lives in shared memory, one copy per block being coded
+    (csrc/scl_aec.cuh AecCtxPolicy), so len(alphabet)^k * (len(alphabet) + 1) must be <= 1600.
 
-    CABI_MODEL = _cabi.MODEL_ADAPTIVE_IID
+    As in the reference there is no halving that works: when one count reaches
+    max_allowed_total_freq the reference's `np.max(count // 2, 1)` raises; here the coder raises
+    AssertionError (status SCL_ST_TOTAL_FREQ)."""
+
+    CABI_MODEL = _cabi.MODEL_ORDER_K
 
     def __init__(self, alphabet, k: int, max_allowed_total_freq: int):
         assert k >= 0
-        if k > 0:
-            raise NotImplementedError("order-k (k > 0) context models are not implemented on the device yet (SURVEY.md 8f)")
         self.k = k
-        self.alphabet = alphabet
-        super().__init__(Frequencies({a: 1 for a in alphabet}), max_allowed_total_freq)
+        self.alphabet = list(alphabet)
+        self.alphabet_to_idx = {a: i for i, a in enumerate(self.alphabet)}
+        self.freqs_kplus1_tuple = np.ones([len(self.alphabet)] * (k + 1), dtype=int)
+        self.max_allowed_total_freq = max_allowed_total_freq
+        self.past_k = [0] * k
+
+    @property
+    def freqs_current(self):
+        row = self.freqs_kplus1_tuple[tuple(self.past_k)] if self.k > 0 else self.freqs_kplus1_tuple
+        return Frequencies(dict(zip(self.alphabet, (int(f) for f in np.ravel(row)))))
 
     def update_model(self, s):
-        AdaptiveIIDFreqModel.update_model(self, s)
+        # host-side single-symbol update (:137-168); the coders apply the same rule on the device
+        cur = (*self.past_k, self.alphabet_to_idx[s])
+        self.freqs_kplus1_tuple[cur] += 1
+        if self.k > 0:
+            self.past_k = self.past_k[1:] + [self.alphabet_to_idx[s]]
+        if self.freqs_kplus1_tuple[cur] >= self.max_allowed_total_freq:
+            raise AssertionError("a (k+1)-tuple count reached max_allowed_total_freq (the reference's halving raises here)")
+
+    # ---- device table: [counts row-major][context index] (include/scl_b200.h scl_coder_model_words) ----
+    def _context_index(self):
+        ctx = 0
+        for d in self.past_k:
+            ctx = ctx * len(self.alphabet) + int(d)
+        return ctx
+
+    def _to_table(self):
+        return [int(v) for v in np.ravel(self.freqs_kplus1_tuple)] + [self._context_index()]
+
+    def _from_table(self, table):
+        n = len(self.alphabet)
+        self.freqs_kplus1_tuple = np.array(table[:-1], dtype=int).reshape([n] * (self.k + 1))
+        ctx, digits = int(table[-1]), []
+        for _ in range(self.k):
+            digits.append(ctx % n)
+            ctx //= n
+        self.past_k = digits[::-1]

@@ -159,6 +159,98 @@ struct AecModel {
     }
 };
 
+// ---- model policies: what the coder lanes ask of a frequency model ---------------------------
+//   total()            sum of freqs_current
+//   query(idx, c, f)   cumulative count below idx and the count of idx
+//   find(v, c, f)      last idx with cumulative count <= v  (v < total)
+//   update(idx)        update_model(s); returns a status word (the reference raises)
+
+// FixedFreqModel / AdaptiveIIDFreqModel (probability_models.py:57-92) over the two-level structure
+struct AecIidPolicy {
+    AecModel M;
+    uint32_t tot, adaptive, max_total, n_sym;
+    SCL_HD uint32_t total() const { return tot; }
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const { M.query(idx, cum, f); }
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        uint32_t idx = M.find(v, cum, f);
+        if (idx >= n_sym) {
+            idx = n_sym - 1;
+            M.query(idx, cum, f);
+        }
+        return idx;
+    }
+    SCL_HD uint32_t update(uint32_t idx) {
+        if (adaptive) {
+            M.add1(idx);
+            tot += 1;
+            if (tot >= max_total) {  // :90-92
+                uint64_t t64 = tot;
+                M.halve(n_sym, t64);
+                tot = (uint32_t)t64;
+            }
+        }
+        return SCL_ST_OK;
+    }
+};
+
+// AdaptiveOrderKFreqModel (probability_models.py:95-168).  Per lane: n_ctx = n_sym^k rows of n_sym
+// 32-bit counters (freqs_kplus1_tuple, row-major) followed by the n_ctx row totals; word i is
+// `stride` bytes after word i-1 like AecModel.  The row index is the base-n_sym number of the past k
+// alphabet indices (past_k, oldest digit first), which is how numpy indexes freqs_kplus1_tuple.
+// Rows are scanned linearly: meant for the small alphabets context models are used with.
+struct AecCtxPolicy {
+    saddr_t w;
+    uint32_t stride, n_sym, n_ctx, ctx, max_total;
+    SCL_HD uint32_t word(uint32_t i) const { return lds32(w + (saddr_t)(i * stride)); }
+    SCL_HD void set_word(uint32_t i, uint32_t v) const { sts32(w + (saddr_t)(i * stride), v); }
+    SCL_HD uint32_t n_words() const { return n_ctx * (n_sym + 1); }
+    SCL_HD uint32_t total() const { return word(n_ctx * n_sym + ctx); }
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const {
+        const uint32_t row = ctx * n_sym;
+        cum = 0;
+        for (uint32_t j = 0; j < idx; ++j) cum += word(row + j);
+        f = word(row + idx);
+    }
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        const uint32_t row = ctx * n_sym;
+        uint32_t idx = 0, below = 0;
+        f = word(row);
+        while (idx + 1 < n_sym && below + f <= v) {  // inclusive prefix <= v: the symbol lies further right
+            below += f;
+            idx += 1;
+            f = word(row + idx);
+        }
+        cum = below;
+        return idx;
+    }
+    // :137-168: count of (past_k, s) += 1, slide past_k; a count reaching max_allowed_total_freq makes the
+    // reference raise (its np.max(count // 2, 1) takes 1 as an axis) -> SCL_ST_TOTAL_FREQ
+    SCL_HD uint32_t update(uint32_t idx) {
+        const uint32_t at = ctx * n_sym + idx, cnt = word(at) + 1, tw = n_ctx * n_sym + ctx;
+        set_word(at, cnt);
+        set_word(tw, word(tw) + 1);
+        ctx = (ctx * n_sym + idx) % n_ctx;
+        return cnt >= max_total ? SCL_ST_TOTAL_FREQ : SCL_ST_OK;
+    }
+    // model table: [n_ctx * n_sym counts, row-major][context index]; NULL = fresh (all ones, context 0)
+    SCL_HD void load(const uint64_t *model) {
+        for (uint32_t r = 0; r < n_ctx; ++r) {
+            uint32_t sum = 0;
+            for (uint32_t j = 0; j < n_sym; ++j) {
+                const uint32_t v = model ? (uint32_t)model[r * n_sym + j] : 1u;
+                set_word(r * n_sym + j, v);
+                sum += v;
+            }
+            set_word(n_ctx * n_sym + r, sum);
+        }
+        ctx = model ? (uint32_t)(model[n_ctx * n_sym] % n_ctx) : 0u;
+    }
+    SCL_HD void store(uint64_t *model) const {
+        for (uint32_t i = 0; i < n_ctx * n_sym; ++i) model[i] = word(i);
+        model[n_ctx * n_sym] = ctx;
+    }
+};
+
 // ---- closed-form renormalisation ------------------------------------------------------------
 // State: low in [0, 2^P), high in (low, 2^P].  Let hm = high - 1.
 // E1/E2 loop (:126-143): every iteration drops a COMMON leading bit of low and hm.  The reference's
@@ -243,17 +335,40 @@ SCL_HD double aec_floor_div(double a, double t, double rcp) {
         q += 1.0;
     return q;
 }
+// shrink_range (:58-78): low += rng * c // T, high = low + rng * (c + f) // T.  One FP64 multiply per
+// quotient while the products stay below 2^53 (rng <= 2^32, T < 2^20: always for the 16-bit IID
+// structure); beyond that (order-k rows that have seen > 2^20 symbols) 64-bit integer division.
+SCL_HD void aec_shrink(uint32_t &low, uint32_t &hm, uint32_t cc, uint32_t f, uint32_t total) {
+    if (total >> 20) {
+        const uint64_t lo64 = low, rng = (uint64_t)hm - lo64 + 1;  // rng * (cc + f) < 2^32 * 2^30
+        hm = (uint32_t)(lo64 + rng * (uint64_t)(cc + f) / total - 1);
+        low = (uint32_t)(lo64 + rng * (uint64_t)cc / total);
+    } else {
+        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
+        const double rng_d = (double)hm - low_d + 1.0;
+        hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
+        low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
+    }
+}
+// decode_step_core's target (:177-201): ((state - low + 1) * T - 1) // rng
+SCL_HD uint32_t aec_target(uint32_t state, uint32_t low, uint32_t hm, uint32_t total) {
+    if (total >> 20) {
+        const uint64_t rng = (uint64_t)hm - low + 1;
+        return (uint32_t)((((uint64_t)state - low + 1) * total - 1) / rng);
+    }
+    const double low_d = (double)low, rng_d = (double)hm - low_d + 1.0;
+    return (uint32_t)aec_floor_div(((double)state - low_d + 1.0) * (double)total - 1.0, rng_d, 1.0 / rng_d);
+}
 
 // ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
-SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total64, const uint8_t *sym, uint64_t sym_cap,
-                                 uint32_t n, FwdBitWriter &w, uint64_t &bits_out, uint64_t &total_out) {
+template <class Policy>
+SCL_HD uint32_t aec2_encode_lane(Policy &M, const AecTab &tab, const AecConst &c, const uint8_t *sym, uint64_t sym_cap, uint32_t n,
+                                 FwdBitWriter &w, uint64_t &bits_out) {
     SymWindow sw;
     sw.init(sym, sym_cap);
     const uint32_t P = c.P;
     const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
-    const uint32_t max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
     uint32_t low = 0, hm = pm, num_mid = 0;  // high = FULL
-    uint32_t total = (uint32_t)total64;      // < 2^20 (16 group totals below 2^16)
     uint32_t st = SCL_ST_OK;
     if (c.DBSB < 32 && (n >> c.DBSB)) st = SCL_ST_OVERFLOW;
     w.put64((uint64_t)n, c.DBSB);
@@ -263,26 +378,16 @@ SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const Aec
             st = SCL_ST_BAD_SYMBOL;
             break;
         }
+        const uint32_t total = M.total();
         if (!(total < QTR)) {  // :110-112
             st = SCL_ST_TOTAL_FREQ;
             break;
         }
         uint32_t cc, f;
         M.query(idx, cc, f);
-        // shrink_range (:58-78): rng * d < 2^33 * 2^20, exact in FP64
-        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
-        const double rng_d = (double)hm - low_d + 1.0;
-        hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
-        low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
-        if (c.model == SCL_MODEL_ADAPTIVE_IID) {  // update_model (:118)
-            M.add1(idx);
-            total += 1;
-            if (total >= max_total) {
-                uint64_t t64 = total;
-                M.halve(c.n_sym, t64);
-                total = (uint32_t)t64;
-            }
-        }
+        aec_shrink(low, hm, cc, f, total);
+        st = M.update(idx);  // update_model (:118)
+        if (st != SCL_ST_OK) break;
         const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
         if (ne) {
             const uint32_t prefix = low >> (P - ne);
@@ -315,7 +420,6 @@ SCL_HD uint32_t aec2_encode_lane(const AecModel &M, const AecTab &tab, const Aec
         w.put_run(0, num_mid);
     }
     bits_out = w.finish();
-    total_out = total;
     if (w.ovf) st = SCL_ST_OVERFLOW;
     return st;
 }
@@ -336,60 +440,44 @@ SCL_HD uint32_t aec_get_bits(BitReader &r, uint64_t &nbc, uint64_t A, uint32_t k
 }
 
 // ArithmeticDecoder.decode_block (arithmetic_coding.py:203-287)
-SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const AecConst &c, uint64_t total64, BitReader &r,
-                                 uint64_t avail_bits, uint8_t *out, uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed,
-                                 uint64_t &total_out) {
+template <class Policy>
+SCL_HD uint32_t aec2_decode_lane(Policy &M, const AecTab &tab, const AecConst &c, BitReader &r, uint64_t avail_bits, uint8_t *out,
+                                 uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed) {
     const uint32_t P = c.P;
     const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
-    const uint32_t max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
     uint64_t size64 = r.get64(c.DBSB);
     size_out = 0;
-    total_out = total64;
     if (size64 > out_cap) return SCL_ST_OVERFLOW;
     if (size64 == 0) return SCL_ST_EMPTY_BLOCK;
     const uint32_t size = (uint32_t)size64;
     const uint64_t A = avail_bits > c.DBSB ? avail_bits - c.DBSB : 0;
     uint64_t nbc = 0;
-    uint32_t low = 0, hm = pm, total = (uint32_t)total64;
+    uint32_t low = 0, hm = pm;
     uint32_t state = aec_get_bits(r, nbc, A, P);  // :222-229 (MSB first, zero fill)
     uint32_t st = SCL_ST_OK;
     OutWindow ow;
     ow.init(out);
     for (uint32_t i = 0;;) {
+        const uint32_t total = M.total();
         if (!(total < QTR)) {
             st = SCL_ST_TOTAL_FREQ;
             break;
         }
-        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
-        const double rng_d = (double)hm - low_d + 1.0;
         uint32_t idx, cc, f;
         if (state < low) {
             idx = c.n_sym - 1;  // searchsorted -> 0, alphabet[-1]
             M.query(idx, cc, f);
         } else {
-            // decode_step_core (:177-201): last idx with cum <= ((state - low + 1) * T - 1) // rng ; product < 2^52
-            double v_d = aec_floor_div(((double)state - low_d + 1.0) * t_d - 1.0, rng_d, 1.0 / rng_d);
-            uint32_t v = (uint32_t)v_d;
+            // decode_step_core (:177-201): last idx with cum <= ((state - low + 1) * T - 1) // rng
+            uint32_t v = aec_target(state, low, hm, total);
             if (v >= total) v = total - 1;
             idx = M.find(v, cc, f);
-            if (idx >= c.n_sym) {
-                idx = c.n_sym - 1;
-                M.query(idx, cc, f);
-            }
         }
-        hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
-        low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
+        aec_shrink(low, hm, cc, f, total);
         ow.push(i, tab.idx2sym[idx]);
         ++i;
-        if (c.model == SCL_MODEL_ADAPTIVE_IID) {
-            M.add1(idx);
-            total += 1;
-            if (total >= max_total) {
-                uint64_t t64 = total;
-                M.halve(c.n_sym, t64);
-                total = (uint32_t)t64;
-            }
-        }
+        st = M.update(idx);
+        if (st != SCL_ST_OK) break;
         if (i == size) break;  // :242-243
         const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
         if (ne) {
@@ -412,7 +500,6 @@ SCL_HD uint32_t aec2_decode_lane(const AecModel &M, const AecTab &tab, const Aec
     }
     if (extra == P) extra = P - 1;
     size_out = size;
-    total_out = total;
     bits_consumed = (uint64_t)((int64_t)nbc - ((int64_t)extra - 1) + (int64_t)c.DBSB);
     return st;
 }

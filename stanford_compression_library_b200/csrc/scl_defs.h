@@ -76,9 +76,11 @@ struct alignas(16) AecTab {
     uint16_t sym2idx[256];
     uint8_t idx2sym[256];
 };
+constexpr uint32_t kAecCtxMaxWords = 1600;  // order-k model: n_ctx * (n_sym + 1) words per lane = 200 KB of shared memory per warp
 struct AecConst {
     uint32_t P, DBSB, n_sym, model;
-    uint64_t max_total;  // FreqModelBase.max_allowed_total_freq
+    uint64_t max_total;      // FreqModelBase.max_allowed_total_freq
+    uint32_t order_k, n_ctx; // AdaptiveOrderKFreqModel: k and n_sym^k (1 for the other models)
 };
 
 }  // namespace scl

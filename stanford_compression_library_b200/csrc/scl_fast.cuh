@@ -33,18 +33,6 @@ SCL_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) {  // (hi:lo) >>
     return s >= 32 ? hi : funnel_r(lo, hi, s);
 #endif
 }
-// x >> s on the FMA pipe (IMAD.HI) instead of the ALU pipe; s in 1..31 (compile-time constant use)
-SCL_HD uint32_t shr_fma(uint32_t x, uint32_t s) {
-#ifdef __CUDA_ARCH__
-    uint32_t r, m = 1u << (32 - s);
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(m));
-    return r;
-#else
-    return x >> s;
-#endif
-}
-
-
 // ---- shared-memory access through plain addresses --------------------------------------------
 // On the device `saddr_t` is a 32-bit shared-window address and every access is ONE explicit
 // ld/st.shared of the stated width (the compiler otherwise splits a 16-byte entry read into
@@ -399,7 +387,6 @@ struct DecConst {
     uint32_t m4;      // (M - 1) * 4
     uint32_t xq_mul;  // 2^(32 - log2 M): umulhi(x, xq_mul) = x >> log2 M
     uint32_t kbase;   // clz(x) - kbase = bits missing to reach L   (kbase = 31 - log2 L)
-    uint32_t nbo;
 };
 
 // One decode step (rans_base_decode_step + expand_state, rANS.py:234-260) on lut entry
@@ -559,7 +546,6 @@ struct RansStepper {
         dc.m4 = ((uint32_t)c.M - 1) << 2;
         dc.xq_mul = c.m_log2 ? (1u << (32 - c.m_log2)) : 0u;
         dc.kbase = 31 - c.l_log2;
-        dc.nbo = NBO;
         l_log2 = c.l_log2;
         m_log2 = c.m_log2;
     }

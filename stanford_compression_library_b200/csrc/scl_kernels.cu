@@ -607,9 +607,6 @@ constexpr uint32_t kAec2Warps = 4;
 constexpr uint32_t kAec2ModelBytes = kAecModelWords * 128;      // per warp
 constexpr uint32_t kAec2MaskBytes = 17 * kEncTabCopies * 16;    // 17 entries x 8 replicas x 16 B
 
-struct Aec2Smem {
-    AecModel M;
-};
 __device__ __forceinline__ AecModel aec2_setup(uint8_t *smem, const AecTab *g_tab, AecTab *s_tab, uint64_t *mbar) {
     // smem: [mask table][models per warp]
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -628,6 +625,18 @@ __device__ __forceinline__ AecModel aec2_setup(uint8_t *smem, const AecTab *g_ta
     return M;
 }
 
+__device__ __forceinline__ AecIidPolicy aec2_iid_policy(const AecModel &M, const AecTab &tab, const AecConst &c) {
+    AecIidPolicy pol;
+    pol.M = M;
+    uint64_t total = 0;
+    M.load(tab.init_freq, nullptr, c.n_sym, total);
+    pol.tot = (uint32_t)total;
+    pol.adaptive = c.model == SCL_MODEL_ADAPTIVE_IID;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    pol.n_sym = c.n_sym;
+    return pol;
+}
+
 __global__ void __launch_bounds__(kAec2Warps * 32) aec2_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ AecTab s_tab;
@@ -635,13 +644,13 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_encode_kernel(const AecT
     const AecModel M = aec2_setup(s_dyn, g_tab, &s_tab, &mbar);
     uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
     if (b >= io.n_blocks) return;
-    uint64_t total = 0, total_out = 0, bits = 0;
-    M.load(s_tab.init_freq, nullptr, c.n_sym, total);
+    AecIidPolicy pol = aec2_iid_policy(M, s_tab, c);
+    uint64_t bits = 0;
     uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(M, s_tab, c, total, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits, total_out);
+    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
     io.status[b] = st;
@@ -654,14 +663,81 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_decode_kernel(const AecT
     const AecModel M = aec2_setup(s_dyn, g_tab, &s_tab, &mbar);
     uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
     if (b >= io.n_blocks) return;
-    uint64_t total = 0, total_out = 0, used = 0;
-    M.load(s_tab.init_freq, nullptr, c.n_sym, total);
+    AecIidPolicy pol = aec2_iid_policy(M, s_tab, c);
+    uint64_t used = 0;
     BitReader r;
     uint64_t off = io.bit_off[b];
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
-    uint32_t st = aec2_decode_lane(M, s_tab, c, total, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used,
-                                   total_out);
+    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arithmetic coder with the order-k context model (AecCtxPolicy): per lane n_ctx rows of n_sym
+// counters + n_ctx row totals, 32-bit, [word][lane] in shared memory (as many warps per CTA as
+// fit); the model table (d_model) carries the counts and the context from one call to the next
+// like the reference's model object does.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kAecCtxMaxWarps = 4;
+static uint32_t aec_ctx_warps(const AecConst &c) {
+    uint32_t per_warp = c.n_ctx * (c.n_sym + 1) * 128, fit = (200u * 1024u) / per_warp;
+    return fit > kAecCtxMaxWarps ? kAecCtxMaxWarps : (fit ? fit : 1);
+}
+
+__device__ __forceinline__ AecCtxPolicy aec_ctx_setup(uint8_t *smem, const AecConst &c) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AecCtxPolicy pol;
+    pol.n_sym = c.n_sym;
+    pol.n_ctx = c.n_ctx;
+    pol.w = saddr_of(smem + warp * (pol.n_words() * 128)) + lane * 4;
+    pol.stride = 128;
+    pol.ctx = 0;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    return pol;
+}
+
+__global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    AecCtxPolicy pol = aec_ctx_setup(s_dyn, c);
+    uint64_t *my_model = model ? model + b * ((uint64_t)c.n_ctx * c.n_sym + 1) : nullptr;
+    pol.load(my_model);
+    uint64_t bits = 0;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    if (my_model) pol.store(my_model);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    AecCtxPolicy pol = aec_ctx_setup(s_dyn, c);
+    uint64_t *my_model = model ? model + b * ((uint64_t)c.n_ctx * c.n_sym + 1) : nullptr;
+    pol.load(my_model);
+    uint64_t used = 0;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    if (my_model) pol.store(my_model);
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
@@ -980,6 +1056,8 @@ extern "C" uint64_t scl_coder_max_encoded_bytes(const scl_coder *c, uint64_t blo
     return (bytes + 31) & ~31ull;         // whole 32-byte sectors (the v2 encoder drains sector-wise)
 }
 
+extern "C" uint64_t scl_coder_model_words(const scl_coder *c) { return c && c->aec ? c->aec->model_words() : 0; }
+
 extern "C" int scl_coder_path(const scl_coder *c, int decode) {
     if (c->rans) return decode ? (c->rans->dec32 ? 0 : 1) : (c->rans->enc32 ? 0 : 1);
     return 0;
@@ -1148,6 +1226,14 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         range_encode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
         return check_launch("range_encode_kernel");
     }
+    if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K) {
+        const uint32_t warps = aec_ctx_warps(c->aec->c);
+        uint32_t g2 = (uint32_t)((n_blocks + warps * 32 - 1) / (warps * 32));
+        size_t smem = (size_t)warps * c->aec->c.n_ctx * (c->aec->c.n_sym + 1) * 128;
+        SCL_CUDA(cudaFuncSetAttribute(aec_ctx_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aec_ctx_encode_kernel<<<g2, warps * 32, smem, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_ctx_encode_kernel");
+    }
     if (c->aec) {
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
         // 16-bit counters when no count can reach 65536: counts start at init_freq and grow by at most
@@ -1210,6 +1296,14 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         SCL_CUDA(cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->range_lut_bytes));
         range_decode_kernel<<<grid, kThreads, c->range_lut_bytes, s>>>(c->d_range, c->d_range_lut, c->range_lut_bytes, c->range->c, io);
         return check_launch("range_decode_kernel");
+    }
+    if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K) {
+        const uint32_t warps = aec_ctx_warps(c->aec->c);
+        uint32_t g2 = (uint32_t)((n_blocks + warps * 32 - 1) / (warps * 32));
+        size_t smem = (size_t)warps * c->aec->c.n_ctx * (c->aec->c.n_sym + 1) * 128;
+        SCL_CUDA(cudaFuncSetAttribute(aec_ctx_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aec_ctx_decode_kernel<<<g2, warps * 32, smem, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_ctx_decode_kernel");
     }
     if (c->aec) {
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);

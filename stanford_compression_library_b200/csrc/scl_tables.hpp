@@ -281,7 +281,17 @@ struct AecHost {
         if (rc) return rc;
         if (p.precision < 4 || p.precision > 32) return SCL_E_UNSUPPORTED;
         if (p.data_block_size_bits > 64) return SCL_E_INVALID;
-        if (p.model != SCL_MODEL_FIXED && p.model != SCL_MODEL_ADAPTIVE_IID) return SCL_E_UNSUPPORTED;
+        if (p.model != SCL_MODEL_FIXED && p.model != SCL_MODEL_ADAPTIVE_IID && p.model != SCL_MODEL_ORDER_K) return SCL_E_UNSUPPORTED;
+        if (p.model != SCL_MODEL_ORDER_K && p.model_order != 0) return SCL_E_INVALID;
+        c.order_k = p.model_order;
+        c.n_ctx = 1;
+        if (p.model == SCL_MODEL_ORDER_K) {  // per-lane table in shared memory: n_sym^k * (n_sym + 1) words
+            for (uint32_t j = 0; j < p.model_order && n_sym > 1; ++j) {
+                c.n_ctx *= n_sym;
+                if ((uint64_t)c.n_ctx * (n_sym + 1) > kAecCtxMaxWords) return SCL_E_UNSUPPORTED;
+            }
+            if ((uint64_t)c.n_ctx * (n_sym + 1) > kAecCtxMaxWords) return SCL_E_UNSUPPORTED;
+        }
         memset(&t, 0, sizeof(t));
         for (uint32_t i = 0; i < n_sym; ++i) {
             if (f[i] == 0 || f[i] >> 31) return SCL_E_INVALID;
@@ -299,6 +309,7 @@ struct AecHost {
     // each symbol narrows the range by at most a factor T < 2^(P-2): <= P bits per symbol, plus
     // the size header and the <= P+1 termination bits
     uint64_t max_encoded_bits(uint64_t n) const { return (uint64_t)c.DBSB + (uint64_t)c.P * n + c.P + 2; }
+    uint64_t model_words() const { return c.model == SCL_MODEL_ORDER_K ? (uint64_t)c.n_ctx * c.n_sym + 1 : c.n_sym; }
 };
 
 }  // namespace scl

@@ -65,6 +65,8 @@ class EmuCoder:
         self.n_sym = freq.size
         h = ctypes.c_void_p()
         rc = lib().emu_create(ctypes.byref(params), _p(alphabet), _p(freq), freq.size, ctypes.byref(h))
+        if rc == 3:  # SCL_E_UNSUPPORTED
+            raise NotImplementedError("emu_create: outside the backend's limits")
         if rc:
             raise ValueError("emu_create rc=%d" % rc)
         self.h = h
@@ -173,6 +175,6 @@ def params_from_case(c):
     if c["coder"] == "range":
         return SclParams(coder=_cabi.CODER_RANGE, data_block_size_bits=p["DATA_BLOCK_SIZE_BITS"], num_bits_out=0, range_factor=0, num_state_bits=0,
                          precision=p["PRECISION"], model=0, max_allowed_total_freq=0)
-    kind = _cabi.MODEL_ADAPTIVE_IID if c["model"]["kind"] == "adaptive_iid" else _cabi.MODEL_FIXED
+    kind = {"adaptive_iid": _cabi.MODEL_ADAPTIVE_IID, "order_k": _cabi.MODEL_ORDER_K}.get(c["model"]["kind"], _cabi.MODEL_FIXED)
     return SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=p["DATA_BLOCK_SIZE_BITS"], num_bits_out=0, range_factor=0, num_state_bits=0,
-                     precision=p["PRECISION"], model=kind, max_allowed_total_freq=c["model"]["max_total"])
+                     precision=p["PRECISION"], model=kind, model_order=c["model"].get("k", 0), max_allowed_total_freq=c["model"]["max_total"])

@@ -29,3 +29,18 @@ def with_garbage(enc, nbits, garbage):
 
 def case_id(c):
     return "%02d-%s-%s" % (c["id"], c["coder"], c["note"][:40].replace(" ", "_"))
+
+
+def fresh_model_table(c):
+    """the model table handed to the oracle: IID/fixed -> the initial freqs; order-k -> ones + context 0"""
+    if c["coder"] != "aec":
+        return None
+    if c["model"]["kind"] == "order_k":
+        n = len(c["freqs"]) ** (c["model"]["k"] + 1)
+        return np.array([1] * n + [0], dtype=np.uint64)
+    return np.array(c["freqs"], dtype=np.uint64)
+
+
+def expected_final_model(c):
+    m = c["model"]
+    return m["final_freqs"] + [m["final_ctx"]] if m["kind"] == "order_k" else m["final_freqs"]

@@ -150,6 +150,29 @@ int emu_tans_tables(void *h, uint32_t *enc, uint32_t *dec, uint64_t n) {
     return 0;
 }
 
+}  // extern "C"
+static AecIidPolicy make_iid_policy(uint32_t *words, const AecTab &t, const AecConst &c, const uint64_t *mm) {
+    AecIidPolicy pol;
+    pol.M = AecModel{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
+    uint64_t total = 0;
+    pol.M.load(t.init_freq, mm, c.n_sym, total);
+    pol.tot = (uint32_t)total;
+    pol.adaptive = c.model == SCL_MODEL_ADAPTIVE_IID;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    pol.n_sym = c.n_sym;
+    return pol;
+}
+static AecCtxPolicy make_ctx_policy(uint32_t *words, const AecConst &c) {
+    AecCtxPolicy pol;
+    pol.w = saddr_of(words);
+    pol.stride = 4;
+    pol.n_sym = c.n_sym;
+    pol.n_ctx = c.n_ctx;
+    pol.ctx = 0;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    return pol;
+}
+extern "C" {
 int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const uint32_t *sizes, uint32_t block_len, uint64_t n_blocks,
                       uint8_t *out, uint64_t out_stride, uint64_t *bit_off, uint64_t *bit_len, uint64_t *model, uint32_t *status) {
     Emu *e = (Emu *)h;
@@ -180,14 +203,19 @@ int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const ui
             w.init(slot, slot + out_stride);
             if (e->range) {
                 st = range_encode_lane(e->range->t, e->range->c, row, sym_stride, n, w, bits);
+            } else if (e->aec->c.model == SCL_MODEL_ORDER_K) {
+                alignas(16) uint32_t words[kAecCtxMaxWords];
+                AecCtxPolicy pol = make_ctx_policy(words, e->aec->c);
+                uint64_t *mm = model ? model + b * e->aec->model_words() : nullptr;
+                pol.load(mm);
+                st = aec2_encode_lane(pol, e->aec->t, e->aec->c, row, sym_stride, n, w, bits);
+                if (mm) pol.store(mm);
             } else if (e->aec2) {
                 alignas(16) uint32_t words[kAecModelWords];
-                AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
                 uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
-                uint64_t total = 0, tout = 0;
-                M.load(e->aec->t.init_freq, mm, e->aec->c.n_sym, total);
-                st = aec2_encode_lane(M, e->aec->t, e->aec->c, total, row, sym_stride, n, w, bits, tout);
-                if (mm) M.store(mm, e->aec->c.n_sym);
+                AecIidPolicy pol = make_iid_policy(words, e->aec->t, e->aec->c, mm);
+                st = aec2_encode_lane(pol, e->aec->t, e->aec->c, row, sym_stride, n, w, bits);
+                if (mm) pol.M.store(mm, e->aec->c.n_sym);
             } else {
                 HostTree F;
                 uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
@@ -224,14 +252,19 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
             if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         } else if (e->range) {
             st = range_decode_lane(e->range->t, e->range->c, e->range->lut.data(), r, avail, row, sym_stride, size, used);
+        } else if (e->aec->c.model == SCL_MODEL_ORDER_K) {
+            alignas(16) uint32_t words[kAecCtxMaxWords];
+            AecCtxPolicy pol = make_ctx_policy(words, e->aec->c);
+            uint64_t *mm = model ? model + b * e->aec->model_words() : nullptr;
+            pol.load(mm);
+            st = aec2_decode_lane(pol, e->aec->t, e->aec->c, r, avail, row, sym_stride, size, used);
+            if (mm) pol.store(mm);
         } else if (e->aec2) {
             alignas(16) uint32_t words[kAecModelWords];
-            AecModel M{saddr_of(words), 4, saddr_of(g_aec_masks), 16};
             uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
-            uint64_t total = 0, tout = 0;
-            M.load(e->aec->t.init_freq, mm, e->aec->c.n_sym, total);
-            st = aec2_decode_lane(M, e->aec->t, e->aec->c, total, r, avail, row, sym_stride, size, used, tout);
-            if (mm) M.store(mm, e->aec->c.n_sym);
+            AecIidPolicy pol = make_iid_policy(words, e->aec->t, e->aec->c, mm);
+            st = aec2_decode_lane(pol, e->aec->t, e->aec->c, r, avail, row, sym_stride, size, used);
+            if (mm) pol.M.store(mm, e->aec->c.n_sym);
         } else {
             HostTree F;
             uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;

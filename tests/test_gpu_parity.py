@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import scl_oracle as so
-from tests.golden_util import case_id, load_golden, with_garbage
+from tests.golden_util import case_id, expected_final_model, load_golden, with_garbage
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +37,7 @@ def _F(freqs):
 def make_codec(c):
     """(encoder, decoder) drop-in objects for a golden case."""
     from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
-    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, FixedFreqModel
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, AdaptiveOrderKFreqModel, FixedFreqModel
     from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
     from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
     from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
@@ -52,6 +52,9 @@ def make_codec(c):
         params = RangeCoderParams(**p)
         return RangeEncoder(params, _F(c["freqs"])), RangeDecoder(params, _F(c["freqs"]))
     params = AECParams(**p)
+    if c["model"]["kind"] == "order_k":
+        m = AdaptiveOrderKFreqModel(list(range(len(c["freqs"]))), c["model"]["k"], c["model"]["max_total"])
+        return ArithmeticEncoder(params, m), ArithmeticDecoder(params, copy.deepcopy(m))
     cls = AdaptiveIIDFreqModel if c["model"]["kind"] == "adaptive_iid" else FixedFreqModel
     m = cls(_F(c["freqs"]), c["model"]["max_total"])
     return ArithmeticEncoder(params, m), ArithmeticDecoder(params, copy.deepcopy(m))
@@ -67,11 +70,13 @@ def test_dropin_classes_match_golden(c):
     assert len(ba) == c["nbits"]
     assert ba.tobytes() == c["enc"].tobytes()
     if c["coder"] == "aec":
-        assert [int(x) for x in enc.freq_model.freqs_current.freq_list] == c["model"]["final_freqs"]
+        assert enc.freq_model._to_table() == expected_final_model(c)
     packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
     block, used = dec.decode_block(BitArray.from_packed(packed, total))
     assert list(block.data_list) == c["data"].tolist()
     assert used == c["consumed"] == c["nbits"]
+    if c["coder"] == "aec":
+        assert dec.freq_model._to_table() == expected_final_model(c)
 
 
 def test_kat_string_symbols():
@@ -243,6 +248,84 @@ def test_aec_model_persists_across_encode_block_calls():
         assert [int(x) for x in enc.freq_model.freqs_current.freq_list] == mf.tolist()
         out, used = dec.decode_block(ba)
         assert list(out.data_list) == blk.tolist() and used == ref_bits
+
+
+def _markov2(n, seed=0):
+    """the source of the reference's order-k test (arithmetic_coding.py:388-402), restated"""
+    rng = np.random.default_rng(seed)
+    bits = rng.choice(2, size=n - 2)
+    x = np.zeros(n, dtype=np.uint8)
+    x[0], x[1] = rng.choice(3), rng.choice(3)
+    for i in range(2, n):
+        x[i] = (x[i - 1] + x[i - 2] + bits[i - 2]) % 3
+    return x
+
+
+def test_aec_order_k_reference_test_restated():
+    """scl/compressors/arithmetic_coding.py:405-463: lossless + expected bitrate for k = 0..3 on a
+    2nd-order Markov source, order 0 == the adaptive IID model exactly; every stream also against the oracle."""
+    from stanford_compression_library_b200 import DataBlock
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, AdaptiveOrderKFreqModel
+
+    n = 10000
+    x = _markov2(n)
+    blk = DataBlock(x.tolist())
+    streams = {}
+    for k, expected in ((0, np.log2(3)), (1, np.log2(3)), (2, 1.0), (3, 1.0)):
+        params = AECParams()
+        m = AdaptiveOrderKFreqModel([0, 1, 2], k, params.MAX_ALLOWED_TOTAL_FREQ)
+        enc, dec = ArithmeticEncoder(params, m), ArithmeticDecoder(params, copy.deepcopy(m))
+        ba = enc.encode_block(blk)
+        out, used = dec.decode_block(ba)
+        assert list(out.data_list) == x.tolist() and used in (len(ba), len(ba) - 1)
+        assert abs(len(ba) / n - expected) < 0.1, (k, len(ba) / n)
+        oracle = so.Oracle.aec([1, 1, 1], model=so.MODEL_ORDER_K, k=k)
+        table = np.array([1] * 3 ** (k + 1) + [0], dtype=np.uint64)
+        ref, ref_bits = oracle.encode_block(x, model_freq=table)
+        assert len(ba) == ref_bits and ba.tobytes() == ref.tobytes()
+        assert enc.freq_model._to_table() == table.tolist() == dec.freq_model._to_table()
+        assert enc.freq_model.freqs_kplus1_tuple.shape == (3,) * (k + 1) and len(enc.freq_model.past_k) == k
+        streams[k] = ba
+    params = AECParams()
+    iid = ArithmeticEncoder(params, AdaptiveIIDFreqModel(_F([1, 1, 1]), params.MAX_ALLOWED_TOTAL_FREQ))
+    assert iid.encode_block(blk) == streams[0]
+
+
+def test_aec_order_k_batched_and_persistent():
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveOrderKFreqModel
+
+    rng = np.random.default_rng(11)
+    for n_sym, k, P in ((2, 5, 32), (4, 2, 32), (6, 2, 20), (16, 1, 32), (3, 5, 32)):
+        B, N = 256, 700
+        host = rng.integers(0, n_sym, size=(B, N)).astype(np.uint8)
+        keep = rng.random((B, N)) < 0.7
+        for j in range(1, N):
+            host[:, j] = np.where(keep[:, j], host[:, j - 1], host[:, j])
+        data = torch.from_numpy(host).cuda()
+        sizes = _seeded_sizes(1, N + 1, B)
+        params = AECParams(PRECISION=P)
+        m = AdaptiveOrderKFreqModel(list(range(n_sym)), k, params.MAX_ALLOWED_TOTAL_FREQ)
+        enc, dec = ArithmeticEncoder(params, m), ArithmeticDecoder(params, copy.deepcopy(m))
+        oracle = so.Oracle.aec([1] * n_sym, PRECISION=P, model=so.MODEL_ORDER_K, k=k)
+        _compare_batch_with_oracle(enc, dec, oracle, data, sample=range(0, B, 7), consumed_equals_length=False)
+        _compare_batch_with_oracle(enc, dec, oracle, data, sizes=sizes, sample=range(0, B, 5), consumed_equals_length=False)
+        assert enc.freq_model._to_table() == [1] * n_sym ** (k + 1) + [0]  # batched calls leave the host model alone
+
+
+def test_aec_order_k_count_limit_and_table_limit():
+    from stanford_compression_library_b200 import DataBlock
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveOrderKFreqModel
+
+    params = AECParams()
+    enc = ArithmeticEncoder(params, AdaptiveOrderKFreqModel([0, 1], 1, 20))
+    with pytest.raises(AssertionError):  # a count reaches 20: the reference's update_model raises (probability_models.py:164-168)
+        enc.encode_block(DataBlock([0] * 40))
+    enc = ArithmeticEncoder(params, AdaptiveOrderKFreqModel(list(range(40)), 1, params.MAX_ALLOWED_TOTAL_FREQ))
+    with pytest.raises(NotImplementedError):  # 40 * 41 words per block do not fit shared memory
+        enc.encode_block(DataBlock([0, 1, 2]))
 
 
 def test_pack_and_frame_kernels():

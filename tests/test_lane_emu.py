@@ -7,7 +7,7 @@ import pytest
 
 from oracle import scl_oracle as so
 from tests.emu_util import EmuCoder, extract_bits, params_from_case
-from tests.golden_util import case_id, load_golden, with_garbage
+from tests.golden_util import case_id, expected_final_model, fresh_model_table, load_golden, with_garbage
 
 CASES = load_golden()
 
@@ -17,19 +17,19 @@ def _roundtrip_case(c, force_generic=False):
     if force_generic:
         coder.force_generic()
     n = c["n"]
-    model = np.array([c["freqs"]], dtype=np.uint64) if c["coder"] == "aec" else None
+    model = fresh_model_table(c)[None] if c["coder"] == "aec" else None
     out, off, ln, st = coder.encode(c["data"].reshape(1, -1), model=model)
     assert st[0] == 0
     assert int(ln[0]) == c["nbits"]
     assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
     if c["coder"] == "aec":
-        assert model[0].tolist() == c["model"]["final_freqs"]
+        assert model[0].tolist() == expected_final_model(c)
     # decode stream + garbage placed at an odd bit offset
     packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
     lead = 5
     bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
     buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
-    model = np.array([c["freqs"]], dtype=np.uint64) if c["coder"] == "aec" else None
+    model = fresh_model_table(c)[None] if c["coder"] == "aec" else None
     if c["coder"] == "aec" and n == 0:
         return
     sym, sizes, used, st = coder.decode(buf, [lead], [total], max(n, 1), model=model)
@@ -336,22 +336,22 @@ def test_emu_aec2_matches_golden(c):
     coder = EmuCoder(params_from_case(c), None, c["freqs"])
     coder.set_aec2(True)
     n = c["n"]
-    model = np.array([c["freqs"]], dtype=np.uint64)
+    model = fresh_model_table(c)[None].copy()
     out, off, ln, st = coder.encode(c["data"].reshape(1, -1), model=model)
     assert st[0] == 0 and int(ln[0]) == c["nbits"]
     assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
-    assert model[0].tolist() == c["model"]["final_freqs"]
+    assert model[0].tolist() == expected_final_model(c)
     if n == 0:
         return
     packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
     lead = 3
     bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
     buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
-    model = np.array([c["freqs"]], dtype=np.uint64)
+    model = fresh_model_table(c)[None].copy()
     sym, sizes, used, st = coder.decode(buf, [lead], [total], n, model=model)
     assert st[0] == 0 and int(sizes[0]) == n and int(used[0]) == c["consumed"]
     assert sym[0, :n].tolist() == c["data"].tolist()
-    assert model[0].tolist() == c["model"]["final_freqs"]
+    assert model[0].tolist() == expected_final_model(c)
 
 
 @pytest.mark.parametrize("seed", range(6))
@@ -390,3 +390,68 @@ def test_emu_aec2_vs_oracle_random(seed):
             if ok[b]:
                 assert st2[b] == 0 and dsz[b] == sizes[b] and used[b] == ln[b], (P, max_total, b)
                 assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+
+
+# ---- order-k context model (csrc/scl_aec.cuh AecCtxPolicy) ------------------------------------
+@pytest.mark.parametrize("n_sym,k", [(1, 2), (2, 0), (2, 1), (2, 7), (3, 3), (4, 2), (7, 1), (16, 1), (39, 1), (256, 0)])
+def test_emu_order_k_vs_oracle_random(n_sym, k):
+    """two consecutive batches through the same model tables (the reference's model object is never
+    reset between encode_block calls), every stream and every final table against the oracle"""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(900 + n_sym * 10 + k)
+    B, N = 3, int(rng.integers(20, 500))
+    words = n_sym ** (k + 1) + 1
+    for P, max_total in ((32, 1 << 30), (14, 1 << 12), (32, 24)):
+        oracle = so.Oracle.aec([1] * n_sym, PRECISION=P, model=so.MODEL_ORDER_K, k=k, max_allowed_total_freq=max_total)
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=P,
+                        model=_cabi.MODEL_ORDER_K, model_order=k, max_allowed_total_freq=max_total)
+        coder = EmuCoder(prm, None, [1] * n_sym)
+        fresh = np.array([1] * (words - 1) + [0], dtype=np.uint64)
+        m_enc, m_dec = np.tile(fresh, (B, 1)), np.tile(fresh, (B, 1))
+        m_ref_e, m_ref_d = np.tile(fresh, (B, 1)), np.tile(fresh, (B, 1))
+        alive = np.ones(B, dtype=bool)
+        for rnd in range(2):
+            # a sticky source so that contexts matter: repeat the previous symbol with probability 0.6
+            sym = rng.integers(0, n_sym, size=(B, N)).astype(np.uint8)
+            keep = rng.random((B, N)) < 0.6
+            for j in range(1, N):
+                sym[:, j] = np.where(keep[:, j], sym[:, j - 1], sym[:, j])
+            sizes = rng.integers(1, N + 1, size=B).astype(np.uint32)
+            out, off, ln, st = coder.encode(sym, sizes=sizes, model=m_enc)
+            dsym, dsz, used, st2 = coder.decode(out, off, ln, N, model=m_dec)
+            for b in range(B):
+                if not alive[b]:
+                    continue
+                try:
+                    enc, nb = oracle.encode_block(sym[b, : sizes[b]], model_freq=m_ref_e[b])
+                except so.OracleError as e:
+                    assert st[b] == e.code == _cabi.ST_TOTAL_FREQ, (P, max_total, b, st[b], e.code)
+                    alive[b] = False  # the reference has raised: its model object is in no defined state
+                    continue
+                assert st[b] == 0 and nb == ln[b], (P, max_total, rnd, b)
+                assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes()
+                assert m_enc[b].tolist() == m_ref_e[b].tolist()
+                ref_sym, ref_used = oracle.decode_block(enc, nb, model_freq=m_ref_d[b], cap=N)
+                assert st2[b] == 0 and dsz[b] == sizes[b] and used[b] == ref_used
+                assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist() == ref_sym.tolist()
+                assert m_dec[b].tolist() == m_ref_d[b].tolist()
+        if max_total == 24 and n_sym <= 4 and k <= 2 and N > 200:
+            assert not alive.all()  # the small limit is meant to trip here
+
+
+def test_emu_order_k_table_size_limit():
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    def make(n_sym, k):
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32,
+                        model=_cabi.MODEL_ORDER_K, model_order=k, max_allowed_total_freq=1 << 30)
+        return EmuCoder(prm, None, [1] * n_sym)
+
+    make(3, 5)  # 243 * 4 = 972 words
+    make(39, 1)  # 39 * 40 = 1560 words
+    for n_sym, k in ((40, 1), (3, 6), (2, 10), (256, 1)):
+        with pytest.raises(NotImplementedError):
+            make(n_sym, k)

@@ -6,7 +6,7 @@ import pytest
 
 from oracle import scl_oracle as so
 from oracle.ref_loader import reference_available
-from tests.golden_util import case_id, load_golden, with_garbage
+from tests.golden_util import expected_final_model, fresh_model_table, case_id, load_golden, with_garbage
 
 CASES = load_golden()
 
@@ -21,6 +21,8 @@ def make_oracle(c):
         return o
     if c["coder"] == "range":
         return so.Oracle.range_coder(c["freqs"], **p)
+    if c["model"]["kind"] == "order_k":
+        return so.Oracle.aec(c["freqs"], model=so.MODEL_ORDER_K, k=c["model"]["k"], max_allowed_total_freq=c["model"]["max_total"], **p)
     kind = so.MODEL_ADAPTIVE_IID if c["model"]["kind"] == "adaptive_iid" else so.MODEL_FIXED
     return so.Oracle.aec(c["freqs"], model=kind, max_allowed_total_freq=c["model"]["max_total"], **p)
 
@@ -53,17 +55,21 @@ def test_kat_tans_literal_and_tables():
 @pytest.mark.parametrize("c", CASES, ids=case_id)
 def test_oracle_matches_golden(c):
     o = make_oracle(c)
-    mf = np.array(c["freqs"], dtype=np.uint64) if c["coder"] == "aec" else None
+    mf = fresh_model_table(c)
     enc, nbits = o.encode_block(c["data"], model_freq=mf)
     assert nbits == c["nbits"]
     assert enc.tobytes() == c["enc"].tobytes()
     if c["coder"] == "aec":
-        assert mf.tolist() == c["model"]["final_freqs"]
+        assert mf.tolist() == expected_final_model(c)
     packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
-    mf = np.array(c["freqs"], dtype=np.uint64) if c["coder"] == "aec" else None
+    mf = fresh_model_table(c)
     dec, used = o.decode_block(packed, total, model_freq=mf, cap=max(16, c["n"]))
     assert dec.tolist() == c["data"].tolist()
-    assert used == c["consumed"] == c["nbits"]
+    assert used == c["consumed"]
+    if c["coder"] != "aec":
+        assert used == c["nbits"]  # (the arithmetic decoder's count can be nbits - 1: reference quirk)
+    else:
+        assert mf.tolist() == expected_final_model(c)
 
 
 def test_oracle_decode_at_bit_offset():

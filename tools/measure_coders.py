@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stanford_compression_library_b200 import Frequencies  # noqa: E402
 from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder  # noqa: E402
-from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel  # noqa: E402
+from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, AdaptiveOrderKFreqModel  # noqa: E402
 from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams  # noqa: E402
 from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder  # noqa: E402
 from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams  # noqa: E402
@@ -65,6 +65,15 @@ def main():
     uni = Frequencies({b: 1 for b in range(256)})
     run("arithmetic adaptive order-0, 262144 x 1 KiB (cfg4 shape / 4)", ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)),
         ArithmeticDecoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)), d1k)
+    # order-k context model on a sticky 4-symbol source
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    fresh = torch.randint(0, 4, (262144, 1024), generator=g, device="cuda:0", dtype=torch.uint8)
+    hold = torch.rand((262144, 1024), generator=g, device="cuda:0") < 0.7
+    run_idx = torch.cummax(torch.where(hold, 0, torch.arange(1024, device="cuda:0")[None, :].expand(262144, -1)), dim=1).values
+    sticky = torch.gather(fresh, 1, run_idx)
+    for k in (0, 2):
+        run("arithmetic order-%d context model, 4 symbols, 262144 x 1 KiB" % k, ArithmeticEncoder(ap, AdaptiveOrderKFreqModel([0, 1, 2, 3], k, ap.MAX_ALLOWED_TOTAL_FREQ)),
+            ArithmeticDecoder(ap, AdaptiveOrderKFreqModel([0, 1, 2, 3], k, ap.MAX_ALLOWED_TOTAL_FREQ)), sticky)
 
 
 if __name__ == "__main__":
