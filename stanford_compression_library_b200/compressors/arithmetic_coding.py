@@ -66,13 +66,18 @@ class _AecCoder(GpuCoderBase):
     def encode_blocks(self, data, sizes=None, reuse=None):
         if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:
             return super().encode_blocks(data, sizes=sizes, reuse=reuse)
-        n_blocks = int(data.shape[0])
-        return self.device_coder().encode_blocks(data, sizes=sizes, model=self._model_tensor(n_blocks), reuse=reuse)
+        return self.device_coder().encode_blocks(data, sizes=sizes, model=self._batch_model(int(data.shape[0])), reuse=reuse)
 
     def decode_blocks(self, enc, max_block_len, out=None, reuse=None):
         if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:
             return super().decode_blocks(enc, max_block_len, out=out, reuse=reuse)
-        return self.device_coder().decode_blocks(enc, max_block_len, model=self._model_tensor(enc.n_blocks), out=out, reuse=reuse)
+        return self.device_coder().decode_blocks(enc, max_block_len, model=self._batch_model(enc.n_blocks), out=out, reuse=reuse)
+
+    def _batch_model(self, n_blocks):
+        table = self.freq_model._to_table()
+        if table[-1] == 0 and all(v == 1 for v in table[:-1]):
+            return None  # untouched model: the kernels start from all ones / context 0 themselves
+        return self._model_tensor(n_blocks)
 
 
 class ArithmeticEncoder(_AecCoder, DataEncoder):

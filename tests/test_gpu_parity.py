@@ -312,6 +312,20 @@ def test_aec_order_k_batched_and_persistent():
         _compare_batch_with_oracle(enc, dec, oracle, data, sample=range(0, B, 7), consumed_equals_length=False)
         _compare_batch_with_oracle(enc, dec, oracle, data, sizes=sizes, sample=range(0, B, 5), consumed_equals_length=False)
         assert enc.freq_model._to_table() == [1] * n_sym ** (k + 1) + [0]  # batched calls leave the host model alone
+        # after a single-block call the model has moved on; batched calls then start every block from THAT state
+        from stanford_compression_library_b200 import DataBlock
+
+        ba = enc.encode_block(DataBlock(host[0, :100].tolist()))
+        dec.decode_block(ba)
+        table = enc.freq_model._to_table()
+        assert table == dec.freq_model._to_table() and table != [1] * n_sym ** (k + 1) + [0]
+        e = enc.encode_blocks(data[:8]).check()
+        d = dec.decode_blocks(e, N).check()
+        assert torch.equal(d.symbols[:, :N], data[:8])
+        for b in range(8):
+            ref, ref_bits = oracle.encode_block(host[b], model_freq=np.array(table, dtype=np.uint64))
+            assert int(e.bit_len[b]) == ref_bits and e.block(b).tobytes() == ref.tobytes()
+        assert enc.freq_model._to_table() == table
 
 
 def test_aec_order_k_count_limit_and_table_limit():
