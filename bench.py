@@ -166,7 +166,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks-per-gpu", type=int, default=BLOCKS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-chunk", type=int, default=32768)
+    ap.add_argument("--e2e-chunk", type=int, default=16384)
+    ap.add_argument("--e2e-depth", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -292,15 +293,15 @@ def main():
 
     # ---- end to end through the public API with HOST buffers ----------------------------------
     # HostCodecPipeline: pinned host raw -> (H2D, encode, pack, D2H) -> pinned host coded bytes + bit lengths,
-    # then host coded -> (H2D, decode, D2H) -> pinned host raw; chunks double-buffered over two streams so
-    # uploads, kernels and downloads overlap.  Every byte crosses PCIe inside the timed region.
+    # then host coded -> (H2D, decode, D2H) -> pinned host raw; chunks flow through an upload, a kernel and a
+    # download stream over a ring of staging slots.  Every byte crosses PCIe inside the timed region.
     from stanford_compression_library_b200.pipeline import HostCodecPipeline
 
     enc, dec = head["enc"], head["dec"]
     host_in = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
     host_in.copy_(data)
     host_out = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
-    pipe = HostCodecPipeline(enc, dec, N, B, chunk_blocks=args.e2e_chunk)
+    pipe = HostCodecPipeline(enc, dec, N, B, chunk_blocks=args.e2e_chunk, depth=args.e2e_depth)
     host_c = torch.empty(head["C"] + (1 << 20), dtype=torch.uint8, pin_memory=True)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     h2d = d2h = 0
@@ -329,8 +330,8 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = {"value": world * B * N * e2e_steps / (tt.item() * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "note": "HostCodecPipeline: pinned host buffers, %d-block chunks double-buffered over 2 streams; raw and coded bytes "
-                                       "cross PCIe inside the timed region (per GPU)" % pipe.chunk}
+           "steps": e2e_steps, "note": "HostCodecPipeline: pinned host buffers, %d-block chunks over upload / kernel / download streams, %d staging slots; raw and "
+                                       "coded bytes cross PCIe inside the timed region (per GPU)" % (pipe.chunk, pipe.depth)}
 
     # total compressed size of the global stream (all-gather of 8 x u64)
     sizes, my_off = gather_compressed_sizes(head["C"])

@@ -173,7 +173,9 @@ int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *d
 
 /* Test hook: 1 = route the fast paths to the first-generation kernels (per-lane direct global
  * access) instead of the TMA/ring kernels; 2 = second-generation decode with per-lane sector
- * stores instead of TMA tile stores; 0 = default.  Keeps every code path parity-tested. */
+ * stores instead of TMA tile stores; 3 / 4 = second-generation decode always / never in its
+ * pipe-balanced instruction selection (normally chosen by batch size); 0 = default.  Keeps every
+ * code path parity-tested. */
 void scl_debug_force_v1(int on);
 
 const char *scl_last_cuda_error(void);

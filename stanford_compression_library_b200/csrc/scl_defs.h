@@ -15,12 +15,14 @@ namespace scl {
 
 // ---- rANS, 32-bit-state fast path ---------------------------------------------------------
 // One entry per BYTE VALUE (not per alphabet index).  Encode step (rANS.py:138-161):
-//   k  = nb0 + (x > thresh_m1 ? NBO : 0)       closed form of the shrink_state while-loop
+//   k  = nb0 + (x > thresh_m1 ? NBO : 0)       closed form of the shrink_state while-loop.  For NBO == 1 the
+//                                              table holds ~thresh_m1, so the test is the carry of x + key and
+//                                              k = nb0 + carry (IADD3 + IMAD.X); for NBO > 1 it holds thresh_m1
 //   x >>= k  (emit the low k bits)
 //   q  = umulhi(x, rcp) >> shift               exact x / f  (checked on the host per symbol)
 //   x' = x + bias + q * cmpl                   == (x / f) * M + cum + x % f
 struct alignas(16) RansEnc32 {
-    uint32_t thresh_m1;
+    uint32_t thresh_key;  // NBO == 1: ~thresh_m1, else thresh_m1
     uint32_t rcp;
     uint32_t bias;
     uint32_t pack;  // cmpl(M - f) << 16 | nb0 << 8 | shift ; 0xFFFFFFFF = byte not in the alphabet

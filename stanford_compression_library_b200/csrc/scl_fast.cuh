@@ -163,14 +163,25 @@ struct EncLaneV2 {
     }
 
     // one symbol: shrink_state + rans_base_encode_step (rANS.py:138-161), see scl_lane.cuh.
-    // e = {thresh_m1, rcp, bias, cmpl << 16 | nb0 << 8 | shift}
+    // e = {NBO == 1 ? ~thresh_m1 : thresh_m1, rcp, bias, cmpl << 16 | nb0 << 8 | shift}
     template <uint32_t NBO, bool CHECK>
     SCL_HD void step(const u32x4 &e) {
         if (CHECK && e.w == kRansEncInvalid) {
             bad = 1;
             return;
         }
-        uint32_t k = byte_of(e.w, 1) + (x > e.x ? NBO : 0u);
+        uint32_t k = byte_of(e.w, 1);
+        if (NBO == 1) {
+#ifdef __CUDA_ARCH__
+            // (x > thresh_m1) is the carry of x + ~thresh_m1 (e.x holds the complement): IADD3 + IMAD.X
+            // instead of ISETP + add + select
+            asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(k) : "r"(x), "r"(e.x), "r"(k));
+#else
+            k += (x > ~e.x ? 1u : 0u);
+#endif
+        } else {
+            k += (x > e.x ? NBO : 0u);
+        }
         lo = funnel_r(lo, hi, k);  // k <= 16 < 32
         hi = funnel_r(hi, x, k);
         room -= k;
@@ -350,7 +361,11 @@ struct DecLaneV2 {
     }
     // top 32 unread bits
     SCL_HD uint32_t peek32() const {
-        saddr_t a = ring + ((bp << 2) & ((kDecRingWords - 1) * 128));
+#ifdef __CUDA_ARCH__
+        saddr_t a = mad32(bp & ((kDecRingWords - 1) * 32), 4u, ring);  // LOP3 + IMAD (the compiler's own form is three ops)
+#else
+        saddr_t a = ring + ((bp & ((kDecRingWords - 1) * 32)) << 2);
+#endif
         uint32_t w0 = lds32(a), w1 = lds32(a + 128);
         return funnel_l(w1, w0, bp);
     }
@@ -387,19 +402,43 @@ struct DecConst {
     uint32_t m4;      // (M - 1) * 4
     uint32_t xq_mul;  // 2^(32 - log2 M): umulhi(x, xq_mul) = x >> log2 M
     uint32_t kbase;   // clz(x) - kbase = bits missing to reach L   (kbase = 31 - log2 L)
+    uint32_t mask;    // M - 1
+    uint32_t l_log2;
+    uint32_t four, neg1;  // 4 and -1 as run-time values: ptxas turns IMAD by a literal power of two back into LEA / IADD3 (ALU pipe)
 };
 
 // One decode step (rans_base_decode_step + expand_state, rANS.py:234-260) on lut entry
 // e = f << 20 | bias << 8 | byte.  k1 + k2 <= 32 for a pair is guaranteed by kFastMaxBitsPerSym.
-template <uint32_t NBO, int POS>
+// BAL = pipe-balanced form for throughput-bound launches (many warps per SM); with few warps the
+// extra cross-pipe hops lengthen the per-symbol dependency chain, so small batches use BAL = false
+// (measured: +2 % at 55 tasks per SM, -3 % at 14).
+template <uint32_t NBO, int POS, bool BAL = false>
 SCL_HD void dec_step(const DecConst &c, uint32_t &x, uint32_t &bits, uint32_t &ksum, uint32_t &acc) {
-    uint32_t e = lds32(c.lut + (saddr_t)((x << 2) & c.m4));
+    // The ALU pipe (LOP3/SHF/PRMT/IADD3, one warp-instruction per 2 cycles) was at 69 % against 22 % for the
+    // FMA pipe (profiles/r1h): with BAL every shift / add that has an IMAD form is issued there instead.
+    uint32_t e, bias, d;
+#ifdef __CUDA_ARCH__
+    if (BAL) {
+        e = lds32(mad32(x & c.mask, c.four, c.lut));  // LOP3 + IMAD
+        bias = mulhi_fma(e, 1u << 24) & 0xFFFu;       // e >> 8 as IMAD.HI, then LOP3
+    } else
+#endif
+    {
+        e = lds32(c.lut + (saddr_t)((x << 2) & c.m4));
+        bias = (e >> 8) & 0xFFFu;
+    }
     uint32_t xq = mulhi_fma(x, c.xq_mul);
     uint32_t f = mulhi_fma(e, 1u << 12);  // e >> 20
-    uint32_t bias = (e >> 8) & 0xFFFu;
     x = mad32(f, xq, bias);
     acc = put_byte<POS>(acc, e);
-    uint32_t d = clz32(x) - c.kbase;      // bits missing to reach L; d >= 1 - NBO because x < 2^(l+NBO)
+    // d = bits missing to reach L = log2 L - (position of the top set bit); d >= 1 - NBO because x < 2^(l+NBO)
+#ifdef __CUDA_ARCH__
+    if (BAL) {
+        asm("bfind.u32 %0, %1;" : "=r"(d) : "r"(x));
+        d = mad32(d, c.neg1, c.l_log2);
+    } else
+#endif
+        d = clz32(x) - c.kbase;
     uint32_t k;
     if (NBO == 1) {
         k = d;
@@ -415,7 +454,7 @@ SCL_HD void dec_step(const DecConst &c, uint32_t &x, uint32_t &bits, uint32_t &k
 }
 
 // decode 16 symbols, last first, into 4 words (byte 3 of w[3] is the first one decoded)
-template <uint32_t NBO>
+template <uint32_t NBO, bool BAL = false>
 SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
     uint32_t x = D.x;
 #pragma unroll
@@ -423,14 +462,14 @@ SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
         uint32_t acc = 0;
         {
             uint32_t bits = D.peek32(), ks = 0;
-            dec_step<NBO, 3>(c, x, bits, ks, acc);
-            dec_step<NBO, 2>(c, x, bits, ks, acc);
+            dec_step<NBO, 3, BAL>(c, x, bits, ks, acc);
+            dec_step<NBO, 2, BAL>(c, x, bits, ks, acc);
             D.bp += ks;
         }
         {
             uint32_t bits = D.peek32(), ks = 0;
-            dec_step<NBO, 1>(c, x, bits, ks, acc);
-            dec_step<NBO, 0>(c, x, bits, ks, acc);
+            dec_step<NBO, 1, BAL>(c, x, bits, ks, acc);
+            dec_step<NBO, 0, BAL>(c, x, bits, ks, acc);
             D.bp += ks;
         }
         w[j] = acc;
@@ -496,21 +535,34 @@ struct TansDecConst {
     uint32_t L;       // table size (power of two)
     uint32_t lmask4;  // (L - 1) * 4
     uint32_t kbase;   // 32 - NUM_STATE_BITS: k = clz(x_shrunk) - kbase
+    uint32_t lmask, nsb_m1, four, neg1;
 };
 
-template <int POS>
+template <int POS, bool BAL = false>
 SCL_HD void tans_dec_step(const TansDecConst &c, uint32_t &x, uint32_t &bits, uint32_t &ksum, uint32_t &acc) {
     // a corrupt state (outside [L, 2L)) wraps inside the table instead of faulting; the final
     // state check reports it (the reference raises KeyError from its dict)
-    uint32_t e = lds32(c.dec + (saddr_t)(((x - c.L) << 2) & c.lmask4));
-    uint32_t xs = e >> 8;
+    uint32_t e, xs, k;
+#ifdef __CUDA_ARCH__
+    if (BAL) {  // same pipe balancing as dec_step: address, e >> 8 and the subtraction go to the FMA pipe
+        e = lds32(mad32(x & c.lmask, c.four, c.dec));  // (x - L) mod L == x mod L
+        xs = mulhi_fma(e, 1u << 24);
+        asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(xs));
+        k = mad32(k, c.neg1, c.nsb_m1);  // NUM_STATE_BITS - bitwidth(x_shrunk): expand_state_num_bits_table (tANS.py:225)
+    } else
+#endif
+    {
+        e = lds32(c.dec + (saddr_t)(((x - c.L) << 2) & c.lmask4));
+        xs = e >> 8;
+        k = clz32(xs) - c.kbase;  // expand_state_num_bits_table (tANS.py:225)
+    }
     acc = put_byte<POS>(acc, e);
-    uint32_t k = clz32(xs) - c.kbase;  // expand_state_num_bits_table (tANS.py:225)
     x = funnel_l(bits, xs, k);
     bits <<= k;
     ksum += k;
 }
 
+template <bool BAL = false>
 SCL_HD void tans_dec_group16(DecLaneV2 &D, const TansDecConst &c, uint32_t w[4]) {
     uint32_t x = D.x;
 #pragma unroll
@@ -518,14 +570,14 @@ SCL_HD void tans_dec_group16(DecLaneV2 &D, const TansDecConst &c, uint32_t w[4])
         uint32_t acc = 0;
         {
             uint32_t bits = D.peek32(), ks = 0;
-            tans_dec_step<3>(c, x, bits, ks, acc);
-            tans_dec_step<2>(c, x, bits, ks, acc);
+            tans_dec_step<3, BAL>(c, x, bits, ks, acc);
+            tans_dec_step<2, BAL>(c, x, bits, ks, acc);
             D.bp += ks;
         }
         {
             uint32_t bits = D.peek32(), ks = 0;
-            tans_dec_step<1>(c, x, bits, ks, acc);
-            tans_dec_step<0>(c, x, bits, ks, acc);
+            tans_dec_step<1, BAL>(c, x, bits, ks, acc);
+            tans_dec_step<0, BAL>(c, x, bits, ks, acc);
             D.bp += ks;
         }
         w[j] = acc;
@@ -537,7 +589,7 @@ SCL_HD void tans_dec_group16(DecLaneV2 &D, const TansDecConst &c, uint32_t w[4])
 // Stepper policies: the same decode driver (header, ragged head, 16-symbol groups) serves rANS
 // and tANS, and the kernels reuse the pieces for their tile-store main loop.
 // ------------------------------------------------------------------------------------------------
-template <uint32_t NBO>
+template <uint32_t NBO, bool BAL = false>
 struct RansStepper {
     DecConst dc;
     uint32_t l_log2, m_log2;
@@ -546,6 +598,10 @@ struct RansStepper {
         dc.m4 = ((uint32_t)c.M - 1) << 2;
         dc.xq_mul = c.m_log2 ? (1u << (32 - c.m_log2)) : 0u;
         dc.kbase = 31 - c.l_log2;
+        dc.mask = (uint32_t)c.M - 1;
+        dc.l_log2 = c.l_log2;
+        dc.four = 4u + (c.l_log2 >> 8);  // l_log2 < 64 or 0xFFFFFFFF (never on this path): opaque to the compiler
+        dc.neg1 = 0xFFFFFFFFu - (c.l_log2 >> 8);
         l_log2 = c.l_log2;
         m_log2 = c.m_log2;
     }
@@ -565,9 +621,10 @@ struct RansStepper {
         D.bp += ks;
         return acc & 0xFFu;
     }
-    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { dec_group16<NBO>(D, dc, w); }
+    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { dec_group16<NBO, BAL>(D, dc, w); }
 };
 
+template <bool BAL = false>
 struct TansStepper {
     TansDecConst tc;
     SCL_HD void init(saddr_t dec, const RansConst &c) {
@@ -575,6 +632,10 @@ struct TansStepper {
         tc.L = (uint32_t)c.L;
         tc.lmask4 = ((uint32_t)c.L - 1) << 2;
         tc.kbase = 32 - c.NSB;
+        tc.lmask = (uint32_t)c.L - 1;
+        tc.nsb_m1 = c.NSB - 1;
+        tc.four = 4u + (c.NSB >> 8);  // opaque 4 / -1, see DecConst
+        tc.neg1 = 0xFFFFFFFFu - (c.NSB >> 8);
     }
     SCL_HD bool degenerate() const { return false; }
     SCL_HD uint32_t one(DecLaneV2 &D) const {
@@ -584,7 +645,7 @@ struct TansStepper {
         D.bp += ks;
         return acc & 0xFFu;
     }
-    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { tans_dec_group16(D, tc, w); }
+    SCL_HD void group16(DecLaneV2 &D, uint32_t w[4]) const { tans_dec_group16<BAL>(D, tc, w); }
 };
 
 // header: [size : DBSB][state : NSB]; returns false (with *st set) when the size does not fit
@@ -657,7 +718,7 @@ SCL_HD uint32_t rans32_decode_lane_v2(DecLaneV2 &D, saddr_t lut, const RansConst
 }
 SCL_HD uint32_t tans_decode_lane_v2(DecLaneV2 &D, saddr_t dec, const RansConst &c, uint8_t *out, uint64_t out_cap, uint32_t &size_out,
                                     uint64_t &bits_consumed) {
-    TansStepper s;
+    TansStepper<> s;
     s.init(dec, c);
     return decode_lane_generic(D, s, c, out, out_cap, size_out, bits_consumed);
 }

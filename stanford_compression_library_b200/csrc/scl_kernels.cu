@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 // __all_sync); otherwise the warp falls back to per-lane sector stores.
 constexpr uint32_t kDecTileBytes = 32 * kTileCols;
 
-template <int KIND, uint32_t NBO>
+template <int KIND, uint32_t NBO, bool BAL>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     fast_decode_v2_kernel(const __grid_constant__ CUtensorMap out_map, uint32_t use_tiles, const uint32_t *__restrict__ g_lut,
                           uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     const uint32_t total_warps = gridDim.x * W;
     const uint32_t swz = (lane >> 1) & 3;
     const saddr_t my_row = saddr_of(tile) + lane * kTileCols;
-    typename std::conditional<KIND == 0, RansStepper<NBO>, TansStepper>::type S;
+    typename std::conditional<KIND == 0, RansStepper<NBO, BAL>, TansStepper<BAL>>::type S;
     S.init(saddr_of(s_lut), c);
 
     for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
@@ -1110,9 +1110,11 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
 
 static bool g_no_tile_store = false;  // test hook (scl_debug_force_v1(2)): v2 decode with per-lane sector stores
 static bool g_force_v1 = false;  // test hook: scl_debug_force_v1(1) routes the fast path to the first-generation kernels
+static int g_force_bal = 0;      // test hook: scl_debug_force_v1(3) / (4) = v2 decode always / never in the pipe-balanced form
 extern "C" void scl_debug_force_v1(int on) {
     g_force_v1 = on == 1;
     g_no_tile_store = on == 2;
+    g_force_bal = on == 3 ? 1 : on == 4 ? -1 : 0;
 }
 
 static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
@@ -1170,9 +1172,13 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
         use_tiles = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
-    cudaError_t e = cudaFuncSetAttribute(fast_decode_v2_kernel<KIND, NBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // pipe-balanced instruction selection pays when the SMs are full (>= 2 rounds of warps); small batches are
+    // latency-bound and keep the shorter dependency chain
+    const bool bal = g_force_bal ? g_force_bal > 0 : n_tasks >= 24u * c->n_sm;
+    auto kern = bal ? fast_decode_v2_kernel<KIND, NBO, true> : fast_decode_v2_kernel<KIND, NBO, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    fast_decode_v2_kernel<KIND, NBO><<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks);
+    kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks);
     return check_launch("fast_decode_v2_kernel");
 }
 

@@ -293,7 +293,7 @@ template <bool CHECK>
 SCL_HD bool rans32_encode_step(const RansEnc32 *tab, uint32_t nbo, uint32_t s, uint32_t &x, LifoBitWriter &w) {
     const RansEnc32 e = tab[s];
     if (CHECK && e.pack == kRansEncInvalid) return false;
-    uint32_t k = ((e.pack >> 8) & 0xFFu) + (x > e.thresh_m1 ? nbo : 0u);
+    uint32_t k = ((e.pack >> 8) & 0xFFu) + (x > (nbo == 1 ? ~e.thresh_key : e.thresh_key) ? nbo : 0u);
     w.put(x & mask32(k), k);
     x >>= k;
     uint32_t q = funnel_r(umulhi32(x, e.rcp), 0u, e.pack);  // >> (pack & 31)

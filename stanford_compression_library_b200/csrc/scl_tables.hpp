@@ -139,7 +139,8 @@ struct RansHost {
             if (nb0 + c.NBO > 31) return;
             u128_t thresh = ((u128_t)max_shrunk + 1) << nb0;
             RansEnc32 e;
-            e.thresh_m1 = (thresh - 1 > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)(thresh - 1);
+            e.thresh_key = (thresh - 1 > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (uint32_t)(thresh - 1);
+            if (c.NBO == 1) e.thresh_key = ~e.thresh_key;
             uint32_t shift;
             uint64_t bias = cum[i];
             uint64_t cmpl = c.M - f;

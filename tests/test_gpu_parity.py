@@ -446,11 +446,15 @@ def test_rans_kernel_generations_agree(kw, shape):
         d2 = dec.decode_blocks(e1, N).check()  # v2 decoder (TMA tile stores) on v1 output
         lib.scl_debug_force_v1(2)
         d3 = dec.decode_blocks(e1, N).check()  # v2 decoder with per-lane sector stores
+        lib.scl_debug_force_v1(3)
+        d4 = dec.decode_blocks(e1, N).check()  # v2 decoder, pipe-balanced instruction selection (large-batch form)
+        lib.scl_debug_force_v1(4)
+        d5 = dec.decode_blocks(e1, N).check()  # v2 decoder, plain form
         lib.scl_debug_force_v1(1)
         d1 = dec.decode_blocks(e2, N).check()  # v1 decoder on v2 output
     finally:
         lib.scl_debug_force_v1(0)
-    for d in (d1, d2, d3):
+    for d in (d1, d2, d3, d4, d5):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
         assert int(d.sizes.min()) == N == int(d.sizes.max())
     # and both against the oracle on a few blocks
@@ -482,11 +486,15 @@ def test_tans_kernel_generations_agree(rf):
         e2 = enc.encode_blocks(data).check()
         assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(p1.buf, e2.pack().buf)
         d2 = dec.decode_blocks(e1, N).check()
+        lib.scl_debug_force_v1(3)
+        d3 = dec.decode_blocks(e1, N).check()  # pipe-balanced form
+        lib.scl_debug_force_v1(4)
+        d4 = dec.decode_blocks(e1, N).check()  # plain form
         lib.scl_debug_force_v1(1)
         d1 = dec.decode_blocks(e2, N).check()
     finally:
         lib.scl_debug_force_v1(0)
-    for d in (d1, d2):
+    for d in (d1, d2, d3, d4):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
     oracle = so.Oracle.tans(zipf_freq_list(), RANGE_FACTOR=rf)
     host = data.cpu().numpy()
