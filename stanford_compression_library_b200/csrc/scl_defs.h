@@ -10,6 +10,7 @@
 #else
 #define SCL_HD inline
 #endif
+#define SCL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 namespace scl {
 

@@ -326,9 +326,13 @@ struct DecLaneV2 {
 
     SCL_HD u32x8 load_sector(uint64_t off) const {
         if (off + 32 <= in_bytes) return ld_sector32(base + off);
+        // the last sectors of the buffer, byte by byte: rolled loops on purpose (this path is inlined at every
+        // refill site; unrolled it was ~400 instructions per site and pushed the hot loops out of the instruction cache)
         u32x8 a;
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
             uint32_t v = 0;
+#pragma unroll 1
             for (int b = 3; b >= 0; --b) {
                 uint64_t p = off + 4 * i + b;
                 v = (v << 8) | (p < in_bytes ? base[p] : 0u);
@@ -393,6 +397,17 @@ struct DecLaneV2 {
     // ... and put it into the ring one group later
     SCL_HD void prefetch_end() {
         if (pf_valid) store_sector(pf);
+        pf_valid = 0;
+    }
+    // out-of-cadence refill (a consumer that read more than 256 bits since the last group boundary)
+    SCL_HD void refill_now() {
+        if (pf_valid) {
+            store_sector(pf);
+            pf_valid = 0;
+        } else {
+            store_sector(load_sector(next_off));
+            next_off += 32;
+        }
     }
 };
 

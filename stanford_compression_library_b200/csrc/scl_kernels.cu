@@ -18,6 +18,7 @@
 #include "scl_aec.cuh"
 #include "scl_fast.cuh"
 #include "scl_lane.cuh"
+#include "scl_range.cuh"
 #include "scl_tables.hpp"
 
 namespace scl {
@@ -503,6 +504,148 @@ __global__ void __launch_bounds__(kThreads) range_decode_kernel(const RangeTab *
 }
 
 // ------------------------------------------------------------------------------------------------
+// range coder, second generation (scl_range.cuh) on the v2 machinery: persistent CTAs, one warp per
+// task of 32 blocks, symbols in by 2-D TMA tiles, coded bytes through sector rings.  Every lane of
+// a warp runs the same instruction stream (the normalisation's extra rounds are a warp vote), so
+// lanes past the end of the batch run as padding with a zero-capacity slot.
+// smem layout as in fast_encode_v2_kernel: [tiles per warp][rings per warp][table 32 KiB][mbarriers];
+// the table is [byte value][lane] so that every lane reads its own bank.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kRangeEncTabBytes = 256 * 32 * 4;
+
+template <bool CHECK>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+    range_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ g_tab, uint32_t shift, BlockIo io,
+                           uint32_t n_tasks) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((2048u - (smem_u32(smem_raw) & 2047u)) & 2047u);
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
+    const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
+    const uint8_t *s_tab = smem + W * kEncWarpSmem;
+    uint64_t *mbars = (uint64_t *)(smem + W * kEncWarpSmem + kRangeEncTabBytes);
+    uint64_t *tab_bar = mbars + W * kTileStages;
+    uint64_t *my_bar = mbars + warp * kTileStages;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(tab_bar)) : "memory");
+        for (uint32_t i = 0; i < W * kTileStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_expect(tab_bar, kRangeEncTabBytes);
+        tma_bulk_g2s((void *)s_tab, g_tab, kRangeEncTabBytes, tab_bar);
+    }
+    mbar_wait(tab_bar, 0);
+
+    const saddr_t my_tab = saddr_of(s_tab) + lane * 4;
+    const uint32_t n = io.block_len;
+    const uint32_t n_tiles = (n + kTileCols - 1) / kTileCols;
+    const uint32_t total_warps = gridDim.x * W;
+    uint32_t tile_seq = 0;
+    const uint32_t swz = (lane >> 1) & 3;
+
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+        const uint64_t b = (uint64_t)task * 32 + lane;
+        const bool active = b < io.n_blocks;
+        if (lane == 0) {
+            for (uint32_t t = 0; t < kTileStages && t < n_tiles; ++t) {
+                uint32_t st = (tile_seq + t) % kTileStages;
+                tma_expect(my_bar + st, kTileBytes);
+                tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)(t * kTileCols), (int32_t)(task * 32), my_bar + st);
+            }
+        }
+        RangeEncV2 L;
+        uint8_t *slot = io.out + (active ? b : 0) * io.out_stride;
+        L.init(ring, slot, active ? slot + io.out_stride : slot);  // padding lanes: zero capacity, nothing is stored
+        L.put_word(n);  // [size : 32] (range_coder.py:201-205)
+        L.spill_check();
+        for (uint32_t t = 0; t < n_tiles; ++t, ++tile_seq) {
+            const uint32_t st = tile_seq % kTileStages;
+            mbar_wait(my_bar + st, (tile_seq / kTileStages) & 1);
+            const uint8_t *row = tiles + st * kTileBytes + lane * kTileCols;
+            const uint32_t left = n - t * kTileCols;  // the same for every lane
+#pragma unroll 1
+            for (uint32_t ch = 0; ch < kTileCols / 16; ++ch) {
+                if (ch * 16 >= left) break;
+                const uint32_t cnt = left - ch * 16 >= 16 ? 16u : left - ch * 16;
+                const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));
+                const u32x4 v = {q.x, q.y, q.z, q.w};
+                range_enc_chunk<CHECK, true>(L, my_tab, 128, shift, v, cnt);
+            }
+            __syncwarp();
+            if (lane == 0 && t + kTileStages < n_tiles) {
+                tma_expect(my_bar + st, kTileBytes);
+                tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)((t + kTileStages) * kTileCols), (int32_t)(task * 32), my_bar + st);
+            }
+        }
+        const uint64_t bits = L.finish();
+        if (active) {
+            uint32_t st = SCL_ST_OK;
+            if (L.bad) st = SCL_ST_BAD_SYMBOL;
+            if (L.ovf) st = SCL_ST_OVERFLOW;
+            io.bit_len[b] = bits;
+            io.bit_off[b] = b * io.out_stride * 8;
+            io.status[b] = st;
+        }
+        __syncwarp();
+    }
+}
+
+// smem: [input rings per warp][LUT]
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+    range_decode_v2_kernel(const uint32_t *__restrict__ g_lut, uint32_t lut_bytes, uint32_t shift, uint32_t T, uint32_t last_entry, DecodeIo io,
+                           uint32_t n_tasks) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const saddr_t ring = saddr_of(smem + warp * kDecWarpSmem) + lane * 4;
+    const uint32_t *s_lut = (const uint32_t *)(smem + W * kDecWarpSmem);
+    stage_table((void *)s_lut, g_lut, lut_bytes, &mbar);
+    const uint32_t total_warps = gridDim.x * W;
+    RangeDecConst dc;
+    dc.lut = saddr_of(s_lut);
+    dc.shift = shift;
+    dc.T = T;
+    dc.last = last_entry;
+
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+        const uint64_t b = (uint64_t)task * 32 + lane;
+        const bool active = b < io.n_blocks;
+        const uint64_t bb = active ? b : io.n_blocks - 1;  // padding lanes decode the last block again, without storing
+        const uint64_t off = io.bit_off[bb];
+        uint8_t *out = io.sym + bb * io.sym_stride;
+        DecLaneV2 D;
+        D.init(io.in, io.in_bytes, off, ring);
+        RangeDecV2 R;
+        uint32_t size = 0;
+        const bool ok = range_dec_header(D, io.sym_stride, size, R);
+        const uint32_t size0 = __shfl_sync(0xffffffffu, size, 0);
+        if (__all_sync(0xffffffffu, ok && size == size0)) {
+            range_dec_body<true>(D, R, dc, out, size, active);  // warp-uniform: the extra normalisation rounds are a vote
+        } else if (active && ok) {
+            range_dec_body<false>(D, R, dc, out, size, true);   // ragged sizes: per-lane control flow
+        }
+        if (active) {
+            uint32_t st = SCL_ST_OK;
+            uint64_t used = 0;
+            if (!ok) {
+                st = SCL_ST_OVERFLOW;
+            } else {
+                used = D.bp - D.start_bp;
+                if (R.ovf) st = SCL_ST_OVERFLOW;
+                if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+            }
+            io.sizes[b] = st == SCL_ST_OK ? size : 0;
+            io.consumed[b] = used;
+            io.status[b] = st;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // arithmetic coder kernels: 32 lanes per CTA, each lane's 256-counter model is a Fenwick tree in
 // shared memory, lane-interleaved (element i of lane l at word i*32 + l => every access of a
 // warp hits 32 distinct banks whatever the per-lane index).
@@ -889,6 +1032,9 @@ struct scl_coder {
     RangeTab *d_range = nullptr;
     uint8_t *d_range_lut = nullptr;
     uint32_t range_lut_bytes = 0;
+    uint32_t *d_range_enc_rep = nullptr;  // [byte value][lane] replicas of RangeHost::enc_tab for range_encode_v2_kernel
+    uint32_t *d_range_dec_lut = nullptr;  // RangeHost::dec_lut
+    uint32_t range_dec_lut_bytes = 0;
     AecTab *d_aec = nullptr;
 };
 
@@ -930,6 +1076,8 @@ extern "C" void scl_coder_destroy(scl_coder *c) {
     cudaFree(c->d_tdec);
     cudaFree(c->d_range);
     cudaFree(c->d_range_lut);
+    cudaFree(c->d_range_enc_rep);
+    cudaFree(c->d_range_dec_lut);
     cudaFree(c->d_aec);
     delete c->rans;
     delete c->tans;
@@ -1022,6 +1170,23 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         if (!rc) {
             c->range_lut_bytes = (uint32_t)round16(c->range->lut.size());
             rc = upload(&c->d_range_lut, c->range->lut.data(), c->range->lut.size(), c->range_lut_bytes, s);
+        }
+        if (!rc && c->range->v2) {
+            const RangeHost &rh = *c->range;
+            std::vector<uint32_t> rep(256 * 32);
+            for (uint32_t sy = 0; sy < 256; ++sy)
+                for (uint32_t l = 0; l < 32; ++l) rep[sy * 32 + l] = rh.enc_tab[sy];
+            rc = upload(&c->d_range_enc_rep, rep.data(), rep.size() * 4, rep.size() * 4, s);
+            c->range_dec_lut_bytes = (uint32_t)round16(rh.dec_lut.size() * 4);
+            if (!rc) rc = upload(&c->d_range_dec_lut, rh.dec_lut.data(), rh.dec_lut.size() * 4, c->range_dec_lut_bytes, s);
+            if (!rc) {
+                cudaError_t e = cudaStreamSynchronize(s);  // `rep` dies here
+                if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+            }
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev);
+            c->v2_ok = c->n_sm > 0;
         }
         break;
     }
@@ -1182,6 +1347,34 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     return check_launch("fast_decode_v2_kernel");
 }
 
+static int launch_range_encode_v2(const scl_coder *c, const BlockIo &io, cudaStream_t s) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return -1;
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {io.block_len, io.n_blocks};
+    cuuint64_t gstr[1] = {io.sym_stride};
+    cuuint32_t box[2] = {kTileCols, 32};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return -1;
+    uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
+    pick_launch(n_tasks, c->n_sm, max_warps_for(kEncWarpSmem, kRangeEncTabBytes + 2048 + 8 * (kMaxWarps * kTileStages + 1)), &grid, &warps);
+    size_t smem = 2048 + (size_t)warps * kEncWarpSmem + kRangeEncTabBytes + 8 * (warps * kTileStages + 1);
+    const uint32_t shift = c->range->c.t_shift;
+    cudaError_t e;
+    if (c->range->c.n_sym < 256) {  // some byte values are not in the alphabet: check every symbol
+        e = cudaFuncSetAttribute(range_encode_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        range_encode_v2_kernel<true><<<grid, warps * 32, smem, s>>>(tmap, c->d_range_enc_rep, shift, io, n_tasks);
+    } else {
+        e = cudaFuncSetAttribute(range_encode_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        range_encode_v2_kernel<false><<<grid, warps * 32, smem, s>>>(tmap, c->d_range_enc_rep, shift, io, n_tasks);
+    }
+    return check_launch("range_encode_v2_kernel");
+}
+
 extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
                                  uint64_t n_blocks, uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_bit_offset,
                                  uint64_t *d_out_bit_len, uint64_t *d_model, uint32_t *d_status, void *stream) {
@@ -1229,6 +1422,11 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         return check_launch("tans_encode_kernel");
     }
     if (c->range) {
+        if (c->range->v2 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
+            (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36)) {
+            int rc2 = launch_range_encode_v2(c, io, s);
+            if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
+        }
         range_encode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
         return check_launch("range_encode_kernel");
     }
@@ -1299,6 +1497,16 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         return check_launch("tans_decode_kernel");
     }
     if (c->range) {
+        if (c->range->v2 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+            n_blocks < (1ull << 36)) {
+            const RangeHost &rh = *c->range;
+            uint32_t n_tasks = (uint32_t)((n_blocks + 31) / 32), g2, warps;
+            pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem, c->range_dec_lut_bytes), &g2, &warps);
+            size_t smem = (size_t)warps * kDecWarpSmem + c->range_dec_lut_bytes;
+            SCL_CUDA(cudaFuncSetAttribute(range_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            range_decode_v2_kernel<<<g2, warps * 32, smem, s>>>(c->d_range_dec_lut, c->range_dec_lut_bytes, rh.c.t_shift, rh.c.T, rh.last_entry, io, n_tasks);
+            return check_launch("range_decode_v2_kernel");
+        }
         SCL_CUDA(cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->range_lut_bytes));
         range_decode_kernel<<<grid, kThreads, c->range_lut_bytes, s>>>(c->d_range, c->d_range_lut, c->range_lut_bytes, c->range->c, io);
         return check_launch("range_decode_kernel");

@@ -262,9 +262,29 @@ struct RangeHost {
         lut.assign((size_t)tot, 0);
         for (uint32_t i = 0; i < n_sym; ++i)
             for (uint64_t v = t.cum[i]; v < (uint64_t)t.cum[i] + t.freq[i]; ++v) lut[v] = (uint8_t)i;
+        build_v2(n_sym);
         return SCL_E_OK;
     }
     std::vector<uint8_t> lut;
+    // second-generation lanes (scl_range.cuh): PRECISION 32, 32-bit size header, power-of-two 16 <= T <= 4096, f <= 4095
+    bool v2 = false;
+    std::vector<uint32_t> enc_tab;  // by BYTE VALUE: freq << 16 | cum; 0xFFFFFFFF = byte not in the alphabet
+    std::vector<uint32_t> dec_lut;  // by v in [0, T): freq << 20 | cum << 8 | byte value
+    uint32_t last_entry = 0;        // dec_lut-format entry of the last alphabet index
+    void build_v2(uint32_t n_sym) {
+        v2 = false;
+        if (c.P != 32 || c.DBSB != 32 || c.t_shift == 0xFFFFFFFFu || c.T < 16 || c.T > 4096) return;
+        enc_tab.assign(256, 0xFFFFFFFFu);
+        dec_lut.assign(c.T, 0);
+        for (uint32_t i = 0; i < n_sym; ++i) {
+            if (t.freq[i] > 4095) return;
+            enc_tab[t.idx2sym[i]] = (t.freq[i] << 16) | t.cum[i];
+            const uint32_t e = (t.freq[i] << 20) | (t.cum[i] << 8) | t.idx2sym[i];
+            for (uint32_t v = t.cum[i]; v < t.cum[i] + t.freq[i]; ++v) dec_lut[v] = e;
+            last_entry = e;
+        }
+        v2 = true;
+    }
     // every symbol can release at most ceil(P/8) bytes... bound: normalise emits a byte only while
     // range < 2^(P-8) effectively; one symbol shrinks range by at most T <= 2^(P-16) => <= 3 bytes
     uint64_t max_encoded_bits(uint64_t n) const { return (uint64_t)c.DBSB + 8ull * (3 * n + c.P / 8); }

@@ -12,6 +12,7 @@
 #include "../../stanford_compression_library_b200/csrc/scl_aec.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_fast.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_lane.cuh"
+#include "../../stanford_compression_library_b200/csrc/scl_range.cuh"
 #include "../../stanford_compression_library_b200/csrc/scl_tables.hpp"
 
 using namespace scl;
@@ -286,6 +287,7 @@ int emu_v2_eligible(void *h) {
         const RansHost &r = e->tans->r;
         return r.max_bits_per_symbol <= kFastMaxBitsPerSym && r.c.L * 4 <= 64 * 1024 && r.c.NSB <= 32;
     }
+    if (e->range) return e->range->v2 ? 1 : 0;
     if (!e->rans) return 0;
     const RansHost &r = *e->rans;
     return r.enc32 && r.dec32 && r.max_bits_per_symbol <= kFastMaxBitsPerSym && (r.c.NBO == 1 || r.c.NBO == 8);
@@ -353,12 +355,55 @@ static void tans_enc_v2_block(const Emu &e, const uint8_t *row, uint32_t n, uint
     status[b] = st;
 }
 
+// range coder, second generation (scl_range.cuh), driven like range_encode_v2_kernel / range_decode_v2_kernel drive it
+static void range_enc_v2_block(const RangeHost &rh, const uint8_t *row, uint32_t n, uint8_t *slot, uint64_t out_stride, uint64_t b,
+                               uint64_t *bit_off, uint64_t *bit_len, uint32_t *status) {
+    static thread_local uint32_t ring[kEncRingWords * kRingStrideWords];
+    RangeEncV2 L;
+    L.init(saddr_of(ring), slot, slot + out_stride);
+    L.put_word(n);
+    L.spill_check();
+    for (uint32_t i = 0; i < n; i += 16) {
+        uint32_t cnt = n - i >= 16 ? 16u : n - i;
+        uint8_t tmp[16] = {0};
+        memcpy(tmp, row + i, cnt);
+        u32x4 v;
+        memcpy(&v, tmp, 16);
+        range_enc_chunk<true, true>(L, saddr_of(rh.enc_tab.data()), 4, rh.c.t_shift, v, cnt);
+    }
+    uint64_t bits = L.finish();
+    uint32_t st = SCL_ST_OK;
+    if (L.bad) st = SCL_ST_BAD_SYMBOL;
+    if (L.ovf) st = SCL_ST_OVERFLOW;
+    bit_len[b] = bits;
+    bit_off[b] = b * out_stride * 8;
+    status[b] = st;
+}
+
+static uint32_t range_dec_v2_block(const RangeHost &rh, DecLaneV2 &D, uint8_t *out, uint64_t out_cap, uint32_t &size_out, uint64_t &used) {
+    RangeDecConst dc;
+    dc.lut = saddr_of(rh.dec_lut.data());
+    dc.shift = rh.c.t_shift;
+    dc.T = rh.c.T;
+    dc.last = rh.last_entry;
+    RangeDecV2 R;
+    uint32_t size = 0;
+    size_out = 0;
+    if (!range_dec_header(D, out_cap, size, R)) return SCL_ST_OVERFLOW;
+    range_dec_body<true>(D, R, dc, out, size, true);
+    size_out = size;
+    used = D.bp - D.start_bp;
+    return R.ovf ? SCL_ST_OVERFLOW : SCL_ST_OK;
+}
+
 int emu_encode_blocks_v2(void *h, const uint8_t *sym, uint64_t sym_stride, uint32_t block_len, uint64_t n_blocks, uint8_t *out,
                          uint64_t out_stride, uint64_t *bit_off, uint64_t *bit_len, uint32_t *status) {
     Emu *e = (Emu *)h;
     if (!emu_v2_eligible(h) || (out_stride & 31) || (((uintptr_t)out) & 31)) return SCL_E_INVALID;
     for (uint64_t b = 0; b < n_blocks; ++b) {
-        if (e->tans)
+        if (e->range)
+            range_enc_v2_block(*e->range, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
+        else if (e->tans)
             tans_enc_v2_block(*e, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
         else if (e->rans->c.NBO == 1)
             enc_v2_block<1>(*e->rans, sym + b * sym_stride, block_len, out + b * out_stride, out_stride, b, bit_off, bit_len, status);
@@ -373,6 +418,21 @@ int emu_decode_blocks_v2(void *h, const uint8_t *in, uint64_t in_bytes, const ui
     Emu *e = (Emu *)h;
     if (!emu_v2_eligible(h) || (sym_stride & 31) || (((uintptr_t)sym) & 31) || (((uintptr_t)in) & 31)) return SCL_E_INVALID;
     static thread_local uint32_t ring[(kDecRingWords + 1) * kRingStrideWords];
+    if (e->range) {
+        for (uint64_t b = 0; b < n_blocks; ++b) {
+            DecLaneV2 D;
+            D.init(in, in_bytes, bit_off[b], saddr_of(ring));
+            uint32_t size = 0;
+            uint64_t used = 0;
+            uint32_t st = range_dec_v2_block(*e->range, D, sym + b * sym_stride, sym_stride, size, used);
+            uint64_t avail = bit_len ? bit_len[b] : (in_bytes * 8 > bit_off[b] ? in_bytes * 8 - bit_off[b] : 0);
+            if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
+            sizes[b] = st == SCL_ST_OK ? size : 0;
+            consumed[b] = used;
+            status[b] = st;
+        }
+        return 0;
+    }
     const RansHost &r = e->tans ? e->tans->r : *e->rans;
     for (uint64_t b = 0; b < n_blocks; ++b) {
         DecLaneV2 D;

@@ -210,6 +210,78 @@ def test_range_batch_vs_oracle():
     _compare_batch_with_oracle(enc, dec, so.Oracle.range_coder(skew), d2)
 
 
+@pytest.mark.parametrize("name,shape", [("zipf", (1000, 4100)), ("zipf", (77, 333)), ("two", (300, 1000)), ("skew", (200, 2048)), ("T16", (130, 777)),
+                                        ("flat", (64, 4096))])
+def test_range_kernel_generations_agree(name, shape):
+    """Second-generation range-coder kernels (TMA tiles, sector rings, voted normalisation) against the
+    first-generation ones and the oracle: identical streams, each decodes the other's output, for block
+    counts that are not a multiple of 32 (padding lanes vote too) and lengths off the 64-byte tile."""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+    from stanford_compression_library_b200.workloads import zipf_freq_list
+
+    tables = {"zipf": zipf_freq_list(), "skew": [4096 - 255] + [1] * 255, "two": [4095, 1], "T16": [5, 3, 7, 1], "flat": [16] * 256}
+    fl = tables[name]
+    B, N = shape
+    rng = np.random.default_rng(31)
+    p = np.asarray(fl, dtype=np.float64) / sum(fl)
+    host = rng.choice(len(fl), size=(B, N), p=p).astype(np.uint8)
+    host[0, :] = len(fl) - 1                      # rarest symbol everywhere
+    host[1, :] = rng.integers(0, len(fl), N)      # far from the table's distribution: many multi-byte releases
+    data = torch.from_numpy(host).cuda()
+    params = RangeCoderParams()
+    enc, dec = RangeEncoder(params, _F(fl)), RangeDecoder(params, _F(fl))
+    lib = _cabi.lib()
+    try:
+        lib.scl_debug_force_v1(1)
+        e1 = enc.encode_blocks(data).check()
+        p1 = e1.pack()
+        lib.scl_debug_force_v1(0)
+        e2 = enc.encode_blocks(data).check()
+        p2 = e2.pack()
+        assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
+        assert torch.equal(p1.buf, p2.buf)
+        d2 = dec.decode_blocks(e1, N).check()      # v2 decoder on v1 output (slots)
+        d3 = dec.decode_blocks(p2, N).check()      # v2 decoder on packed streams (byte-granular offsets)
+        lib.scl_debug_force_v1(1)
+        d1 = dec.decode_blocks(e2, N).check()      # v1 decoder on v2 output
+    finally:
+        lib.scl_debug_force_v1(0)
+    for d in (d1, d2, d3):
+        assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
+        assert int(d.sizes.min()) == N == int(d.sizes.max())
+    oracle = so.Oracle.range_coder(fl)
+    for b in (0, 1, 2, B - 1):
+        ref_bytes, ref_bits = oracle.encode_block(host[b])
+        got = e2.block(b)
+        assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()
+
+
+def test_range_v2_decoder_ragged_sizes_and_alphabet_check():
+    """v2 decoder on a batch whose blocks differ in size (per-lane control flow instead of the vote), and the
+    v2 encoder's bad-symbol status when a byte value is not in the alphabet."""
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+
+    fl = [5, 3, 7, 1]
+    rng = np.random.default_rng(32)
+    B, N = 100, 500
+    host = rng.integers(0, 4, size=(B, N)).astype(np.uint8)
+    sizes = rng.integers(0, N + 1, size=B).astype(np.int32)
+    params = RangeCoderParams()
+    enc, dec = RangeEncoder(params, _F(fl)), RangeDecoder(params, _F(fl))
+    e = enc.encode_blocks(torch.from_numpy(host).cuda(), sizes=torch.from_numpy(sizes).cuda()).check()  # ragged: first-generation encoder
+    d = dec.decode_blocks(e, N).check()
+    assert torch.equal(d.sizes.cpu(), torch.from_numpy(sizes))
+    out = d.symbols.cpu().numpy()
+    for b in range(B):
+        assert (out[b, : sizes[b]] == host[b, : sizes[b]]).all()
+    host[3, 17] = 9  # not in the alphabet
+    e = enc.encode_blocks(torch.from_numpy(host).cuda())
+    with pytest.raises(KeyError):
+        e.check()
+    assert int((e.status != 0).sum()) == 1 and int(e.status[3]) != 0
+
+
 def test_aec_batch_vs_oracle_cfg4_shape():
     from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
     from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel

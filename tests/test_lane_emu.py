@@ -282,6 +282,95 @@ def test_emu_tans_v2_vs_oracle_zipf_lengths(rf):
         assert (st == 0).all() and (dsz == N).all() and (used == ln).all() and (dsym[:, :N] == sym).all()
 
 
+# ---- second-generation range-coder lanes (csrc/scl_range.cuh) -----------------------------------
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "range"], ids=case_id)
+def test_emu_range_v2_matches_golden(c):
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    if not coder.v2_eligible():
+        pytest.skip("parameter set not eligible for the range-coder v2 lanes")
+    n = c["n"]
+    out, off, ln, st = coder.encode_v2(c["data"].reshape(1, -1))
+    assert st[0] == 0 and int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    for lead in (0, 8, 248, 264):
+        bits = np.concatenate([np.ones(lead, dtype=np.uint8), np.unpackbits(packed)[:total]])
+        buf = np.concatenate([np.packbits(bits), np.zeros(7, dtype=np.uint8)])
+        sym, sizes, used, st = coder.decode_v2(buf, [lead], [total], max(n, 1))
+        assert st[0] == 0 and int(sizes[0]) == n and int(used[0]) == c["consumed"]
+        assert sym[0, :n].tolist() == c["data"].tolist()
+
+
+def _range_tables():
+    from stanford_compression_library_b200.workloads import zipf_freq_list
+
+    skew = [4096 - 255] + [1] * 255          # one dominant symbol: long settled runs, rare symbols release 2+ bytes
+    two = [4095, 1]                           # the reference's hardest shape: underflow chains
+    small_t = [5, 3, 7, 1]                    # T = 16, the smallest total the v2 lanes take
+    flat = [16] * 256
+    return {"zipf": zipf_freq_list(), "skew": skew, "two": two, "T16": small_t, "flat": flat}
+
+
+@pytest.mark.parametrize("name", ["zipf", "skew", "two", "T16", "flat"])
+def test_emu_range_v2_vs_oracle(name):
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    fl = _range_tables()[name]
+    n_sym = len(fl)
+    rng = np.random.default_rng(7)
+    prm = SclParams(coder=_cabi.CODER_RANGE, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, fl)
+    assert coder.v2_eligible()
+    oracle = so.Oracle.range_coder(fl)
+    p = np.asarray(fl, dtype=np.float64) / sum(fl)
+    for N in (0, 1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 100, 511, 1024, 4096):
+        sym = rng.choice(n_sym, size=(6, N), p=p).astype(np.uint8)
+        if N:
+            sym[0, :] = n_sym - 1                     # rarest symbol everywhere
+            sym[1, :] = 0                             # most frequent symbol everywhere
+            sym[2, :] = rng.integers(0, n_sym, N)     # uniform draws: far from the table's distribution
+        out, off, ln, st = coder.encode_v2(sym)
+        assert (st == 0).all(), (N, st)
+        for b in range(6):
+            enc, nb = oracle.encode_block(sym[b])
+            assert nb == ln[b], (N, b, nb, ln[b])
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (N, b)
+        dsym, dsz, used, st = coder.decode_v2(out, off, ln, max(N, 1))
+        assert (st == 0).all() and (dsz == N).all() and (used == ln).all(), (N, st, dsz, used, ln)
+        assert (dsym[:, :N] == sym).all()
+        # trailing garbage and the oracle's decoder agree on a bit-shifted copy as well
+        b = 3
+        bits = np.concatenate([np.zeros(40, dtype=np.uint8), np.unpackbits(extract_bits(out, off[b], ln[b]))[: int(ln[b])], rng.integers(0, 2, 77).astype(np.uint8)])
+        buf = np.concatenate([np.packbits(bits), np.zeros(8, dtype=np.uint8)])
+        dsym, dsz, used, st = coder.decode_v2(buf, [40], [int(ln[b]) + 77], max(N, 1))
+        assert st[0] == 0 and dsz[0] == N and used[0] == ln[b] and (dsym[0, :N] == sym[b]).all()
+
+
+def test_emu_range_v2_corrupt_stream_matches_v1_lanes():
+    """garbage input: the v2 lanes must make the v1 (reference-literal) lanes' choices (last-symbol
+    fallbacks of searchsorted) for as long as the stream lasts"""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+    from stanford_compression_library_b200.workloads import zipf_freq_list
+
+    fl = zipf_freq_list()
+    prm = SclParams(coder=_cabi.CODER_RANGE, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, fl)
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        N = 200
+        payload = rng.integers(0, 256, 600).astype(np.uint8)
+        buf = np.concatenate([np.array([0, 0, 0, N], dtype=np.uint8), payload, np.zeros(40, dtype=np.uint8)])
+        total = 8 * (4 + 600)
+        s1, z1, u1, st1 = coder.decode(buf, [0], [total], N)
+        s2, z2, u2, st2 = coder.decode_v2(buf, [0], [total], N)
+        assert st1[0] == st2[0] and u1[0] == u2[0] and z1[0] == z2[0]
+        assert (s1[0, :N] == s2[0, :N]).all()
+
+
 # ---- second-generation arithmetic-coder lanes (csrc/scl_aec.cuh) -------------------------------
 def _renorm_literal(P, low, high):
     """the reference's two loops (arithmetic_coding.py:126-150), literally"""
