@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         }
         RangeEncV2 L;
         uint8_t *slot = io.out + (active ? b : 0) * io.out_stride;
-        L.init(ring, slot, active ? slot + io.out_stride : slot);  // padding lanes: zero capacity, nothing is stored
+        L.init(ring, slot, active ? slot + io.out_stride : slot, shift);  // padding lanes: zero capacity, nothing is stored
         L.put_word(n);  // [size : 32] (range_coder.py:201-205)
         L.spill_check();
         for (uint32_t t = 0; t < n_tiles; ++t, ++tile_seq) {
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                 const uint32_t cnt = left - ch * 16 >= 16 ? 16u : left - ch * 16;
                 const uint4 q = *(const uint4 *)(row + ((ch ^ swz) << 4));
                 const u32x4 v = {q.x, q.y, q.z, q.w};
-                range_enc_chunk<CHECK, true>(L, my_tab, 128, shift, v, cnt);
+                range_enc_chunk<CHECK, true>(L, my_tab, 128, v, cnt);
             }
             __syncwarp();
             if (lane == 0 && t + kTileStages < n_tiles) {
@@ -607,6 +607,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     RangeDecConst dc;
     dc.lut = saddr_of(s_lut);
     dc.shift = shift;
+    dc.neg1 = 0xFFFFFFFFu - (shift >> 8);  // opaque -1
     dc.T = T;
     dc.last = last_entry;
 

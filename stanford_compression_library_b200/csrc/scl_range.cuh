@@ -4,12 +4,11 @@
 // The first-generation lanes (scl_lane.cuh) follow the reference loop by loop: 64-bit low/range, a
 // `while` normalisation whose trip count differs per lane, one scattered 4-byte global store per
 // word.  Measured: ~1000 cycles per warp-symbol (profiles/r1e_range_v1).  Here
-//   * low / range / state are 32-bit (low + range <= 2^32 always holds, see `norm_once`; the one
-//     case where the sum is exactly 2^32 is caught by the wrap test);
+//   * low / range / state are 32-bit (low + range <= 2^32 always holds, see `range_norm_mul`);
 //   * the normalisation runs two predicated iterations for every lane and then a warp-uniform
 //     `while (any lane still has to shift)` loop (rare: a symbol releases > 2 bytes only when the
 //     range underflows repeatedly), so the warp never diverges;
-//   * range // T is a shift; the decoder's (state - low) // r is an fp32 reciprocal estimate with
+//   * range // T is a multiply-high; the decoder's (state - low) // r is an fp32 reciprocal estimate with
 //     an exact integer correction, and one LUT read returns symbol, cum and freq;
 //   * coded bytes move through the lane-interleaved shared-memory rings of scl_fast.cuh and
 //     touch HBM in whole 32-byte sectors; symbols arrive by TMA tile (encode) and leave as
@@ -32,24 +31,26 @@ constexpr uint32_t kRangeTop = 1u << 24;     // TOP    = 2^(P-8)   (range_coder.
 constexpr uint32_t kRangeBottom = 1u << 16;  // BOTTOM = 2^(P-16)  (range_coder.py:73)
 constexpr uint32_t kRangeMaxExtra = 64;      // cap on the extra normalisation rounds of one symbol (hang protection only)
 
-// Does normalize() (range_coder.py:107-179 / :240-267) have to shift out a byte, and if the range
-// underflowed, what does it become first?  low + range <= 2^32 is an invariant: shrink_range only
-// narrows [low, low + range), a settled shift strips the common top byte of low and low + range,
-// and the underflow branch replaces range by (2^32 - low) mod 2^16.  So `hi` wraps only when the
-// sum is exactly 2^32, where the reference's unbounded-int XOR has bit 32 set (never settled).
+// One round of normalize() (range_coder.py:107-179 / :240-267): returns whether a byte is shifted out, and
+// replaces `range` first when it underflowed.
+//   settled  <=>  low and low + range agree above bit 24 (the reference XORs unbounded ints, so a sum of
+//                 exactly 2^32 is "not settled")  <=>  adding range does not carry out of low's 24 low bits
+//             <=>  range <= 0xFFFFFF - (low & 0xFFFFFF)
+// low + range <= 2^32 is an invariant (shrink_range only narrows [low, low + range); a settled shift strips
+// the common top byte; the underflow branch takes range = (2^32 - low) mod 2^16), so 32-bit low / range lose
+// nothing.  Measured alternatives (profiles/README.md, step r1q): the ALU pipe is the busy one here (93 % against
+// 15 % for the FMA pipe), but doing the shifts as multiplications by 256 / 1 on the FMA pipe was slower for the
+// encoder (longer latency per round, extra moves); only the decoder's bit cache, which nothing waits for, is
+// advanced that way.
 SCL_HD bool range_norm_test(uint32_t low, uint32_t &range) {
-    const uint32_t hi = low + range;
-    const bool settled = ((low ^ hi) < kRangeTop) & (hi >= low);
-    const bool under = !settled & (range < kRangeBottom);
-    range = under ? ((0u - low) & (kRangeBottom - 1)) : range;  // (MASK + 1 - low) & (BOTTOM - 1)
-    return settled | under;
+    const bool ns = range > (~low & 0x00FFFFFFu);  // not settled
+    const bool lt = range < kRangeBottom;
+    const uint32_t fix = (0u - low) & (kRangeBottom - 1);  // (MASK + 1 - low) & (BOTTOM - 1)
+    range = (ns & lt) ? fix : range;
+    return lt | !ns;
 }
-
 // the same test without touching the state: is another round needed?
-SCL_HD bool range_needs_norm(uint32_t low, uint32_t range) {
-    const uint32_t hi = low + range;
-    return (((low ^ hi) < kRangeTop) & (hi >= low)) | (range < kRangeBottom);
-}
+SCL_HD bool range_needs_norm(uint32_t low, uint32_t range) { return (range <= (~low & 0x00FFFFFFu)) | (range < kRangeBottom); }
 
 // ------------------------------------------------------------------------------------------------
 // encoder lane.  Bytes are appended to a 64-bit window (ahi:alo, newest byte in the low byte of
@@ -62,8 +63,11 @@ struct RangeEncV2 {
     saddr_t ring;
     uint8_t *gbegin, *gend;  // output slot; the stream starts at gbegin
     uint32_t ovf, bad;
+    uint32_t rshift, neg1;   // log2 T; and -1 as a run-time value (see DecConst)
 
-    SCL_HD void init(saddr_t ring_, uint8_t *slot_begin, uint8_t *slot_end) {
+    SCL_HD void init(saddr_t ring_, uint8_t *slot_begin, uint8_t *slot_end, uint32_t shift) {
+        rshift = shift;  // 4 <= shift <= 12
+        neg1 = 0xFFFFFFFFu - (shift >> 8);
         low = 0;
         range = 0xFFFFFFFFu;  // range_coder.py:191-192
         ahi = alo = nb = 0;
@@ -113,8 +117,8 @@ struct RangeEncV2 {
             rofs += 8 * 128;
         }
     }
-    // one normalisation round as straight-line code: a lane that has nothing to shift shifts by 0
-    SCL_HD bool norm_once() {
+    // one normalisation round as straight-line code: a lane that has nothing to shift multiplies by 1
+    SCL_HD void norm_once() {
         const bool go = range_norm_test(low, range);
         const uint32_t k = go ? 8u : 0u;
         ahi = funnel_l(alo, ahi, k);
@@ -122,18 +126,17 @@ struct RangeEncV2 {
         nb += k >> 3;
         low <<= k;
         range <<= k;
-        return go;
     }
-    // e = freq << 16 | cum for the symbol (0xFFFFFFFF: not in the alphabet); shift = log2 T
+    // e = freq << 16 | cum for the symbol (0xFFFFFFFF: not in the alphabet)
     template <bool CHECK, bool VOTE>
-    SCL_HD void step(uint32_t e, uint32_t shift) {
+    SCL_HD void step(uint32_t e) {
         if (CHECK && e == 0xFFFFFFFFu) {
             bad = 1;
             e = 1u << 16;  // keep every lane on the same path; the block's status reports the bad symbol
         }
-        const uint32_t r = range >> shift;  // shrink_range (range_coder.py:88-105)
-        low += (e & 0xFFFFu) * r;
-        range = r * (e >> 16);
+        const uint32_t r = range >> rshift;  // range // T: shrink_range (range_coder.py:88-105)
+        low = mad32(e & 0xFFFFu, r, low);
+        range = r * mulhi_fma(e, 1u << 16);
         norm_once();
         norm_once();  // a lane that did not shift in the first round does not in the second (state unchanged)
         // Two rounds are enough for all but ~0.02 % of symbols (Zipf data: 30 % shift 0 bytes, 62 % one, 8 % two),
@@ -184,7 +187,7 @@ struct RangeEncV2 {
 
 // 16 symbols of one lane (cnt < 16 only in the block's last chunk)
 template <bool CHECK, bool VOTE>
-SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, uint32_t shift, const u32x4 &v, uint32_t cnt) {
+SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v, uint32_t cnt) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     if (cnt == 16) {
         uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
@@ -192,7 +195,7 @@ SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, uin
         for (int j = 0; j < 4; ++j) {  // one word = 4 symbols per trip: the code stays resident in the instruction cache
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                L.template step<CHECK, VOTE>(lds32(tab + (saddr_t)mad32(byte_of(w0, b), sym_stride, 0u)), shift);
+                L.template step<CHECK, VOTE>(lds32(tab + (saddr_t)mad32(byte_of(w0, b), sym_stride, 0u)));
                 if (b & 1) L.spill_check();
             }
             if (j & 1) L.drain_check();  // <= 4 words per 8 symbols from the fixed rounds: the 16-word ring never overruns
@@ -202,7 +205,7 @@ SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, uin
         }
     } else {
         for (uint32_t i = 0; i < cnt; ++i) {
-            L.template step<CHECK, VOTE>(lds32(tab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)), shift);
+            L.template step<CHECK, VOTE>(lds32(tab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)));
             L.spill_check();
             L.drain_check();
         }
@@ -215,6 +218,7 @@ SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, uin
 struct RangeDecConst {
     saddr_t lut;     // lut[v] = freq << 20 | cum << 8 | byte value, v in [0, T)
     uint32_t shift;  // log2 T
+    uint32_t neg1;   // -1 as a run-time value
     uint32_t T;
     uint32_t last;   // the entry of the LAST alphabet index (numpy's searchsorted(...) - 1 == -1 and beyond-the-end cases)
 };
@@ -224,15 +228,15 @@ struct RangeDecV2 {
     uint32_t bits;  // the next unread stream bits, left-aligned (refreshed by the caller every two symbols)
     uint32_t ovf;
 
-    SCL_HD bool norm_once(DecLaneV2 &D) {
+    SCL_HD void norm_once(DecLaneV2 &D, uint32_t neg1) {
+        (void)neg1;
         const bool go = range_norm_test(low, range);
-        const uint32_t k = go ? 8u : 0u;
+        const uint32_t k = go ? 8u : 0u, mm = go ? 256u : 1u;
         state = funnel_l(bits, state, k);  // (state << 8) | next byte, or unchanged
-        bits <<= k;
+        bits *= mm;
         D.bp += k;
         low <<= k;
         range <<= k;
-        return go;
     }
     // decode_symbol (range_coder.py:225-238) + normalize (:240-267); returns the LUT entry (byte value in bits 0..7)
     template <bool VOTE>
@@ -258,22 +262,22 @@ struct RangeDecV2 {
         const bool last = state < low || q >= c.T;  // searchsorted index -1 -> alphabet[-1]; past the end -> the last symbol
         uint32_t e = lds32(c.lut + (saddr_t)((q & (c.T - 1)) << 2));
         if (last) e = c.last;
-        low += ((e >> 8) & 0xFFFu) * r;
-        range = r * (e >> 20);
-        norm_once(D);
-        norm_once(D);
+        low = mad32(mulhi_fma(e, 1u << 24) & 0xFFFu, r, low);
+        range = r * mulhi_fma(e, 1u << 12);
+        norm_once(D, c.neg1);
+        norm_once(D, c.neg1);
         const bool need = range_needs_norm(low, range);  // see RangeEncV2::step
-        if (SCL_UNLIKELY(VOTE ? warp_any(need) : need)) extra_rounds<VOTE>(D, need);
+        if (SCL_UNLIKELY(VOTE ? warp_any(need) : need)) extra_rounds<VOTE>(D, need, c.neg1);
         return e;
     }
     template <bool VOTE>
-    SCL_HD void extra_rounds(DecLaneV2 &D, bool need) {
+    SCL_HD void extra_rounds(DecLaneV2 &D, bool need, uint32_t neg1) {
         uint32_t guard = 0;
 #pragma unroll 1
         do {
             if (D.filled - D.bp < 64u) D.refill_now();  // far more extra rounds than the prefetch cadence allows for
             bits = D.peek32();
-            if (need) norm_once(D);
+            if (need) norm_once(D, neg1);
             bits = D.peek32();
             need = range_needs_norm(low, range);
             if (++guard > kRangeMaxExtra) {

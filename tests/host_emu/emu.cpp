@@ -360,7 +360,7 @@ static void range_enc_v2_block(const RangeHost &rh, const uint8_t *row, uint32_t
                                uint64_t *bit_off, uint64_t *bit_len, uint32_t *status) {
     static thread_local uint32_t ring[kEncRingWords * kRingStrideWords];
     RangeEncV2 L;
-    L.init(saddr_of(ring), slot, slot + out_stride);
+    L.init(saddr_of(ring), slot, slot + out_stride, rh.c.t_shift);
     L.put_word(n);
     L.spill_check();
     for (uint32_t i = 0; i < n; i += 16) {
@@ -369,7 +369,7 @@ static void range_enc_v2_block(const RangeHost &rh, const uint8_t *row, uint32_t
         memcpy(tmp, row + i, cnt);
         u32x4 v;
         memcpy(&v, tmp, 16);
-        range_enc_chunk<true, true>(L, saddr_of(rh.enc_tab.data()), 4, rh.c.t_shift, v, cnt);
+        range_enc_chunk<true, true>(L, saddr_of(rh.enc_tab.data()), 4, v, cnt);
     }
     uint64_t bits = L.finish();
     uint32_t st = SCL_ST_OK;
@@ -384,6 +384,7 @@ static uint32_t range_dec_v2_block(const RangeHost &rh, DecLaneV2 &D, uint8_t *o
     RangeDecConst dc;
     dc.lut = saddr_of(rh.dec_lut.data());
     dc.shift = rh.c.t_shift;
+    dc.neg1 = 0xFFFFFFFFu;
     dc.T = rh.c.T;
     dc.last = rh.last_entry;
     RangeDecV2 R;

@@ -37,7 +37,7 @@ def run(name, enc, dec, data):
     td = timeit(lambda: dec.decode_blocks(e, N, reuse=d))
     raw, C = B * N, e.total_bytes()
     res = dict(coder=name, blocks=B, block_len=N, bits_per_symbol=8 * C / raw, encode_ms=te, decode_ms=td, encode_GBps=raw / te / 1e6, decode_GBps=raw / td / 1e6,
-               encode_roofline_frac=(raw + C) / te / 1e6 / 6458.4, decode_roofline_frac=(raw + C) / td / 1e6 / 6458.4)
+               encode_roofline_frac=(raw + C) / te / 1e6 / 6548.5, decode_roofline_frac=(raw + C) / td / 1e6 / 6548.5)
     print(json.dumps(res))
     return res
 
@@ -52,7 +52,7 @@ def main():
     big = sample_blocks(p, 262144, 4096, seed=2, device="cuda:0")
     th = timeit(lambda: histogram_blocks(big, per_block=False))
     tb = timeit(lambda: histogram_blocks(big, total=False))
-    print(json.dumps(dict(coder="histogram 262144 x 4 KiB", total_only_ms=th, total_only_GBps=big.numel() / th / 1e6, roofline_frac=big.numel() / th / 1e6 / 6458.4,
+    print(json.dumps(dict(coder="histogram 262144 x 4 KiB", total_only_ms=th, total_only_GBps=big.numel() / th / 1e6, roofline_frac=big.numel() / th / 1e6 / 6548.5,
                           per_block_ms=tb, per_block_GBps=big.numel() / tb / 1e6)))
     del big
     run("rANS default (cfg2)", rANSEncoder(rANSParams(fr)), rANSDecoder(rANSParams(fr)), d4k)
@@ -61,6 +61,11 @@ def main():
     run("tANS RF=1 L=4096 (cfg3)", tANSEncoder(tp), tANSDecoder(tp), d4k)
     rp = RangeCoderParams()
     run("range coder (cfg2 shape)", RangeEncoder(rp, fr), RangeDecoder(rp, fr), d4k)
+    big = sample_blocks(p, 262144, 4096, seed=2, device="cuda:0")
+    run("range coder (262144 x 4 KiB, the bench.py shape)", RangeEncoder(rp, fr), RangeDecoder(rp, fr), big)
+    run("tANS RF=1 L=4096 (262144 x 4 KiB, the bench.py shape)", tANSEncoder(tp), tANSDecoder(tp), big)
+    del big
+    torch.cuda.empty_cache()
     ap = AECParams()
     uni = Frequencies({b: 1 for b in range(256)})
     run("arithmetic adaptive order-0, 262144 x 1 KiB (cfg4 shape / 4)", ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)),
