@@ -33,6 +33,15 @@ VARIANTS = {
 HEADLINE = "default"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def host_threads():
     """Host threads the CPU arm may use: the cores this process is allowed on (torchrun exports
     OMP_NUM_THREADS=1, so the OpenMP default is not a usable answer)."""
@@ -155,7 +164,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -175,6 +184,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr for the rest of
+    # the run, so that library chatter (NCCL's version banner under NCCL_DEBUG, torch warnings) cannot get in
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -366,7 +381,7 @@ def main():
             "kernel_paths": hs["kernel_paths"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps,
             "clocks": head["clocks"], "also": also, "global_compressed_bytes": int(sum(sizes)),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
