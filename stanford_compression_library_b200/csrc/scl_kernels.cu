@@ -600,7 +600,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const saddr_t ring = saddr_of(smem + warp * kDecWarpSmem) + lane * 4;
+    saddr_t ring = saddr_of(smem + warp * kDecWarpSmem) + lane * 4;
+    asm volatile("" : "+r"(ring));  // keep it in a register: the compiler otherwise recomputes it from threadIdx at every peek (8 instructions)
     const uint32_t *s_lut = (const uint32_t *)(smem + W * kDecWarpSmem);
     stage_table((void *)s_lut, g_lut, lut_bytes, &mbar);
     const uint32_t total_warps = gridDim.x * W;

@@ -27,6 +27,18 @@ SCL_HD bool warp_any(bool p) {
 #endif
 }
 
+// 1 / x to ~23 bits: one MUFU.RCP (the IEEE-rounded __frcp_rn is a Newton step, a range check and a slow-path
+// call on top of it; the quotient estimate is corrected exactly afterwards, so the approximation is enough)
+SCL_HD float rcp_approx(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 constexpr uint32_t kRangeTop = 1u << 24;     // TOP    = 2^(P-8)   (range_coder.py:72)
 constexpr uint32_t kRangeBottom = 1u << 16;  // BOTTOM = 2^(P-16)  (range_coder.py:73)
 constexpr uint32_t kRangeMaxExtra = 64;      // cap on the extra normalisation rounds of one symbol (hang protection only)
@@ -244,12 +256,7 @@ struct RangeDecV2 {
         const uint32_t r = range >> c.shift;
         const uint32_t a = state - low;
         // q = a // r: fp32 estimate (error << 1 for q <= T + 1), clamped, then corrected exactly
-        float qf = (float)a *
-#ifdef __CUDA_ARCH__
-                   __frcp_rn((float)r);
-#else
-                   (1.0f / (float)r);
-#endif
+        float qf = (float)a * rcp_approx((float)r);
         const float cap = (float)(c.T + 1);
         uint32_t q = (uint32_t)(qf < cap ? qf : cap);
         if (q <= c.T) {  // q * r <= T * r <= range < 2^32; |a - q * r| < 2 r <= 2^29 because T >= 16 (host-checked)
