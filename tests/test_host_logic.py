@@ -141,3 +141,30 @@ def test_normalize_frequencies_properties():
     p = np.array(zipf_probabilities())
     f = normalize_frequencies(np.round(p * 1e9).astype(np.int64), 4096)
     assert [f.freq_dict[b] for b in range(256)] == zipf_freq_list()
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract on stdout: ONE JSON line (library chatter goes to stderr), carrying the
+    tier's keys for the reference arm; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rans_encode_plus_decode_throughput" and d["unit"] == "MB/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank of a multi-process launch does no work and prints nothing
+    env.update(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
