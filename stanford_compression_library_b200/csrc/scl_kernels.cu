@@ -953,6 +953,77 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const uint8_t *__restric
     }
 }
 
+// Second generation: one warp per block, 16 output bytes per lane and step.  Byte i of a block's packed
+// payload is bits [8i - lead, 8i - lead + 8) of its stream (lead = 0, or the framing's 3 + num_pad bits);
+// once the destination is 16-byte aligned and all 128 bits are real stream bits, a chunk is five aligned
+// 32-bit source words, four funnel shifts and one 128-bit store (a warp reads ~528 and writes 512
+// contiguous bytes per step).  The few bytes before / after go through the bitwise path above.
+// Needs a 4-byte aligned `src` that is readable up to the next 4-byte boundary after the last stream bit.
+template <bool FRAMED>
+__device__ __forceinline__ uint32_t pack_payload_byte(const uint8_t *src, uint64_t off, uint64_t nbits, uint32_t num_pad, uint64_t lead,
+                                                       uint64_t i) {
+    uint32_t v = 0;
+    if (8 * i >= lead && 8 * i - lead + 8 <= nbits) return src_byte_at_bit(src, off + 8 * i - lead);
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint64_t q = 8 * i + k;
+        uint32_t bit = 0;
+        if (FRAMED && q < 3) {
+            bit = (num_pad >> (2 - q)) & 1u;
+        } else if (q >= lead && q - lead < nbits) {
+            const uint64_t p = off + (q - lead);
+            bit = (src[p >> 3] >> (7 - (p & 7))) & 1u;
+        }
+        v |= bit << (7 - k);
+    }
+    return v;
+}
+
+constexpr int kPackWarps = 8;
+template <bool FRAMED>
+__global__ void __launch_bounds__(kPackWarps * 32) pack_v2_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_bit_off,
+                                                                  const uint64_t *__restrict__ bit_len, uint8_t *__restrict__ dst,
+                                                                  const uint64_t *__restrict__ dst_byte_off, uint64_t n_blocks) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp0 = (uint64_t)blockIdx.x * kPackWarps + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * kPackWarps;
+    const uint32_t *src32 = (const uint32_t *)src;
+    for (uint64_t b = warp0; b < n_blocks; b += n_warps) {
+        const uint64_t off = src_bit_off[b], nbits = bit_len[b];
+        uint8_t *d = dst + dst_byte_off[b];
+        const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
+        const uint64_t lead = FRAMED ? 3 + num_pad : 0;
+        const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
+        if (FRAMED) {
+            if (lane < 4) d[lane] = (uint8_t)(payload_bytes >> (8 * (3 - lane)));  // u32 big-endian (HeaderHandler)
+            d += 4;
+        }
+        // head: up to the first 16-byte aligned destination byte whose bits are all stream bits
+        uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
+        while (8 * head < lead) head += 16;
+        if (head > payload_bytes) head = payload_bytes;
+        // full chunks: 8 * (i0 + 16) - lead <= nbits
+        const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
+        for (uint64_t i = lane; i < head; i += 32) d[i] = (uint8_t)pack_payload_byte<FRAMED>(src, off, nbits, num_pad, lead, i);
+        for (uint64_t ch = lane; ch < n_chunks; ch += 32) {
+            const uint64_t i0 = head + 16 * ch;
+            const uint64_t S = off + 8 * i0 - lead;  // absolute source bit of the chunk's first bit
+            const uint32_t *w = src32 + (S >> 5);
+            const uint32_t sh = (uint32_t)(S & 31);
+            uint32_t W[5];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) W[j] = bswap32(__ldg(w + j));
+            W[4] = sh ? bswap32(__ldg(w + 4)) : 0u;  // not needed (and possibly past the stream) when the chunk is word aligned
+            uint4 o;
+            o.x = bswap32(funnel_l(W[1], W[0], sh));
+            o.y = bswap32(funnel_l(W[2], W[1], sh));
+            o.z = bswap32(funnel_l(W[3], W[2], sh));
+            o.w = bswap32(funnel_l(W[4], W[3], sh));
+            *(uint4 *)(d + i0) = o;
+        }
+        for (uint64_t i = head + 16 * n_chunks + lane; i < payload_bytes; i += 32)
+            d[i] = (uint8_t)pack_payload_byte<FRAMED>(src, off, nbits, num_pad, lead, i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Byte histograms: DataBlock.get_counts (scl/core/data_block.py:37-64) for a batch of blocks, the
 // step before the coders.  One warp per block; each lane streams 16-byte
@@ -1541,11 +1612,25 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     return SCL_E_INVALID;
 }
 
+// warps of 32 lanes each take whole blocks, grid-stride: enough CTAs to fill the GPU (8 per SM), no more than the blocks need
+static uint32_t pack_grid(uint64_t n_blocks) {
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    uint64_t want = (n_blocks + kPackWarps - 1) / kPackWarps, cap = (uint64_t)(n_sm > 0 ? n_sm : 1) * 8;
+    return (uint32_t)(want < cap ? want : cap);
+}
+
 extern "C" int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
                                uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream) {
     if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
     if (n_blocks == 0) return SCL_E_OK;
     if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    if (!g_force_v1 && (((uintptr_t)d_src) & 3) == 0) {
+        pack_v2_kernel<false><<<pack_grid(n_blocks), kPackWarps * 32, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
+                                                                                                 d_dst_byte_offset, n_blocks);
+        return check_launch("pack_v2_kernel");
+    }
     pack_kernel<false><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
                                                                                   d_dst_byte_offset);
     return check_launch("pack_kernel");
@@ -1556,6 +1641,11 @@ extern "C" int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_
     if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
     if (n_blocks == 0) return SCL_E_OK;
     if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    if (!g_force_v1 && (((uintptr_t)d_src) & 3) == 0) {
+        pack_v2_kernel<true><<<pack_grid(n_blocks), kPackWarps * 32, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
+                                                                                                d_dst_byte_offset, n_blocks);
+        return check_launch("frame_v2_kernel");
+    }
     pack_kernel<true><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
                                                                                  d_dst_byte_offset);
     return check_launch("frame_kernel");

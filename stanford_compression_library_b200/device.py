@@ -86,7 +86,8 @@ class EncodedBlocks:
     def pack(self) -> "EncodedBlocks":
         """Contiguous, byte-aligned, left-aligned streams == concatenated BitArray.tobytes()."""
         offs, total = self.packed_offsets()
-        dst = torch.zeros(total + 16, dtype=torch.uint8, device=self.buf.device)
+        dst = torch.empty(total + 16, dtype=torch.uint8, device=self.buf.device)  # the kernel writes every byte below `total`
+        dst[total:].zero_()
         with torch.cuda.device(self.buf.device):
             rc = _cabi.lib().scl_pack_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
         _cabi.check(rc, "scl_pack_blocks")
@@ -100,7 +101,8 @@ class EncodedBlocks:
         ends = torch.cumsum(nbytes, 0)
         offs = ends - nbytes
         total = int(ends[-1]) if self.n_blocks else 0
-        dst = torch.zeros(total + 16, dtype=torch.uint8, device=self.buf.device)
+        dst = torch.empty(total + 16, dtype=torch.uint8, device=self.buf.device)
+        dst[total:].zero_()
         with torch.cuda.device(self.buf.device):
             rc = _cabi.lib().scl_frame_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
         _cabi.check(rc, "scl_frame_blocks")

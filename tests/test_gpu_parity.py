@@ -414,6 +414,51 @@ def test_aec_order_k_count_limit_and_table_limit():
         enc.encode_block(DataBlock([0, 1, 2]))
 
 
+@pytest.mark.parametrize("coder", ["rans_default", "rans_nbo8", "range", "aec"])
+def test_pack_and_frame_kernel_generations_agree(coder):
+    """pack / frame, second generation (warp per block, 16-byte chunks by funnel shift) against the byte-wise
+    first generation: identical bytes for bit-misaligned (61-bit rANS header), byte-aligned (NUM_BITS_OUT=8,
+    range coder) and forward bit-granular (arithmetic) streams of ragged lengths, empty blocks included."""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.compressors.rANS import rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeEncoder
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies
+
+    fl = zipf_freq_list()
+    B, N = 700, 4096
+    data = sample_blocks(fl, B, N, seed=41, device="cuda:0")
+    sizes = _seeded_sizes(0, N + 1, B)
+    sizes[:4] = torch.tensor([0, 1, 15, N], dtype=sizes.dtype)
+    if coder == "rans_default":
+        enc = rANSEncoder(rANSParams(zipf_frequencies()))
+    elif coder == "rans_nbo8":
+        enc = rANSEncoder(rANSParams(zipf_frequencies(), NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12))
+    elif coder == "range":
+        enc = RangeEncoder(RangeCoderParams(), zipf_frequencies())
+    else:
+        ap = AECParams()
+        enc = ArithmeticEncoder(ap, AdaptiveIIDFreqModel(_F([1] * 256), ap.MAX_ALLOWED_TOTAL_FREQ))
+        data, sizes = data[:, :1024].contiguous(), torch.clamp(sizes, max=1024)
+    e = enc.encode_blocks(data, sizes=sizes).check()
+    lib = _cabi.lib()
+    try:
+        lib.scl_debug_force_v1(1)
+        p1, (f1, o1) = e.pack(), e.frame()
+        lib.scl_debug_force_v1(0)
+        p2, (f2, o2) = e.pack(), e.frame()
+        pp1 = p2.pack()  # packing an already packed (byte-aligned, contiguous) buffer is the identity
+    finally:
+        lib.scl_debug_force_v1(0)
+    assert torch.equal(p1.buf, p2.buf) and torch.equal(p1.bit_offset, p2.bit_offset)
+    assert torch.equal(f1, f2) and torch.equal(o1, o2)
+    assert torch.equal(pp1.buf, p2.buf)
+    for b in (0, 1, 2, 3, 4, B - 1):  # and against the host's BitArray.tobytes()
+        off, nb = int(p2.bit_offset[b]) // 8, (int(e.bit_len[b]) + 7) // 8
+        assert p2.buf[off : off + nb].cpu().numpy().tobytes() == e.block(b).tobytes()
+
+
 def test_pack_and_frame_kernels():
     from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
     from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies

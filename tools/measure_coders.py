@@ -56,6 +56,14 @@ def main():
                           per_block_ms=tb, per_block_GBps=big.numel() / tb / 1e6)))
     del big
     run("rANS default (cfg2)", rANSEncoder(rANSParams(fr)), rANSDecoder(rANSParams(fr)), d4k)
+    # pack / frame kernels on the cfg2 batch's encoder output: bytes moved = 2 x coded bytes
+    e = rANSEncoder(rANSParams(fr)).encode_blocks(d4k).check()
+    C = e.total_bytes()
+    tp = timeit(lambda: e.pack())
+    tf = timeit(lambda: e.frame())
+    print(json.dumps(dict(coder="pack / frame of 65536 rANS streams (incl. torch cumsum + allocation)", coded_bytes=C, pack_ms=tp, frame_ms=tf,
+                          pack_GBps_read_plus_write=2 * C / tp / 1e6, frame_GBps_read_plus_write=2 * C / tf / 1e6)))
+    del e
     run("rANS nbo8 rf4096 (cfg2)", rANSEncoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), rANSDecoder(rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)), d4k)
     tp = tANSParams(fr, RANGE_FACTOR=1)
     run("tANS RF=1 L=4096 (cfg3)", tANSEncoder(tp), tANSDecoder(tp), d4k)
