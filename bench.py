@@ -128,6 +128,48 @@ def cpu_baseline(fl, kw, data_host, n_threads, label):
     }
 
 
+def bench_other_configs(data, freqs, peak, dev):
+    """tANS on configs[2] and the arithmetic coder on configs[3]: encode / decode MB/s of raw bytes, CUDA events,
+    best of 5, round trip checked."""
+    import torch
+
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+
+    def measure(enc, dec, d):
+        nB, n = d.shape
+        e = enc.encode_blocks(d)
+        r = dec.decode_blocks(e, n)
+        e.check(), r.check()
+        assert torch.equal(r.symbols[:, :n], d), "round trip failed"
+        C = e.total_bytes()
+        best = [1e30, 1e30]
+        for _ in range(5):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            enc.encode_blocks(d, reuse=e)
+            ev[1].record()
+            dec.decode_blocks(e, n, reuse=r)
+            ev[2].record()
+            torch.cuda.synchronize()
+            best = [min(best[0], ev[0].elapsed_time(ev[1])), min(best[1], ev[1].elapsed_time(ev[2]))]
+        raw = nB * n
+        return {"blocks": nB, "block_len": n, "encode_ms": best[0], "decode_ms": best[1], "encode_MBps": raw / best[0] / 1e3, "decode_MBps": raw / best[1] / 1e3,
+                "bits_per_symbol": 8.0 * C / raw, "roofline_encode_frac": (raw + C) / best[0] / 1e6 / peak, "roofline_decode_frac": (raw + C) / best[1] / 1e6 / peak}
+
+    out = {}
+    tp = tANSParams(freqs, RANGE_FACTOR=1)  # 256-symbol alphabet, L = M = 4096 states (SURVEY.md 8a on configs[2])
+    out["cfg3_tans_65536_blocks_L4096"] = measure(tANSEncoder(tp), tANSDecoder(tp), data[:65536])
+    ap = AECParams()
+    uni = Frequencies({b: 1 for b in range(256)})
+    d4 = data.reshape(-1, 1024)[: 1 << 20]  # the same Zipf bytes as 1 KiB blocks
+    out["cfg4_arithmetic_adaptive_order0_%d_blocks_x_1KiB" % d4.shape[0]] = measure(
+        ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)), ArithmeticDecoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)), d4)
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU implementation of the path (the oracle port -- the Python reference
     cannot travel to the GPU box) on all host threads, same metric / config, bounded sample per step."""
@@ -360,6 +402,9 @@ def main():
         for k in VARIANTS:
             r = bench_variant(k, data[:65536], max(5, args.steps // 2), 3)
             also["cfg2_65536_blocks_" + k] = summarize(r, 1)
+        # BASELINE configs[2] (tANS, same 65 536 x 4 KiB batch) and configs[3] (arithmetic coder, adaptive order-0 model,
+        # 1 048 576 x 1 KiB) through the same drop-in classes: informative lines, the headline stays rANS
+        also.update(bench_other_configs(data, freqs, peak, dev))
         from oracle import scl_oracle as so
 
         so.build()
