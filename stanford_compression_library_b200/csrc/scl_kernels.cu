@@ -998,7 +998,8 @@ __global__ void __launch_bounds__(kPackWarps * 32) pack_v2_kernel(const uint8_t 
         }
         // head: up to the first 16-byte aligned destination byte whose bits are all stream bits
         uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
-        while (8 * head < lead) head += 16;
+        if (FRAMED)
+            while (8 * head < lead) head += 16;
         if (head > payload_bytes) head = payload_bytes;
         // full chunks: 8 * (i0 + 16) - lead <= nbits
         const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
@@ -1027,26 +1028,28 @@ __global__ void __launch_bounds__(kPackWarps * 32) pack_v2_kernel(const uint8_t 
 // ------------------------------------------------------------------------------------------------
 // Byte histograms: DataBlock.get_counts (scl/core/data_block.py:37-64) for a batch of blocks, the
 // step before the coders.  One warp per block; each lane streams 16-byte
-// pieces of the row (coalesced 512 B per warp load) into one of 4 lane-interleaved sub-histograms
+// pieces of the row (coalesced 512 B per warp load) into one of kHistSub lane-interleaved sub-histograms
 // in shared memory (cuts same-bin atomic contention on skewed data), then the warp writes the
 // block's 256 counts and/or folds them into a grid-wide total.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHistWarps = 8;
+constexpr int kHistSub = 4;  // sub-histograms per warp (dynamic shared memory: kHistWarps * kHistSub KiB)
 __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(const uint8_t *__restrict__ sym, uint64_t sym_stride,
                                                                     const uint32_t *__restrict__ sizes, uint32_t block_len, uint64_t n_blocks,
                                                                     uint32_t *__restrict__ counts, unsigned long long *__restrict__ total) {
-    __shared__ uint32_t s_hist[kHistWarps][4][256];
+    extern __shared__ __align__(16) uint32_t s_hist_raw[];
+    uint32_t(*s_hist)[kHistSub][256] = (uint32_t(*)[kHistSub][256])s_hist_raw;
     __shared__ uint32_t s_total[256];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_total[i] = 0;
     __syncthreads();
     uint32_t(*h)[256] = s_hist[warp];
     for (uint64_t b = (uint64_t)blockIdx.x * kHistWarps + warp; b < n_blocks; b += (uint64_t)gridDim.x * kHistWarps) {
-        for (uint32_t i = lane; i < 4 * 256; i += 32) (&h[0][0])[i] = 0;
+        for (uint32_t i = lane; i < kHistSub * 256; i += 32) (&h[0][0])[i] = 0;
         __syncwarp();
         const uint8_t *row = sym + b * sym_stride;
         const uint32_t n = sizes ? sizes[b] : block_len;
-        uint32_t *mine = h[lane & 3];
+        uint32_t *mine = h[lane & (kHistSub - 1)];
         uint32_t i = 0;
         if ((((uintptr_t)row) & 15) == 0) {
             for (uint32_t base = 0; base + 512 <= n; base += 512) {
@@ -1065,7 +1068,9 @@ __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(const uint8_
         for (uint32_t k = i + lane; k < n; k += 32) atomicAdd(&mine[row[k]], 1u);
         __syncwarp();
         for (uint32_t v = lane; v < 256; v += 32) {
-            uint32_t c = h[0][v] + h[1][v] + h[2][v] + h[3][v];
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < kHistSub; ++j) c += h[j][v];
             if (counts) counts[b * 256 + v] = c;
             if (total && c) atomicAdd(&s_total[v], c);
         }
@@ -1495,8 +1500,9 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         return check_launch("tans_encode_kernel");
     }
     if (c->range) {
-        if (c->range->v2 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
-            (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36)) {
+        // block_len < 2^24: the lanes count ring words in 32 bits (* 128), and a symbol releases at most 3 bytes
+        if (c->range->v2 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && block_len < (1u << 24) && (sym_stride % 16) == 0 &&
+            (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36)) {
             int rc2 = launch_range_encode_v2(c, io, s);
             if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
         }
@@ -1546,8 +1552,9 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     uint32_t grid = (uint32_t)((n_blocks + kThreads - 1) / kThreads);
     if (c->rans) {
         const RansHost &r = *c->rans;
+        // sym_stride * kFastMaxBitsPerSym < 2^31: the lanes keep the stream position in 32 bits (as the encoder's guard on block_len)
         if (r.dec32 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
-            n_blocks < (1ull << 36))
+            n_blocks < (1ull << 36) && sym_stride * kFastMaxBitsPerSym < (1ull << 31))
             return r.c.NBO == 1 ? launch_decode_v2<0, 1>(c, r.c, c->d_dec32, c->dec32_bytes, io, s)
                                 : launch_decode_v2<0, 8>(c, r.c, c->d_dec32, c->dec32_bytes, io, s);
         if (r.dec32)
@@ -1559,7 +1566,7 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     if (c->tans) {
         const TansHost &t = *c->tans;
         if (c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
-            n_blocks < (1ull << 36))
+            n_blocks < (1ull << 36) && sym_stride * kFastMaxBitsPerSym < (1ull << 31))
             return launch_decode_v2<1, 1>(c, t.r.c, c->d_tdec, c->ttab_bytes, io, s);
         if (c->ttab_bytes <= kTansSmemTableMax) {
             SCL_CUDA(cudaFuncSetAttribute(tans_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
@@ -1570,8 +1577,9 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         return check_launch("tans_decode_kernel");
     }
     if (c->range) {
+        // sym_stride < 2^24 bounds the decoded size, hence the 32-bit bit position of DecLaneV2 (<= 24 bits per symbol)
         if (c->range->v2 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
-            n_blocks < (1ull << 36)) {
+            sym_stride < (1ull << 24) && n_blocks < (1ull << 36)) {
             const RangeHost &rh = *c->range;
             uint32_t n_tasks = (uint32_t)((n_blocks + 31) / 32), g2, warps;
             pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem, c->range_dec_lut_bytes), &g2, &warps);
@@ -1668,10 +1676,13 @@ extern "C" int scl_histogram_blocks(const uint8_t *d_sym, uint64_t sym_stride, c
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     uint64_t want = (n_blocks + kHistWarps - 1) / kHistWarps;
-    uint32_t grid = (uint32_t)(want < (uint64_t)n_sm * 4 ? want : (uint64_t)n_sm * 4);  // <= 4 CTAs per SM, grid-stride over blocks
+    const uint64_t per_sm = (227 * 1024) / (kHistWarps * kHistSub * 1024 + 2048);  // resident CTAs per SM by shared memory
+    uint32_t grid = (uint32_t)(want < (uint64_t)n_sm * per_sm ? want : (uint64_t)n_sm * per_sm);  // grid-stride over blocks
     // s_total is 32-bit per CTA: bound the bytes one CTA can see
     if ((n_blocks / grid + 1) * kHistWarps * (uint64_t)block_len >= (1ull << 32)) return SCL_E_UNSUPPORTED;
-    histogram_kernel<<<grid, kHistWarps * 32, 0, (cudaStream_t)stream>>>(d_sym, sym_stride, d_sizes, block_len, n_blocks, d_counts,
+    const int hist_smem = kHistWarps * kHistSub * 256 * 4;
+    SCL_CUDA(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem));
+    histogram_kernel<<<grid, kHistWarps * 32, hist_smem, (cudaStream_t)stream>>>(d_sym, sym_stride, d_sizes, block_len, n_blocks, d_counts,
                                                                        (unsigned long long *)d_total);
     return check_launch("histogram_kernel");
 }
