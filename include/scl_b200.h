@@ -149,7 +149,11 @@ int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64_t in_bytes
 /* Compact per-block streams into one contiguous buffer: block b is copied to byte offset
  * d_dst_byte_offset[b] of d_dst, left-aligned, zero-padded to a whole byte -- the bytes of
  * BitArray.tobytes() (bitarray_utils.py:25).  d_dst_byte_offset is caller-computed (exclusive
- * prefix sum of ceil(bit_len/8), or any layout with room). */
+ * prefix sum of ceil(bit_len/8), or any layout with room).
+ * A 4-byte aligned d_src takes the fast kernel (16-byte chunks per lane), which reads whole
+ * aligned 32-bit words: the source must be readable up to the next 4-byte boundary after the last
+ * stream bit (slot buffers sized with scl_coder_max_encoded_bytes are).  Other sources take the
+ * byte-wise kernel. */
 int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len,
                     uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream);
 
