@@ -203,15 +203,29 @@ SCL_HD void range_enc_chunk(RangeEncV2 &L, saddr_t tab, uint32_t sym_stride, con
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     if (cnt == 16) {
         uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        uint32_t e0, e1, e2, e3;  // the word's four table entries, fetched one word ahead of their use
+        e0 = lds32(tab + (saddr_t)mad32(byte_of(w0, 0), sym_stride, 0u));
+        e1 = lds32(tab + (saddr_t)mad32(byte_of(w0, 1), sym_stride, 0u));
+        e2 = lds32(tab + (saddr_t)mad32(byte_of(w0, 2), sym_stride, 0u));
+        e3 = lds32(tab + (saddr_t)mad32(byte_of(w0, 3), sym_stride, 0u));
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {  // one word = 4 symbols per trip: the code stays resident in the instruction cache
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                L.template step<CHECK, VOTE>(lds32(tab + (saddr_t)mad32(byte_of(w0, b), sym_stride, 0u)));
-                if (b & 1) L.spill_check();
-            }
+            // (after the last word w1 repeats w3's bytes: four harmless extra loads instead of a branch)
+            const uint32_t n0 = lds32(tab + (saddr_t)mad32(byte_of(w1, 0), sym_stride, 0u));
+            const uint32_t n1 = lds32(tab + (saddr_t)mad32(byte_of(w1, 1), sym_stride, 0u));
+            const uint32_t n2 = lds32(tab + (saddr_t)mad32(byte_of(w1, 2), sym_stride, 0u));
+            const uint32_t n3 = lds32(tab + (saddr_t)mad32(byte_of(w1, 3), sym_stride, 0u));
+            L.template step<CHECK, VOTE>(e0);
+            L.template step<CHECK, VOTE>(e1);
+            L.spill_check();
+            L.template step<CHECK, VOTE>(e2);
+            L.template step<CHECK, VOTE>(e3);
+            L.spill_check();
             if (j & 1) L.drain_check();  // <= 4 words per 8 symbols from the fixed rounds: the 16-word ring never overruns
-            w0 = w1;
+            e0 = n0;
+            e1 = n1;
+            e2 = n2;
+            e3 = n3;
             w1 = w2;
             w2 = w3;
         }
