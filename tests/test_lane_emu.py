@@ -348,6 +348,43 @@ def test_emu_range_v2_vs_oracle(name):
         assert st[0] == 0 and dsz[0] == N and used[0] == ln[b] and (dsym[0, :N] == sym[b]).all()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_emu_range_v2_random_tables_vs_oracle(seed):
+    """random power-of-two totals (16 .. 4096), random alphabet sizes and skews, data drawn uniformly (not from the
+    table): the v2 lanes against the oracle, bit for bit, and back"""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(100 + seed)
+    T = 1 << int(rng.integers(4, 13))
+    n_sym = int(rng.integers(2, min(256, T) + 1))
+    # random composition of T into n_sym positive parts, skewed
+    w = rng.random(n_sym) ** int(rng.integers(1, 6))
+    f = np.maximum(1, np.floor(w / w.sum() * (T - n_sym)).astype(np.int64) + 1)
+    while f.sum() > T:
+        f[np.argmax(f)] -= 1
+    f[np.argmin(f)] += T - f.sum()
+    if f.max() > 4095:  # outside the v2 lanes' table format: split the surplus
+        pytest.skip("f > 4095")
+    fl = [int(x) for x in f]
+    assert sum(fl) == T and min(fl) >= 1
+    prm = SclParams(coder=_cabi.CODER_RANGE, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32, model=0,
+                    max_allowed_total_freq=0)
+    coder = EmuCoder(prm, None, fl)
+    assert coder.v2_eligible()
+    oracle = so.Oracle.range_coder(fl)
+    for N in (1, 33, 257, 1500):
+        sym = rng.integers(0, n_sym, size=(4, N)).astype(np.uint8)
+        sym[0, :] = int(np.argmin(f))
+        out, off, ln, st = coder.encode_v2(sym)
+        assert (st == 0).all()
+        for b in range(4):
+            enc, nb = oracle.encode_block(sym[b])
+            assert nb == ln[b] and extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (T, n_sym, N, b)
+        dsym, dsz, used, st = coder.decode_v2(out, off, ln, N)
+        assert (st == 0).all() and (dsz == N).all() and (used == ln).all() and (dsym[:, :N] == sym).all()
+
+
 def test_emu_range_v2_corrupt_stream_matches_v1_lanes():
     """garbage input: the v2 lanes must make the v1 (reference-literal) lanes' choices (last-symbol
     fallbacks of searchsorted) for as long as the stream lasts"""

@@ -108,3 +108,19 @@ def test_log_binning_rejects_too_large_values():
 @pytest.mark.parametrize("c", CASES, ids=ids)
 def test_device_rans_stage_matches_reference_composition(c):
     _run_case(c)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_streams_round_trip_random_sequences_with_oracle_stage(seed, monkeypatch):
+    """random LZ77 sequences (small and huge offsets, zero counts, empty literal lists) through the streams coder
+    and back, the oracle standing in for the rANS stage"""
+    so.build()
+    monkeypatch.setattr(lz, "rANSEncoder", _OracleRansEncoder)
+    monkeypatch.setattr(lz, "rANSDecoder", _OracleRansDecoder)
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(0, 60))
+    seqs = [lz.LZ77Sequence(int(rng.integers(0, 40)), int(rng.integers(0, 300)), int(rng.integers(0, 1 << int(rng.integers(1, 31))))) for _ in range(n)]
+    literals = [int(x) for x in rng.integers(0, 256, size=int(rng.integers(0, 200)))]
+    bits = lz.LZ77StreamsEncoder().encode_block(seqs, literals)
+    (dseqs, dlits), used = lz.LZ77StreamsDecoder().decode_block(bits + BitArray("110"))
+    assert dseqs == seqs and list(dlits) == literals and used == len(bits)
