@@ -216,7 +216,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks-per-gpu", type=int, default=BLOCKS_PER_GPU)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-chunk", type=int, default=16384)
     ap.add_argument("--e2e-depth", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
