@@ -154,15 +154,48 @@ int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64_t in_bytes
  * aligned 32-bit words: the source must be readable up to the next 4-byte boundary after the last
  * stream bit (slot buffers sized with scl_coder_max_encoded_bytes are).  Other sources take the
  * byte-wise kernel. */
+#define SCL_PACK_BYTEWISE 1u /* flags: take the byte-wise kernel even for an aligned source (tests) */
 int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len,
-                    uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream);
+                    uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, uint32_t flags,
+                    void *stream);
 
 /* Same, but each block is written in the reference's on-disk framing
  * (EncodedBlockWriter.write_block, scl/core/encoded_stream.py:150-175):
  *   [u32 BE payload bytes][3-bit pad count][pad zeros][stream]  (Padder :22-46, HeaderHandler :93-103).
  * Block b occupies 4 + ceil((bit_len+3)/8) bytes at d_dst_byte_offset[b]. */
 int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len,
-                     uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream);
+                     uint64_t n_blocks, uint8_t *d_dst, const uint64_t *d_dst_byte_offset, uint32_t flags,
+                     void *stream);
+
+/* Record offsets of the contiguous layout: d_byte_offset[b] = sum over j < b of size(j), d_byte_offset[n_blocks] =
+ * total bytes, with size(j) = ceil(bit_len[j] / 8) (framed == 0) or 4 + ceil((bit_len[j] + 3) / 8) (framed != 0);
+ * the running file position of EncodedBlockWriter (scl/core/encoded_stream.py:150-175), as a device scan.
+ * d_status (may be NULL): a block whose status is not SCL_ST_OK takes no room.  d_bit_offset (may be NULL, [n_blocks]):
+ * the first stream bit of block b inside the packed buffer, i.e. what scl_decode_blocks wants. */
+int scl_packed_offsets(const uint64_t *d_bit_len, const uint32_t *d_status, uint64_t n_blocks, uint32_t framed,
+                       uint64_t *d_byte_offset, uint64_t *d_bit_offset, void *stream);
+
+/* encode_block for n_blocks DataBlocks with the CONTIGUOUS output the reference's writer produces
+ * (b"".join(encode_block(b).tobytes()), or, framed != 0, the records of EncodedBlockWriter.write_block,
+ * scl/core/encoded_stream.py:150-175) -- one call, symbols in, finished stream out.
+ *   d_scratch / scratch_stride  slots as for scl_encode_blocks (out_stride rules apply): a LIFO stream's start is
+ *                               only known when its block is finished, so a block is coded into its slot first
+ *   d_dst / dst_bytes           the packed buffer and its capacity; a record that would end past it is dropped and
+ *                               its block gets SCL_ST_OVERFLOW
+ *   d_byte_offset [n_blocks+1]  record offsets, [n_blocks] = total bytes written
+ *   d_bit_offset  [n_blocks]    first stream bit of block b in d_dst (feed it to scl_decode_blocks)
+ *   d_workspace                 scl_encode_packed_workspace_bytes() bytes of device scratch
+ * Blocks with a non-OK status take no room in d_dst (their d_bit_offset is unspecified).
+ * The second-generation rANS / tANS kernels do all of this in ONE launch: per-warp sums of the 32 record sizes,
+ * a decoupled look-back across CTAs for the exclusive prefix, and the copy of each finished task to its final
+ * offset overlapped with the coding of the next; the other kernel families run encode, scl_packed_offsets and
+ * the copy kernel back to back. */
+uint64_t scl_encode_packed_workspace_bytes(const scl_coder *c, uint64_t n_blocks);
+int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes,
+                             uint32_t block_len, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride,
+                             uint8_t *d_dst, uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset,
+                             uint64_t *d_bit_offset, uint64_t *d_bit_len, uint64_t *d_model, uint32_t *d_status,
+                             void *d_workspace, uint64_t workspace_bytes, void *stream);
 
 /* Byte counts of n_blocks blocks: DataBlock.get_counts (scl/core/data_block.py:37-64) in bulk -- the
  * step before the coders (build a Frequencies table from the data).  d_counts [n_blocks][256]
@@ -175,12 +208,13 @@ int scl_histogram_blocks(const uint8_t *d_sym, uint64_t sym_stride, const uint32
 int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries,
                             void *stream);
 
-/* Test hook: 1 = route the fast paths to the first-generation kernels (per-lane direct global
- * access) instead of the TMA/ring kernels; 2 = second-generation decode with per-lane sector
- * stores instead of TMA tile stores; 3 / 4 = second-generation decode always / never in its
- * pipe-balanced instruction selection (normally chosen by batch size); 0 = default.  Keeps every
- * code path parity-tested. */
-void scl_debug_force_v1(int on);
+/* Test hook, per handle (no process-global state): 1 = route this coder's fast paths to the
+ * first-generation kernels (per-lane direct global access) instead of the TMA/ring kernels; 2 =
+ * second-generation decode with per-lane sector stores instead of TMA tile stores; 3 / 4 =
+ * second-generation decode always / never in its pipe-balanced instruction selection (normally
+ * chosen by batch size); 0 = default.  Keeps every code path parity-tested.  Set it before issuing
+ * work on the handle; it is read at launch time. */
+void scl_coder_debug_path(scl_coder *c, int mode);
 
 const char *scl_last_cuda_error(void);
 const char *scl_version(void);

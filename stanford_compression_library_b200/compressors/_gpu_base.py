@@ -62,6 +62,11 @@ class GpuCoderBase:
         """Encode B independent blocks: data uint8 [B, N] (device or host tensor / ndarray)."""
         return self.device_coder().encode_blocks(data, sizes=sizes, reuse=reuse)
 
+    def encode_blocks_packed(self, data, sizes=None, framed: bool = False, capacity: int = None, reuse: EncodedBlocks = None) -> EncodedBlocks:
+        """encode_blocks with the writer's contiguous output produced by the same launch:
+        `buf[: byte_offset[-1]]` == b"".join(encode_block(b).tobytes()) (or the framed file bytes)."""
+        return self.device_coder().encode_blocks_packed(data, sizes=sizes, framed=framed, capacity=capacity, reuse=reuse)
+
     def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, out=None, reuse: DecodedBlocks = None) -> DecodedBlocks:
         """Decode B independent streams into uint8 [B, >=max_block_len]."""
         return self.device_coder().decode_blocks(enc, max_block_len, out=out, reuse=reuse)
@@ -76,9 +81,14 @@ class GpuCoderBase:
     def _decode_one(self, bitarray: BitArray, model=None):
         dev = self.device_coder()
         enc = EncodedBlocks.from_bitarrays([bitarray], device=dev.device)
-        # the block size is in the stream; a stream of n bits cannot hold more than n symbols'
-        # worth of header-declared data that we are willing to allocate for
+        # The block size comes from the stream's own header, so a corrupt stream could ask for a ~4 GiB
+        # output before any validity check.  Bound it by what a stream of this length can hold
+        # (`_max_symbols_for_bits`: from the cheapest symbol of a static table; adaptive models only get
+        # the flat cap).
         size_cap = self._peek_size(bitarray)
+        limit = self._max_symbols_for_bits(len(bitarray))
+        if size_cap > limit:
+            raise ValueError("block header declares %d symbols, more than a %d-bit stream can hold (corrupt stream?)" % (size_cap, len(bitarray)))
         dec = dev.decode_blocks(enc, size_cap, model=model)
         dec.check()
         n = int(dec.sizes[0])
@@ -94,6 +104,22 @@ class GpuCoderBase:
 
     def _size_bits(self) -> int:
         return int(self.params.DATA_BLOCK_SIZE_BITS)
+
+    def _max_symbols_for_bits(self, nbits: int) -> int:
+        """Upper bound on the symbols a stream of `nbits` bits can decode to.  A symbol of probability p
+        costs about -log2 p bits; with a static table whose most probable symbol has f_max of M that is
+        log2(M / f_max) bits, which can be arbitrarily close to (or exactly) zero -- then there is no
+        bound from the length and only a flat allocation cap applies."""
+        f = self._freqs()
+        fl = [int(x) for x in f.freq_list]
+        total, fmax = sum(fl), max(fl)
+        flat_cap = 1 << 28  # symbols we are willing to allocate for on the say-so of one header
+        if fmax >= total:
+            return flat_cap
+        import math
+
+        per_sym = math.log2(total / fmax)
+        return int(min(flat_cap, 64 + (nbits + 64) / per_sym))
 
 
 def encode_uint8_file(encoder, input_file_path: str, encoded_file_path: str, block_size: int = 10000, blocks_per_batch: int = 65536):

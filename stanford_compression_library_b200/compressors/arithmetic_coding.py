@@ -53,6 +53,15 @@ class _AecCoder(GpuCoderBase):
                                model_order=int(getattr(self.freq_model, "k", 0)) if self.freq_model.CABI_MODEL == _cabi.MODEL_ORDER_K else 0,
                                max_allowed_total_freq=int(self.freq_model.max_allowed_total_freq))
 
+    def _max_symbols_for_bits(self, nbits: int) -> int:
+        # an adaptive model can drive the cost of a repeated symbol towards zero bits: no bound from the
+        # stream length, only the flat allocation cap
+        from .probability_models import FixedFreqModel
+
+        if isinstance(self.freq_model, FixedFreqModel):
+            return super()._max_symbols_for_bits(nbits)
+        return 1 << 28
+
     def _model_tensor(self, n_blocks=1):
         dev = self.device_coder()
         return torch.tensor([self.freq_model._to_table()], dtype=torch.int64, device=dev.device).repeat(n_blocks, 1)
@@ -67,6 +76,10 @@ class _AecCoder(GpuCoderBase):
         if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:
             return super().encode_blocks(data, sizes=sizes, reuse=reuse)
         return self.device_coder().encode_blocks(data, sizes=sizes, model=self._batch_model(int(data.shape[0])), reuse=reuse)
+
+    def encode_blocks_packed(self, data, sizes=None, framed=False, capacity=None, reuse=None):
+        model = self._batch_model(int(data.shape[0])) if self.freq_model.CABI_MODEL == _cabi.MODEL_ORDER_K else None
+        return self.device_coder().encode_blocks_packed(data, sizes=sizes, model=model, framed=framed, capacity=capacity, reuse=reuse)
 
     def decode_blocks(self, enc, max_block_len, out=None, reuse=None):
         if self.freq_model.CABI_MODEL != _cabi.MODEL_ORDER_K:

@@ -22,12 +22,19 @@ class DataBlock:
         return d.tolist() if hasattr(d, "tolist") else list(d)
 
     def get_alphabet(self):
-        return set(self._as_python_list())
+        alphabet = set()
+        for d in self._as_python_list():  # grown element by element like data_block.py:30-35
+            alphabet.add(d)
+        return alphabet
 
     def get_counts(self, order=0):
+        """{symbol: count}.  Keys come out in the reference's order -- the iteration order of the alphabet
+        SET (data_block.py:57-64), not first occurrence: key order defines the cumulative table of a
+        `Frequencies` built from these counts, hence the bitstream."""
         if order != 0:
             raise NotImplementedError("[order != 0] counts not implemented")
-        return dict(Counter(self._as_python_list()))
+        counts = Counter(self._as_python_list())
+        return {a: counts[a] for a in self.get_alphabet()}
 
     def get_empirical_distribution(self, order=0) -> ProbabilityDist:
         if order != 0:

@@ -18,6 +18,7 @@
 #include "scl_aec.cuh"
 #include "scl_fast.cuh"
 #include "scl_lane.cuh"
+#include "scl_pack.cuh"
 #include "scl_range.cuh"
 #include "scl_tables.hpp"
 
@@ -170,8 +171,9 @@ __global__ void __launch_bounds__(kThreads) rans64_decode_kernel(const RansGener
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
     uint64_t used = 0;
-    uint32_t st = rans64_decode_lane(s_tab, c, r, io.sym + b * io.sym_stride, io.sym_stride, size, used);
-    if (st == SCL_ST_OK && used > avail_bits_of(io, b, off)) st = SCL_ST_TRUNCATED;
+    const uint64_t avail = avail_bits_of(io, b, off);
+    uint32_t st = rans64_decode_lane(s_tab, c, r, avail, io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
@@ -202,10 +204,71 @@ __device__ __forceinline__ void tma_tile_2d(void *smem_dst, const CUtensorMap *t
 // smem layout: [tiles+rings per warp ...][table 32 KiB][mbarriers]
 // KIND 0 = rANS (arithmetic step), KIND 1 = tANS (table step; g_tab2 = enc_table, staged after the
 // replicated per-symbol table)
-template <int KIND, uint32_t NBO, bool CHECK>
+//
+// PACKED: the kernel also produces the contiguous output (EncodedBlockWriter's job in the reference,
+// encoded_stream.py:150-175).  A LIFO stream's start is only known when its block is finished, and its place in
+// the packed buffer depends on every earlier block's size, so a task still encodes into its scratch slots;
+// then (i) the warp sums its 32 record sizes (__reduce_add_sync), (ii) the last warp of a CTA to finish a round
+// adds up the CTA's tasks -- they are consecutive -- and resolves the cross-CTA exclusive prefix by decoupled
+// look-back over one word per (round, CTA) (scl_pack.cuh), (iii) every warp copies its 32 streams to their
+// final byte offsets (pack_block_warp).  Step (iii) of a task is DEFERRED until the warp has encoded its next
+// task: by then the prefix is long resolved, so no warp ever waits on a neighbour, and the copy (pure memory
+// traffic) runs under the other warps' arithmetic.  Depends on the in-order dispatch of CTAs (a CTA only waits
+// for lower-numbered CTAs of the same round, or for earlier rounds), like every single-pass scan.
+struct PackedOut {
+    uint8_t *dst;            // packed destination
+    uint64_t dst_bytes;      // its capacity
+    uint64_t *byte_off;      // [n_blocks + 1] record offsets, [n_blocks] = total
+    uint64_t *cta_state;     // [rounds * gridDim.x] look-back words, zeroed before the launch
+    uint32_t framed;
+};
+struct PackCtl {  // per CTA, shared memory; [round & 1]
+    unsigned long long warp_tot[2][kMaxWarps];   // record bytes of each warp's task
+    unsigned long long warp_excl[2][kMaxWarps];  // byte offset of each warp's task in dst
+    uint32_t excl_tag[2][kMaxWarps];             // round + 1 once warp_excl is valid
+    uint32_t arrive[2];
+};
+
+template <bool FRAMED>
+__device__ __forceinline__ void packed_copy_task(const BlockIo &io, const PackedOut &po, uint64_t task, uint64_t base, uint32_t lane) {
+    const uint64_t b = task * 32 + lane;
+    const bool active = b < io.n_blocks;
+    uint64_t bits = 0;
+    uint32_t nb = 0;
+    if (active && io.status[b] == SCL_ST_OK) {
+        bits = io.bit_len[b];
+        nb = (uint32_t)packed_size(bits, FRAMED);
+    }
+    uint32_t incl = nb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += u;
+    }
+    const uint64_t at = base + (incl - nb);
+    if (active) {
+        po.byte_off[b] = at;
+        io.bit_off[b] = 8 * at + packed_lead_bits(bits, FRAMED);
+        if (nb && at + nb > po.dst_bytes) {
+            io.status[b] = SCL_ST_OVERFLOW;
+            nb = 0;
+        }
+    }
+    __syncwarp();  // the slots were written lane by lane; from here on every lane reads every slot
+    for (uint32_t l = 0; l < 32; ++l) {
+        const uint32_t nb_l = __shfl_sync(0xffffffffu, nb, l);
+        if (!nb_l) continue;
+        const uint64_t bits_l = __shfl_sync(0xffffffffu, bits, l), at_l = __shfl_sync(0xffffffffu, at, l);
+        const uint64_t src_off = (task * 32 + l + 1) * io.out_stride * 8 - bits_l;  // the stream ends at its slot's end
+        pack_block_warp<FRAMED, false>(io.out, src_off, bits_l, po.dst + at_l, lane);
+    }
+}
+
+template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
-                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks) {
+                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, PackedOut po) {
+    __shared__ PackCtl ctl;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // round the dynamic window up to 2 KiB so that ring addresses can be composed with OR
     uint8_t *smem = smem_raw + ((2048u - (smem_u32(smem_raw) & 2047u)) & 2047u);
@@ -223,6 +286,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         for (uint32_t i = 0; i < W * kTileStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (PACKED && threadIdx.x < 2 * kMaxWarps) {
+        (&ctl.excl_tag[0][0])[threadIdx.x] = 0;
+        if (threadIdx.x < 2) ctl.arrive[threadIdx.x] = 0;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         tma_expect(tab_bar, kEncTabBytes + tab2_bytes);
@@ -238,7 +305,24 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     uint32_t tile_seq = 0;  // tiles consumed by this warp so far (selects stage and mbarrier parity)
     const uint32_t swz = (lane >> 1) & 3;
 
-    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+    // PACKED: wait for the byte offset of this warp's task of round `r` (published by the CTA's last warp of that
+    // round), then copy the task's streams there
+    auto packed_finish = [&](uint32_t r, uint32_t task) {
+        if (lane == 0) {
+            const volatile uint32_t *tag = &ctl.excl_tag[r & 1][warp];
+            while (*tag != r + 1) __nanosleep(100);
+        }
+        __syncwarp();
+        __threadfence_block();
+        const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][warp];
+        if (po.framed)
+            packed_copy_task<true>(io, po, task, base, lane);
+        else
+            packed_copy_task<false>(io, po, task, base, lane);
+    };
+
+    uint32_t round = 0;
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         if (lane == 0) {
@@ -290,6 +374,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                 tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)((t + kTileStages) * kTileCols), (int32_t)(task * 32), my_bar + st);
             }
         }
+        uint32_t rec_bytes = 0;  // PACKED: bytes of this lane's record in the contiguous output
         if (active) {
             L.put(L.x, c.NSB);  // header in front of the payload (rANS.py:199,206-208)
             uint32_t st = SCL_ST_OK;
@@ -299,11 +384,48 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             if (L.bad) st = SCL_ST_BAD_SYMBOL;
             if (L.ovf) st = SCL_ST_OVERFLOW;
             io.bit_len[b] = bits;
-            io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+            if (!PACKED) io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
             io.status[b] = st;
+            if (PACKED && st == SCL_ST_OK) rec_bytes = (uint32_t)packed_size(bits, po.framed != 0);
         }
         __syncwarp();
+        if (PACKED) {
+            // (i) this task's total; (ii) arrive at the CTA's round; the last warp to arrive resolves the round
+            const uint32_t T = __reduce_add_sync(0xffffffffu, rec_bytes);
+            const uint32_t first = round * total_warps + blockIdx.x * W;  // first task of this CTA's round
+            const uint32_t nvalid = n_tasks - first < W ? n_tasks - first : W;
+            const uint32_t par = round & 1;
+            uint32_t old = 0;
+            if (lane == 0) {
+                *(volatile unsigned long long *)&ctl.warp_tot[par][warp] = T;
+                __threadfence_block();
+                old = atomicAdd(&ctl.arrive[par], 1u);
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == nvalid - 1) {
+                if (lane == 0) ctl.arrive[par] = 0;
+                __threadfence_block();
+                const uint64_t t = lane < nvalid ? *(const volatile unsigned long long *)&ctl.warp_tot[par][lane] : 0ull;
+                const uint64_t incl = warp_incl_scan_u64(t, lane);
+                const uint64_t A = __shfl_sync(0xffffffffu, incl, 31);
+                const int64_t g = (int64_t)round * gridDim.x + blockIdx.x;
+                if (lane == 0) st_relaxed_gpu(po.cta_state + g, (g ? kLbAgg : kLbPrefix) | A);
+                uint64_t excl = 0;
+                if (g) {
+                    excl = lookback_exclusive(po.cta_state, g, lane);
+                    if (lane == 0) st_relaxed_gpu(po.cta_state + g, kLbPrefix | (excl + A));
+                }
+                if (lane == 0 && first + nvalid == n_tasks) po.byte_off[io.n_blocks] = excl + A;  // the very last round: grand total
+                if (lane < nvalid) *(volatile unsigned long long *)&ctl.warp_excl[par][lane] = excl + incl - t;
+                __threadfence_block();
+                __syncwarp();
+                if (lane < nvalid) *(volatile uint32_t *)&ctl.excl_tag[par][lane] = round + 1;
+            }
+            // (iii) deferred by one task: copy the PREVIOUS task's streams to their final place
+            if (round) packed_finish(round - 1, task - total_warps);
+        }
     }
+    if (PACKED && round) packed_finish(round - 1, blockIdx.x * W + warp + (round - 1) * total_warps);
 }
 
 // Decode.  Output goes through a per-warp 32 x 64-byte tile in shared memory (64-byte swizzle, so
@@ -889,139 +1011,62 @@ __global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_decode_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------------
-// stream packing: bit-granular copy of each block's stream to a byte-aligned destination
+// stream packing: bit-granular copy of each block's stream to a byte-aligned destination (scl_pack.cuh)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t src_byte_at_bit(const uint8_t *src, uint64_t pos) {  // 8 bits starting at bit `pos`
-    uint64_t by = pos >> 3;
-    uint32_t sh = (uint32_t)(pos & 7);
-    uint32_t v = ((uint32_t)src[by] << 8);
-    if (sh) v |= src[by + 1];
-    return (v >> (8 - sh)) & 0xFFu;
-}
+// Optional arguments of both kernels: `status` (a failed block takes no room and is not copied), `dst_bytes`
+// (a record that would end past the destination is dropped and its status set to OVERFLOW), `new_bit_off`
+// (where the block's first stream bit now lies in dst; may alias src_bit_off).
+struct PackIo {
+    const uint8_t *src;
+    const uint64_t *src_bit_off;
+    const uint64_t *bit_len;
+    uint64_t n_blocks;
+    uint8_t *dst;
+    uint64_t dst_bytes;  // 0 = unchecked
+    const uint64_t *dst_byte_off;
+    uint32_t *status;
+    uint64_t *new_bit_off;
+};
 
-// one CTA per block; FRAMED adds the reference's block framing (encoded_stream.py:22-46,93-103)
+// first generation: one CTA per block, byte-wise (any source alignment)
 template <bool FRAMED>
-__global__ void __launch_bounds__(kThreads) pack_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_bit_off,
-                                                         const uint64_t *__restrict__ bit_len, uint8_t *__restrict__ dst,
-                                                         const uint64_t *__restrict__ dst_byte_off) {
+__global__ void __launch_bounds__(kThreads) pack_kernel(PackIo io) {
     const uint64_t b = blockIdx.x;
-    const uint64_t off = src_bit_off[b], nbits = bit_len[b];
-    uint8_t *d = dst + dst_byte_off[b];
-    if (!FRAMED) {
-        const uint64_t nbytes = (nbits + 7) >> 3;
-        for (uint64_t i = threadIdx.x; i < nbytes; i += kThreads) {
-            uint64_t rem = nbits - 8 * i;  // bits of the stream left at byte i (>= 1)
-            uint32_t v;
-            if (rem >= 8) {
-                v = src_byte_at_bit(src, off + 8 * i);
-            } else {  // last partial byte: take only `rem` bits, zero-pad on the right (tobytes())
-                v = 0;
-                for (uint32_t k = 0; k < (uint32_t)rem; ++k) {
-                    uint64_t p = off + 8 * i + k;
-                    v |= ((src[p >> 3] >> (7 - (p & 7))) & 1u) << (7 - k);
-                }
-            }
-            d[i] = (uint8_t)v;
-        }
-    } else {
-        // padded payload = [num_pad : 3][0 * num_pad][stream]; its length is a whole number of bytes
-        const uint32_t num_pad = (uint32_t)((8 - (nbits + 3) % 8) % 8);
-        const uint64_t lead = 3 + num_pad;
-        const uint64_t payload_bytes = (nbits + lead) >> 3;
+    if (io.status && io.status[b] != SCL_ST_OK) return;
+    const uint64_t off = io.src_bit_off[b], nbits = io.bit_len[b], at = io.dst_byte_off[b];
+    __syncthreads();  // everybody has read src_bit_off[b] before it may be overwritten below
+    if (io.dst_bytes && at + packed_size(nbits, FRAMED) > io.dst_bytes) {
+        if (threadIdx.x == 0 && io.status) io.status[b] = SCL_ST_OVERFLOW;
+        return;
+    }
+    if (threadIdx.x == 0 && io.new_bit_off) io.new_bit_off[b] = 8 * at + packed_lead_bits(nbits, FRAMED);
+    uint8_t *d = io.dst + at;
+    const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
+    const uint64_t lead = FRAMED ? 3 + num_pad : 0;
+    const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
+    if (FRAMED) {
         if (threadIdx.x < 4) d[threadIdx.x] = (uint8_t)(payload_bytes >> (8 * (3 - threadIdx.x)));  // u32 big-endian
-        for (uint64_t i = threadIdx.x; i < payload_bytes; i += kThreads) {
-            uint32_t v = 0;
-            if (8 * i >= lead) {
-                v = src_byte_at_bit(src, off + 8 * i - lead);
-            } else {
-                for (uint32_t k = 0; k < 8; ++k) {
-                    uint64_t q = 8 * i + k;
-                    uint32_t bit;
-                    if (q < 3)
-                        bit = (num_pad >> (2 - q)) & 1u;
-                    else if (q < lead)
-                        bit = 0;
-                    else {
-                        uint64_t p = off + (q - lead);
-                        bit = (src[p >> 3] >> (7 - (p & 7))) & 1u;
-                    }
-                    v |= bit << (7 - k);
-                }
-            }
-            d[4 + i] = (uint8_t)v;
-        }
+        d += 4;
     }
+    for (uint64_t i = threadIdx.x; i < payload_bytes; i += kThreads) d[i] = (uint8_t)pack_payload_byte<FRAMED, true>(io.src, off, nbits, num_pad, lead, i);
 }
 
-// Second generation: one warp per block, 16 output bytes per lane and step.  Byte i of a block's packed
-// payload is bits [8i - lead, 8i - lead + 8) of its stream (lead = 0, or the framing's 3 + num_pad bits);
-// once the destination is 16-byte aligned and all 128 bits are real stream bits, a chunk is five aligned
-// 32-bit source words, four funnel shifts and one 128-bit store (a warp reads ~528 and writes 512
-// contiguous bytes per step).  The few bytes before / after go through the bitwise path above.
-// Needs a 4-byte aligned `src` that is readable up to the next 4-byte boundary after the last stream bit.
-template <bool FRAMED>
-__device__ __forceinline__ uint32_t pack_payload_byte(const uint8_t *src, uint64_t off, uint64_t nbits, uint32_t num_pad, uint64_t lead,
-                                                       uint64_t i) {
-    uint32_t v = 0;
-    if (8 * i >= lead && 8 * i - lead + 8 <= nbits) return src_byte_at_bit(src, off + 8 * i - lead);
-    for (uint32_t k = 0; k < 8; ++k) {
-        const uint64_t q = 8 * i + k;
-        uint32_t bit = 0;
-        if (FRAMED && q < 3) {
-            bit = (num_pad >> (2 - q)) & 1u;
-        } else if (q >= lead && q - lead < nbits) {
-            const uint64_t p = off + (q - lead);
-            bit = (src[p >> 3] >> (7 - (p & 7))) & 1u;
-        }
-        v |= bit << (7 - k);
-    }
-    return v;
-}
-
+// second generation: one warp per block, 16 output bytes per lane and step (pack_block_warp)
 constexpr int kPackWarps = 8;
 template <bool FRAMED>
-__global__ void __launch_bounds__(kPackWarps * 32) pack_v2_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_bit_off,
-                                                                  const uint64_t *__restrict__ bit_len, uint8_t *__restrict__ dst,
-                                                                  const uint64_t *__restrict__ dst_byte_off, uint64_t n_blocks) {
+__global__ void __launch_bounds__(kPackWarps * 32) pack_v2_kernel(PackIo io) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warp0 = (uint64_t)blockIdx.x * kPackWarps + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * kPackWarps;
-    const uint32_t *src32 = (const uint32_t *)src;
-    for (uint64_t b = warp0; b < n_blocks; b += n_warps) {
-        const uint64_t off = src_bit_off[b], nbits = bit_len[b];
-        uint8_t *d = dst + dst_byte_off[b];
-        const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
-        const uint64_t lead = FRAMED ? 3 + num_pad : 0;
-        const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
-        if (FRAMED) {
-            if (lane < 4) d[lane] = (uint8_t)(payload_bytes >> (8 * (3 - lane)));  // u32 big-endian (HeaderHandler)
-            d += 4;
+    for (uint64_t b = warp0; b < io.n_blocks; b += n_warps) {
+        if (io.status && io.status[b] != SCL_ST_OK) continue;
+        const uint64_t off = io.src_bit_off[b], nbits = io.bit_len[b], at = io.dst_byte_off[b];
+        __syncwarp();
+        if (io.dst_bytes && at + packed_size(nbits, FRAMED) > io.dst_bytes) {
+            if (lane == 0 && io.status) io.status[b] = SCL_ST_OVERFLOW;
+            continue;
         }
-        // head: up to the first 16-byte aligned destination byte whose bits are all stream bits
-        uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
-        if (FRAMED)
-            while (8 * head < lead) head += 16;
-        if (head > payload_bytes) head = payload_bytes;
-        // full chunks: 8 * (i0 + 16) - lead <= nbits
-        const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
-        for (uint64_t i = lane; i < head; i += 32) d[i] = (uint8_t)pack_payload_byte<FRAMED>(src, off, nbits, num_pad, lead, i);
-        for (uint64_t ch = lane; ch < n_chunks; ch += 32) {
-            const uint64_t i0 = head + 16 * ch;
-            const uint64_t S = off + 8 * i0 - lead;  // absolute source bit of the chunk's first bit
-            const uint32_t *w = src32 + (S >> 5);
-            const uint32_t sh = (uint32_t)(S & 31);
-            uint32_t W[5];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) W[j] = bswap32(__ldg(w + j));
-            W[4] = sh ? bswap32(__ldg(w + 4)) : 0u;  // not needed (and possibly past the stream) when the chunk is word aligned
-            uint4 o;
-            o.x = bswap32(funnel_l(W[1], W[0], sh));
-            o.y = bswap32(funnel_l(W[2], W[1], sh));
-            o.z = bswap32(funnel_l(W[3], W[2], sh));
-            o.w = bswap32(funnel_l(W[4], W[3], sh));
-            *(uint4 *)(d + i0) = o;
-        }
-        for (uint64_t i = head + 16 * n_chunks + lane; i < payload_bytes; i += 32)
-            d[i] = (uint8_t)pack_payload_byte<FRAMED>(src, off, nbits, num_pad, lead, i);
+        if (lane == 0 && io.new_bit_off) io.new_bit_off[b] = 8 * at + packed_lead_bits(nbits, FRAMED);
+        pack_block_warp<FRAMED, true>(io.src, off, nbits, io.dst + at, lane);
     }
 }
 
@@ -1114,6 +1159,9 @@ struct scl_coder {
     uint32_t *d_range_dec_lut = nullptr;  // RangeHost::dec_lut
     uint32_t range_dec_lut_bytes = 0;
     AecTab *d_aec = nullptr;
+    // test hook (scl_coder_debug_path): 1 = first-generation kernels, 2 = v2 decode with per-lane sector stores,
+    // 3 / 4 = v2 decode always / never in the pipe-balanced form.  Per handle: no process-global state.
+    int debug_mode = 0;
 };
 
 static thread_local char g_cuda_err[256] = "";
@@ -1215,7 +1263,11 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         for (uint32_t sy = 0; sy < 256; ++sy)
             for (uint32_t j = 0; j < kEncTabCopies; ++j) trep[sy * kEncTabCopies + j] = t.sym_tab[sy];
         if (!rc) rc = upload(&c->d_tsymx8, trep.data(), trep.size() * sizeof(TansSym), trep.size() * sizeof(TansSym), s);
-        if (rc) break;
+        if (rc) {
+            cudaStreamSynchronize(s);  // the uploads issued so far read host vectors that die with this scope
+            cudaFree(d_rows);
+            break;
+        }
         {
             int dev = 0;
             cudaGetDevice(&dev);
@@ -1351,14 +1403,10 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
     *grid = (uint32_t)n_sm;
 }
 
-static bool g_no_tile_store = false;  // test hook (scl_debug_force_v1(2)): v2 decode with per-lane sector stores
-static bool g_force_v1 = false;  // test hook: scl_debug_force_v1(1) routes the fast path to the first-generation kernels
-static int g_force_bal = 0;      // test hook: scl_debug_force_v1(3) / (4) = v2 decode always / never in the pipe-balanced form
-extern "C" void scl_debug_force_v1(int on) {
-    g_force_v1 = on == 1;
-    g_no_tile_store = on == 2;
-    g_force_bal = on == 3 ? 1 : on == 4 ? -1 : 0;
+extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
+    if (c) c->debug_mode = mode;
 }
+static inline bool force_v1(const scl_coder *c) { return c->debug_mode == 1; }
 
 static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
     size_t avail = 227 * 1024 - 1024 - fixed;  // 227 KiB per CTA minus slack for static smem / barriers
@@ -1366,9 +1414,12 @@ static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
     return w > kMaxWarps ? kMaxWarps : w;
 }
 
+// look-back words a packed launch may need: one per (round, CTA); rounds * grid <= tasks + grid
+static uint64_t packed_state_words(uint64_t n_blocks) { return (n_blocks + 31) / 32 + 4096; }
+
 template <int KIND, uint32_t NBO>
 static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void *tab8, const uint32_t *tab2, uint32_t tab2_bytes,
-                            const BlockIo &io, cudaStream_t s) {
+                            const BlockIo &io, const PackedOut *packed, cudaStream_t s) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return -1;
     CUtensorMap tmap;
@@ -1380,19 +1431,35 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return -1;
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048;
+    size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048 + (packed ? 2048 : 0);  // PACKED: the static PackCtl block
     pick_launch(n_tasks, c->n_sm, max_warps_for(kEncWarpSmem, fixed), &grid, &warps);
     size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t) + 2048;
-    cudaError_t e;
-    if (rc.check_sym) {
-        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        fast_encode_v2_kernel<KIND, NBO, true><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks);
-    } else {
-        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        fast_encode_v2_kernel<KIND, NBO, false><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks);
+    PackedOut po{};
+    if (packed) {
+        po = *packed;
+        const uint64_t rounds = (n_tasks + (uint64_t)grid * warps - 1) / ((uint64_t)grid * warps);
+        cudaError_t e = cudaMemsetAsync(po.cta_state, 0, rounds * grid * sizeof(uint64_t), s);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
+    cudaError_t e;
+#define SCL_LAUNCH_ENC(CHK, PK)                                                                                                    \
+    do {                                                                                                                           \
+        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, po);    \
+    } while (0)
+    if (rc.check_sym) {
+        if (packed)
+            SCL_LAUNCH_ENC(true, true);
+        else
+            SCL_LAUNCH_ENC(true, false);
+    } else {
+        if (packed)
+            SCL_LAUNCH_ENC(false, true);
+        else
+            SCL_LAUNCH_ENC(false, false);
+    }
+#undef SCL_LAUNCH_ENC
     return check_launch("fast_encode_v2_kernel");
 }
 
@@ -1407,7 +1474,7 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     memset(&omap, 0, sizeof(omap));
     uint32_t use_tiles = 0;
     PFN_tmapEncodeTiled enc = tmap_encoder();
-    if (enc && io.sym_stride >= kTileCols && !g_no_tile_store) {
+    if (enc && io.sym_stride >= kTileCols && c->debug_mode != 2) {
         cuuint64_t gdim[2] = {io.sym_stride, io.n_blocks};
         cuuint64_t gstr[1] = {io.sym_stride};
         cuuint32_t box[2] = {kTileCols, 32};
@@ -1417,7 +1484,7 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     }
     // pipe-balanced instruction selection pays when the SMs are full (>= 2 rounds of warps); small batches are
     // latency-bound and keep the shorter dependency chain
-    const bool bal = g_force_bal ? g_force_bal > 0 : n_tasks >= 24u * c->n_sm;
+    const bool bal = c->debug_mode == 3 ? true : c->debug_mode == 4 ? false : n_tasks >= 24u * c->n_sm;
     auto kern = bal ? fast_decode_v2_kernel<KIND, NBO, true> : fast_decode_v2_kernel<KIND, NBO, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
@@ -1453,9 +1520,13 @@ static int launch_range_encode_v2(const scl_coder *c, const BlockIo &io, cudaStr
     return check_launch("range_encode_v2_kernel");
 }
 
-extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
-                                 uint64_t n_blocks, uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_bit_offset,
-                                 uint64_t *d_out_bit_len, uint64_t *d_model, uint32_t *d_status, void *stream) {
+// `packed` non-NULL: the caller wants the contiguous output; *fused is set when the launched kernel produced it
+// itself (second-generation rANS / tANS), otherwise the streams are in their slots as usual
+static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
+                              uint64_t n_blocks, uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_bit_offset,
+                              uint64_t *d_out_bit_len, uint64_t *d_model, uint32_t *d_status, const PackedOut *packed, bool *fused,
+                              void *stream) {
+    if (fused) *fused = false;
     if (!c || !d_out || !d_out_bit_offset || !d_out_bit_len || !d_status) return SCL_E_INVALID;
     if (n_blocks == 0) return SCL_E_OK;
     if (!d_sym && (d_sizes || block_len)) return SCL_E_INVALID;
@@ -1466,12 +1537,15 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     if (c->rans) {
         const RansHost &r = *c->rans;
         // second-generation kernel: uniform block length, TMA-compatible input, sector-aligned output
-        if (r.enc32 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 &&
+        if (r.enc32 && c->v2_ok && !force_v1(c) && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 &&
             (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
             (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
-            int rc2 = r.c.NBO == 1 ? launch_encode_v2<0, 1>(c, r.c, c->d_enc32x8, nullptr, 0, io, s)
-                                   : launch_encode_v2<0, 8>(c, r.c, c->d_enc32x8, nullptr, 0, io, s);
-            if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
+            int rc2 = r.c.NBO == 1 ? launch_encode_v2<0, 1>(c, r.c, c->d_enc32x8, nullptr, 0, io, packed, s)
+                                   : launch_encode_v2<0, 8>(c, r.c, c->d_enc32x8, nullptr, 0, io, packed, s);
+            if (rc2 >= 0) {  // < 0: tensor map could not be built -> first-generation kernel
+                if (fused) *fused = packed != nullptr;
+                return rc2;
+            }
         }
         if (r.enc32) {
             if (r.c.check_sym)
@@ -1485,11 +1559,14 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     }
     if (c->tans) {
         const TansHost &t = *c->tans;
-        if (c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
+        if (c->v2_ok && !force_v1(c) && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
             (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
             (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
-            int rc2 = launch_encode_v2<1, 1>(c, t.r.c, c->d_tsymx8, c->d_tenc, c->ttab_bytes, io, s);
-            if (rc2 >= 0) return rc2;
+            int rc2 = launch_encode_v2<1, 1>(c, t.r.c, c->d_tsymx8, c->d_tenc, c->ttab_bytes, io, packed, s);
+            if (rc2 >= 0) {
+                if (fused) *fused = packed != nullptr;
+                return rc2;
+            }
         }
         if (c->ttab_bytes <= kTansSmemTableMax) {
             SCL_CUDA(cudaFuncSetAttribute(tans_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTansSmemTableMax));
@@ -1501,7 +1578,7 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     }
     if (c->range) {
         // block_len < 2^24: the lanes count ring words in 32 bits (* 128), and a symbol releases at most 3 bytes
-        if (c->range->v2 && c->v2_ok && !g_force_v1 && !d_sizes && block_len >= kTileCols && block_len < (1u << 24) && (sym_stride % 16) == 0 &&
+        if (c->range->v2 && c->v2_ok && !force_v1(c) && !d_sizes && block_len >= kTileCols && block_len < (1u << 24) && (sym_stride % 16) == 0 &&
             (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36)) {
             int rc2 = launch_range_encode_v2(c, io, s);
             if (rc2 >= 0) return rc2;  // < 0: tensor map could not be built -> first-generation kernel
@@ -1524,7 +1601,7 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
         // second generation: every counter and group total must stay below 65536
-        if (!d_model && 16 * max_init + block_len < 65536 && !g_force_v1) {
+        if (!d_model && 16 * max_init + block_len < 65536 && !force_v1(c)) {
             uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
             size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;
             SCL_CUDA(cudaFuncSetAttribute(aec2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1540,6 +1617,60 @@ extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint6
     return SCL_E_INVALID;
 }
 
+extern "C" int scl_encode_blocks(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes, uint32_t block_len,
+                                 uint64_t n_blocks, uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_bit_offset,
+                                 uint64_t *d_out_bit_len, uint64_t *d_model, uint32_t *d_status, void *stream) {
+    return encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_out, out_stride, d_out_bit_offset, d_out_bit_len, d_model,
+                              d_status, nullptr, nullptr, stream);
+}
+
+static int pack_launch(const PackIo &io, bool framed, bool bytewise, cudaStream_t s);
+
+extern "C" int scl_packed_offsets(const uint64_t *d_bit_len, const uint32_t *d_status, uint64_t n_blocks, uint32_t framed,
+                                  uint64_t *d_byte_offset, uint64_t *d_bit_offset, void *stream) {
+    if (!d_bit_len || !d_byte_offset) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_blocks == 0) {
+        SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
+        return SCL_E_OK;
+    }
+    const uint64_t n_tiles = (n_blocks + kScanTile - 1) / kScanTile;
+    if (n_tiles > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    scan_tile_totals_kernel<<<(uint32_t)n_tiles, kScanThreads, 0, s>>>(d_bit_len, d_status, n_blocks, framed, d_byte_offset);
+    scan_tile_offsets_kernel<<<1, kScanThreads, 0, s>>>(n_blocks, n_tiles, d_byte_offset);
+    scan_tile_final_kernel<<<(uint32_t)n_tiles, kScanThreads, 0, s>>>(d_bit_len, d_status, n_blocks, framed, d_byte_offset, d_bit_offset);
+    return check_launch("scan_tile_kernels");
+}
+
+extern "C" uint64_t scl_encode_packed_workspace_bytes(const scl_coder *c, uint64_t n_blocks) {
+    (void)c;
+    return packed_state_words(n_blocks) * sizeof(uint64_t);
+}
+
+extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym, uint64_t sym_stride, const uint32_t *d_sizes,
+                                        uint32_t block_len, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride, uint8_t *d_dst,
+                                        uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset, uint64_t *d_bit_offset,
+                                        uint64_t *d_bit_len, uint64_t *d_model, uint32_t *d_status, void *d_workspace,
+                                        uint64_t workspace_bytes, void *stream) {
+    if (!c || !d_dst || !d_byte_offset || !d_bit_offset || !d_bit_len || !d_status || !d_scratch) return SCL_E_INVALID;
+    if (!d_workspace || workspace_bytes < scl_encode_packed_workspace_bytes(c, n_blocks)) return SCL_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_blocks == 0) {
+        SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
+        return SCL_E_OK;
+    }
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u};
+    bool fused = false;
+    int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
+                                d_status, &po, &fused, stream);
+    if (rc || fused) return rc;
+    // every other kernel family: streams are in their slots -> offsets by scan, then the copy kernel
+    rc = scl_packed_offsets(d_bit_len, d_status, n_blocks, framed, d_byte_offset, nullptr, stream);
+    if (rc) return rc;
+    PackIo pio{d_scratch, d_bit_offset, d_bit_len, n_blocks, d_dst, dst_bytes, d_byte_offset, d_status, d_bit_offset};
+    return pack_launch(pio, framed != 0, false, s);
+}
+
 extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64_t in_bytes, const uint64_t *d_bit_offset,
                                  const uint64_t *d_bit_len, uint64_t n_blocks, uint8_t *d_sym, uint64_t sym_stride, uint32_t *d_sizes,
                                  uint64_t *d_bits_consumed, uint64_t *d_model, uint32_t *d_status, void *stream) {
@@ -1553,7 +1684,7 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     if (c->rans) {
         const RansHost &r = *c->rans;
         // sym_stride * kFastMaxBitsPerSym < 2^31: the lanes keep the stream position in 32 bits (as the encoder's guard on block_len)
-        if (r.dec32 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+        if (r.dec32 && c->v2_ok && !force_v1(c) && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
             n_blocks < (1ull << 36) && sym_stride * kFastMaxBitsPerSym < (1ull << 31))
             return r.c.NBO == 1 ? launch_decode_v2<0, 1>(c, r.c, c->d_dec32, c->dec32_bytes, io, s)
                                 : launch_decode_v2<0, 8>(c, r.c, c->d_dec32, c->dec32_bytes, io, s);
@@ -1565,7 +1696,7 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     }
     if (c->tans) {
         const TansHost &t = *c->tans;
-        if (c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+        if (c->v2_ok && !force_v1(c) && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
             n_blocks < (1ull << 36) && sym_stride * kFastMaxBitsPerSym < (1ull << 31))
             return launch_decode_v2<1, 1>(c, t.r.c, c->d_tdec, c->ttab_bytes, io, s);
         if (c->ttab_bytes <= kTansSmemTableMax) {
@@ -1578,7 +1709,7 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
     }
     if (c->range) {
         // sym_stride < 2^24 bounds the decoded size, hence the 32-bit bit position of DecLaneV2 (<= 24 bits per symbol)
-        if (c->range->v2 && c->v2_ok && !g_force_v1 && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
+        if (c->range->v2 && c->v2_ok && !force_v1(c) && (((uintptr_t)d_in) & 31) == 0 && (sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 &&
             sym_stride < (1ull << 24) && n_blocks < (1ull << 36)) {
             const RangeHost &rh = *c->range;
             uint32_t n_tasks = (uint32_t)((n_blocks + 31) / 32), g2, warps;
@@ -1604,7 +1735,7 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
-        if (!d_model && 16 * max_init + sym_stride < 65536 && !g_force_v1) {  // decoded size <= sym_stride is enforced by the lane
+        if (!d_model && 16 * max_init + sym_stride < 65536 && !force_v1(c)) {  // decoded size <= sym_stride is enforced by the lane
             uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
             size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;
             SCL_CUDA(cudaFuncSetAttribute(aec2_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1629,34 +1760,36 @@ static uint32_t pack_grid(uint64_t n_blocks) {
     return (uint32_t)(want < cap ? want : cap);
 }
 
-extern "C" int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
-                               uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream) {
-    if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
-    if (n_blocks == 0) return SCL_E_OK;
-    if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
-    if (!g_force_v1 && (((uintptr_t)d_src) & 3) == 0) {
-        pack_v2_kernel<false><<<pack_grid(n_blocks), kPackWarps * 32, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
-                                                                                                 d_dst_byte_offset, n_blocks);
+static int pack_launch(const PackIo &io, bool framed, bool bytewise, cudaStream_t s) {
+    if (io.n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
+    if (!bytewise && (((uintptr_t)io.src) & 3) == 0) {
+        if (framed)
+            pack_v2_kernel<true><<<pack_grid(io.n_blocks), kPackWarps * 32, 0, s>>>(io);
+        else
+            pack_v2_kernel<false><<<pack_grid(io.n_blocks), kPackWarps * 32, 0, s>>>(io);
         return check_launch("pack_v2_kernel");
     }
-    pack_kernel<false><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
-                                                                                  d_dst_byte_offset);
+    if (framed)
+        pack_kernel<true><<<(uint32_t)io.n_blocks, kThreads, 0, s>>>(io);
+    else
+        pack_kernel<false><<<(uint32_t)io.n_blocks, kThreads, 0, s>>>(io);
     return check_launch("pack_kernel");
 }
 
-extern "C" int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
-                                uint8_t *d_dst, const uint64_t *d_dst_byte_offset, void *stream) {
+extern "C" int scl_pack_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
+                               uint8_t *d_dst, const uint64_t *d_dst_byte_offset, uint32_t flags, void *stream) {
     if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
     if (n_blocks == 0) return SCL_E_OK;
-    if (n_blocks > 0x7FFFFFFFull) return SCL_E_UNSUPPORTED;
-    if (!g_force_v1 && (((uintptr_t)d_src) & 3) == 0) {
-        pack_v2_kernel<true><<<pack_grid(n_blocks), kPackWarps * 32, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
-                                                                                                d_dst_byte_offset, n_blocks);
-        return check_launch("frame_v2_kernel");
-    }
-    pack_kernel<true><<<(uint32_t)n_blocks, kThreads, 0, (cudaStream_t)stream>>>(d_src, d_src_bit_offset, d_bit_len, d_dst,
-                                                                                 d_dst_byte_offset);
-    return check_launch("frame_kernel");
+    PackIo io{d_src, d_src_bit_offset, d_bit_len, n_blocks, d_dst, 0, d_dst_byte_offset, nullptr, nullptr};
+    return pack_launch(io, false, (flags & SCL_PACK_BYTEWISE) != 0, (cudaStream_t)stream);
+}
+
+extern "C" int scl_frame_blocks(const uint8_t *d_src, const uint64_t *d_src_bit_offset, const uint64_t *d_bit_len, uint64_t n_blocks,
+                                uint8_t *d_dst, const uint64_t *d_dst_byte_offset, uint32_t flags, void *stream) {
+    if (!d_src || !d_src_bit_offset || !d_bit_len || !d_dst || !d_dst_byte_offset) return SCL_E_INVALID;
+    if (n_blocks == 0) return SCL_E_OK;
+    PackIo io{d_src, d_src_bit_offset, d_bit_len, n_blocks, d_dst, 0, d_dst_byte_offset, nullptr, nullptr};
+    return pack_launch(io, true, (flags & SCL_PACK_BYTEWISE) != 0, (cudaStream_t)stream);
 }
 
 extern "C" int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *dec_packed, uint64_t n_entries, void *stream) {

@@ -433,7 +433,11 @@ SCL_HD uint32_t find_bin(const T *cum, uint32_t n, T v) {
     return lo - 1;
 }
 
-SCL_HD uint32_t rans64_decode_lane(const RansGeneric &t, const RansConst &c, BitReader &r, uint8_t *out,
+// `avail_bits` = bits the stream may hold from its first bit on.  The reader returns zero bits past the
+// end of the buffer, so a malformed stream (a zero state never grows under `x = (x << nbo) + bits`) must
+// not be allowed to spin: once the reads have gone past `avail_bits` the reference would have raised
+// ValueError from bitarray_to_uint on an empty slice (rANS.py:256, bitarray_utils.py:38) -> TRUNCATED.
+SCL_HD uint32_t rans64_decode_lane(const RansGeneric &t, const RansConst &c, BitReader &r, uint64_t avail_bits, uint8_t *out,
                                    uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed) {
     uint64_t size64 = r.get64(c.DBSB);
     uint64_t x = r.get64(c.NSB);
@@ -444,7 +448,13 @@ SCL_HD uint32_t rans64_decode_lane(const RansGeneric &t, const RansConst &c, Bit
         uint64_t block_id = x / c.M, slot = x % c.M;  // rans_base_decode_step (rANS.py:234-249)
         uint32_t idx = find_bin<uint64_t>(t.cum, c.n_sym, slot);
         x = block_id * t.freq[idx] + slot - t.cum[idx];
-        while (x < c.L) x = (x << nbo) + r.get(nbo);  // expand_state (rANS.py:251-260)
+        while (x < c.L) {  // expand_state (rANS.py:251-260)
+            x = (x << nbo) + r.get(nbo);
+            if (SCL_UNLIKELY(r.used > avail_bits)) {
+                bits_consumed = r.used;
+                return SCL_ST_TRUNCATED;
+            }
+        }
         out[p - 1] = t.idx2sym[idx];
     }
     size_out = size;

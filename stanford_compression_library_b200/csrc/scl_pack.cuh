@@ -1,0 +1,241 @@
+// scl_pack.cuh -- contiguous ("packed") output: the device side of concatenating the per-block streams the
+// way the reference does on the host (b"".join(encode_block(b).tobytes()), or EncodedBlockWriter.write_block's
+// framed records, scl/core/encoded_stream.py:150-175).
+//
+// A LIFO coder only knows where a block's stream starts once the block is finished, and a block's place in
+// the packed buffer depends on the sizes of every block before it.  Three pieces, device-only:
+//   * pack_block_warp: one warp copies one finished stream, bit-granular source -> byte-aligned destination,
+//     16 bytes per lane and step (five aligned source words, four funnel shifts, one 128-bit store);
+//   * lookback_exclusive: the cross-CTA exclusive prefix of byte counts by decoupled look-back over one
+//     64-bit word (flag : 2 | value : 62) per producer -- the `north_star`'s ballot / prefix-sum compaction at
+//     the one place a lane-per-block layout has for it;
+//   * the three small scan kernels behind scl_packed_offsets (callers that already hold bit lengths).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "scl_lane.cuh"
+
+namespace scl {
+
+// bytes block b occupies in the packed / framed layout
+SCL_HD uint64_t packed_size(uint64_t nbits, bool framed) { return framed ? 4 + ((nbits + 3 + 7) >> 3) : (nbits + 7) >> 3; }
+// first stream bit inside the block's record: 0 packed; framed = 32 header bits + 3-bit pad count + pad zeros
+SCL_HD uint32_t packed_lead_bits(uint64_t nbits, bool framed) { return framed ? 32u + 3u + (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u; }
+
+// ---- global-memory access flavours ---------------------------------------------------------------------
+// NC = the source was written by an EARLIER kernel (read-only path); otherwise plain loads, which see this
+// kernel's own stores once the writer and the reader have met at a barrier.
+template <bool NC>
+__device__ __forceinline__ uint32_t pk_ld32(const uint32_t *p) {
+    return NC ? __ldg(p) : *p;
+}
+template <bool NC>
+__device__ __forceinline__ uint32_t pk_ld8(const uint8_t *p) {
+    return NC ? (uint32_t)__ldg(p) : (uint32_t)*p;
+}
+
+template <bool NC>
+__device__ __forceinline__ uint32_t src_byte_at_bit(const uint8_t *src, uint64_t pos) {  // 8 bits starting at bit `pos`
+    uint64_t by = pos >> 3;
+    uint32_t sh = (uint32_t)(pos & 7);
+    uint32_t v = (pk_ld8<NC>(src + by) << 8);
+    if (sh) v |= pk_ld8<NC>(src + by + 1);
+    return (v >> (8 - sh)) & 0xFFu;
+}
+
+// Byte i of a block's payload is bits [8i - lead, 8i - lead + 8) of its stream (lead = 0, or the framing's
+// 3 + num_pad bits); bytes that straddle the lead or the end of the stream are composed bit by bit.
+template <bool FRAMED, bool NC>
+__device__ __forceinline__ uint32_t pack_payload_byte(const uint8_t *src, uint64_t off, uint64_t nbits, uint32_t num_pad, uint64_t lead,
+                                                       uint64_t i) {
+    uint32_t v = 0;
+    if (8 * i >= lead && 8 * i - lead + 8 <= nbits) return src_byte_at_bit<NC>(src, off + 8 * i - lead);
+    for (uint32_t k = 0; k < 8; ++k) {
+        const uint64_t q = 8 * i + k;
+        uint32_t bit = 0;
+        if (FRAMED && q < 3) {
+            bit = (num_pad >> (2 - q)) & 1u;
+        } else if (q >= lead && q - lead < nbits) {
+            const uint64_t p = off + (q - lead);
+            bit = (pk_ld8<NC>(src + (p >> 3)) >> (7 - (p & 7))) & 1u;
+        }
+        v |= bit << (7 - k);
+    }
+    return v;
+}
+
+// One warp, one block: stream bits [off, off + nbits) of `src` -> record at `d` (packed: the stream, left-aligned,
+// zero-padded to a byte == BitArray.tobytes(); FRAMED: [u32 BE payload bytes][3-bit pad count][pad zeros][stream],
+// encoded_stream.py:22-46,93-103).  Once the destination is 16-byte aligned and all 128 bits are stream bits a
+// chunk is five aligned 32-bit source words, four funnel shifts and one 128-bit store.  `src` must be 4-byte
+// aligned and readable up to the next 4-byte boundary after the last stream bit.
+template <bool FRAMED, bool NC>
+__device__ __forceinline__ void pack_block_warp(const uint8_t *__restrict__ src, uint64_t off, uint64_t nbits, uint8_t *__restrict__ d,
+                                                uint32_t lane) {
+    const uint32_t *src32 = (const uint32_t *)src;
+    const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
+    const uint64_t lead = FRAMED ? 3 + num_pad : 0;
+    const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
+    if (FRAMED) {
+        if (lane < 4) d[lane] = (uint8_t)(payload_bytes >> (8 * (3 - lane)));  // u32 big-endian (HeaderHandler)
+        d += 4;
+    }
+    // head: up to the first 16-byte aligned destination byte whose bits are all stream bits
+    uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (FRAMED && 8 * head < lead) head += 16;  // lead <= 10 bits
+    if (head > payload_bytes) head = payload_bytes;
+    // full chunks: 8 * (i0 + 16) - lead <= nbits
+    const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
+    for (uint64_t i = lane; i < head; i += 32) d[i] = (uint8_t)pack_payload_byte<FRAMED, NC>(src, off, nbits, num_pad, lead, i);
+    for (uint64_t ch = lane; ch < n_chunks; ch += 32) {
+        const uint64_t i0 = head + 16 * ch;
+        const uint64_t S = off + 8 * i0 - lead;  // absolute source bit of the chunk's first bit
+        const uint32_t *w = src32 + (S >> 5);
+        const uint32_t sh = (uint32_t)(S & 31);
+        uint32_t W[5];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) W[j] = bswap32(pk_ld32<NC>(w + j));
+        W[4] = sh ? bswap32(pk_ld32<NC>(w + 4)) : 0u;  // not needed (and possibly past the stream) when the chunk is word aligned
+        uint4 o;
+        o.x = bswap32(funnel_l(W[1], W[0], sh));
+        o.y = bswap32(funnel_l(W[2], W[1], sh));
+        o.z = bswap32(funnel_l(W[3], W[2], sh));
+        o.w = bswap32(funnel_l(W[4], W[3], sh));
+        *(uint4 *)(d + i0) = o;
+    }
+    for (uint64_t i = head + 16 * n_chunks + lane; i < payload_bytes; i += 32)
+        d[i] = (uint8_t)pack_payload_byte<FRAMED, NC>(src, off, nbits, num_pad, lead, i);
+}
+
+// ---- decoupled look-back ----------------------------------------------------------------------------------
+// state[i] = flag << 62 | value: flag 0 = not there yet, 1 = the producer's own total, 2 = inclusive prefix up to
+// and including producer i.  One 64-bit word carries flag and value together, so relaxed accesses suffice.
+constexpr uint64_t kLbAgg = 1ull << 62, kLbPrefix = 2ull << 62, kLbMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_relaxed_gpu(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint64_t *p, uint64_t v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_incl_scan_u64(uint64_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (uint32_t)o) v += u;
+    }
+    return v;
+}
+
+// Sum of the values of producers 0 .. g-1; the whole (converged) warp calls it.  Each step inspects 32
+// predecessors: it stops at the nearest published prefix, otherwise adds 32 totals and moves on.  Spins
+// (with back-off) only while a predecessor has published nothing at all.
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t *state, int64_t g, uint32_t lane) {
+    uint64_t excl = 0;
+    int64_t idx = g - 1 - (int64_t)lane;
+    while (true) {
+        uint64_t v;
+        uint32_t spins = 0;
+        while (true) {
+            v = idx >= 0 ? ld_relaxed_gpu(state + idx) : kLbPrefix;  // before producer 0: the empty prefix
+            if (!__any_sync(0xffffffffu, (v >> 62) == 0)) break;
+            __nanosleep(spins < 8 ? 40 : 400);
+            ++spins;
+        }
+        const uint32_t pm = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const uint64_t val = v & kLbMask;
+        if (pm) {
+            const uint32_t first = (uint32_t)__ffs((int)pm) - 1;
+            return excl + warp_sum_u64(lane <= first ? val : 0);
+        }
+        excl += warp_sum_u64(val);
+        idx -= 32;
+    }
+}
+
+// ---- scl_packed_offsets: exclusive scan of packed sizes in three small launches ------------------------------
+// (1) every CTA leaves the total of its kScanTile items in out[first item of the tile] (scratch use of the
+// output array), (2) one CTA turns those totals into exclusive tile offsets and writes the grand total to
+// out[n], (3) every CTA scans its tile from its offset.  No workspace, no atomics.
+constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t scan_item(const uint64_t *bit_len, const uint32_t *status, uint64_t i, uint64_t n, bool framed) {
+    if (i >= n) return 0;
+    if (status && status[i] != SCL_ST_OK) return 0;  // a failed block takes no room
+    return packed_size(bit_len[i], framed);
+}
+
+__device__ __forceinline__ uint64_t block_excl_scan_u64(uint64_t v, uint64_t *total) {  // kScanThreads threads
+    __shared__ uint64_t s_warp[kScanThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t incl = warp_incl_scan_u64(v, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < kScanThreads / 32; ++w) {
+        const uint64_t t = s_warp[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_totals_kernel(const uint64_t *__restrict__ bit_len, const uint32_t *__restrict__ status,
+                                                                         uint64_t n, uint32_t framed, uint64_t *__restrict__ out) {
+    const uint64_t first = (uint64_t)blockIdx.x * kScanTile;
+    uint64_t v = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) v += scan_item(bit_len, status, first + (uint64_t)threadIdx.x * kScanItems + j, n, framed != 0);
+    uint64_t tot;
+    block_excl_scan_u64(v, &tot);
+    if (threadIdx.x == 0) out[first] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(uint64_t n, uint64_t n_tiles, uint64_t *__restrict__ out) {
+    uint64_t carry = 0;
+    for (uint64_t t0 = 0; t0 < n_tiles; t0 += kScanThreads) {
+        const uint64_t t = t0 + threadIdx.x;
+        const uint64_t v = t < n_tiles ? out[t * kScanTile] : 0;
+        uint64_t tot;
+        const uint64_t ex = block_excl_scan_u64(v, &tot);
+        if (t < n_tiles) out[t * kScanTile] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_final_kernel(const uint64_t *__restrict__ bit_len, const uint32_t *__restrict__ status,
+                                                                        uint64_t n, uint32_t framed, uint64_t *__restrict__ out_bytes,
+                                                                        uint64_t *__restrict__ out_bits) {
+    const uint64_t first = (uint64_t)blockIdx.x * kScanTile;
+    const uint64_t base = out_bytes[first];  // read by every thread before anybody overwrites it
+    __syncthreads();
+    uint64_t item[kScanItems], v = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        item[j] = scan_item(bit_len, status, first + (uint64_t)threadIdx.x * kScanItems + j, n, framed != 0);
+        v += item[j];
+    }
+    uint64_t tot;
+    uint64_t pos = base + block_excl_scan_u64(v, &tot);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        const uint64_t i = first + (uint64_t)threadIdx.x * kScanItems + j;
+        if (i < n) {
+            out_bytes[i] = pos;
+            if (out_bits) out_bits[i] = 8 * pos + packed_lead_bits(bit_len[i], framed != 0);
+            pos += item[j];
+        }
+    }
+}
+
+}  // namespace scl

@@ -52,6 +52,8 @@ class EncodedBlocks:
     """Output of `encode_blocks`: per-block bit streams inside one device byte buffer.
 
     Block b is bits [bit_offset[b], bit_offset[b] + bit_len[b]) of `buf` (MSB-first).
+    `byte_offset` (int64 [B + 1], packed / framed layouts only): where block b's record starts in `buf`;
+    the last entry is the total number of bytes.
     """
 
     buf: torch.Tensor  # uint8 [n_bytes], device
@@ -59,6 +61,9 @@ class EncodedBlocks:
     bit_len: torch.Tensor  # int64 [B]
     status: torch.Tensor  # int32 [B]
     out_stride: int = 0
+    byte_offset: torch.Tensor = None
+    framed: bool = False
+    _scratch: object = None  # buffers a reusing call writes again (encode_blocks_packed)
 
     @property
     def n_blocks(self):
@@ -71,6 +76,8 @@ class EncodedBlocks:
 
     def total_bytes(self) -> int:
         """Sum over blocks of ceil(bit_len / 8): the `C` of the roofline accounting."""
+        if self.byte_offset is not None and not self.framed:
+            return int(self.byte_offset[-1])
         return int(((self.bit_len + 7) // 8).sum())
 
     def block(self, b: int) -> BitArray:
@@ -79,34 +86,44 @@ class EncodedBlocks:
         host = self.buf[first:last].cpu().numpy()
         return BitArray.from_packed(host, n, off - 8 * first)
 
-    def packed_offsets(self):
-        nbytes = (self.bit_len + 7) // 8
-        return torch.cumsum(nbytes, 0) - nbytes, int(nbytes.sum())
+    def packed_offsets(self, framed: bool = False):
+        """(byte offsets int64 [B + 1], bit offsets int64 [B]) of the packed / framed layout: a device scan
+        (scl_packed_offsets), no host round trip."""
+        B = self.n_blocks
+        dev = self.buf.device
+        byte_off = torch.empty(B + 1, dtype=torch.int64, device=dev)
+        bit_off = torch.empty(B, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().scl_packed_offsets(_ptr(self.bit_len), None, B, 1 if framed else 0, _ptr(byte_off), _ptr(bit_off), _stream())
+        _cabi.check(rc, "scl_packed_offsets")
+        return byte_off, bit_off
 
-    def pack(self) -> "EncodedBlocks":
-        """Contiguous, byte-aligned, left-aligned streams == concatenated BitArray.tobytes()."""
-        offs, total = self.packed_offsets()
+    def _repack(self, framed: bool, bytewise: bool):
+        byte_off, bit_off = self.packed_offsets(framed)
+        total = int(byte_off[-1])
         dst = torch.empty(total + 16, dtype=torch.uint8, device=self.buf.device)  # the kernel writes every byte below `total`
         dst[total:].zero_()
+        fn = _cabi.lib().scl_frame_blocks if framed else _cabi.lib().scl_pack_blocks
         with torch.cuda.device(self.buf.device):
-            rc = _cabi.lib().scl_pack_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
-        _cabi.check(rc, "scl_pack_blocks")
-        return EncodedBlocks(dst, offs * 8, self.bit_len, self.status, 0)
+            rc = fn(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(byte_off), 1 if bytewise else 0, _stream())
+        _cabi.check(rc, "scl_frame_blocks" if framed else "scl_pack_blocks")
+        return dst, byte_off, bit_off, total
 
-    def frame(self):
+    def pack(self, bytewise: bool = False) -> "EncodedBlocks":
+        """Contiguous, byte-aligned, left-aligned streams == concatenated BitArray.tobytes().
+        (`encode_blocks_packed` produces this form directly, in the encode launch itself.)
+        bytewise=True takes the first-generation copy kernel (tests)."""
+        dst, byte_off, bit_off, _ = self._repack(False, bytewise)
+        return EncodedBlocks(dst, bit_off, self.bit_len, self.status, 0, byte_off, False)
+
+    def frame(self, bytewise: bool = False):
         """Bytes of the reference's EncodedBlockWriter file format (encoded_stream.py:150-175).
 
         Returns (uint8 device tensor, int64 byte offsets [B+1])."""
-        nbytes = 4 + (self.bit_len + 3 + 7) // 8
-        ends = torch.cumsum(nbytes, 0)
-        offs = ends - nbytes
-        total = int(ends[-1]) if self.n_blocks else 0
-        dst = torch.empty(total + 16, dtype=torch.uint8, device=self.buf.device)
-        dst[total:].zero_()
-        with torch.cuda.device(self.buf.device):
-            rc = _cabi.lib().scl_frame_blocks(_ptr(self.buf), _ptr(self.bit_offset), _ptr(self.bit_len), self.n_blocks, _ptr(dst), _ptr(offs), _stream())
-        _cabi.check(rc, "scl_frame_blocks")
-        return dst[:total], torch.cat([offs, ends[-1:]]) if self.n_blocks else offs
+        if self.framed:
+            return self.buf[: int(self.byte_offset[-1])], self.byte_offset
+        dst, byte_off, _, total = self._repack(True, bytewise)
+        return dst[:total], byte_off
 
     @classmethod
     def from_bitarrays(cls, blocks, device="cuda"):
@@ -195,16 +212,62 @@ class DeviceCoder:
         _cabi.check(rc, "scl_encode_blocks")
         return reuse if reuse is not None else EncodedBlocks(buf, bit_off, bit_len, status, stride)
 
+    def encode_blocks_packed(self, data, sizes=None, model=None, framed: bool = False, capacity: int = None, reuse: EncodedBlocks = None) -> EncodedBlocks:
+        """encode_blocks + the contiguous output of the reference's writer in ONE call (scl_encode_blocks_packed):
+        `buf` is b"".join(encode_block(b).tobytes()) -- or, framed=True, the bytes of the EncodedBlockWriter file
+        (encoded_stream.py:150-175) -- `byte_offset[B]` its length, `bit_offset` what decode_blocks wants.
+        capacity: bytes to reserve for `buf` (default: the worst case, B * max_encoded_bytes (+ 5 framed));
+        `reuse`: the EncodedBlocks of an earlier call of the same shape (no allocation in the call)."""
+        data = self._to_device(data, torch.uint8)
+        if data.dim() == 1:
+            data = data[None, :]
+        B, N = data.shape
+        if sizes is not None:
+            sizes = self._to_device(sizes, torch.int32)
+        lib = _cabi.lib()
+        if reuse is not None:
+            assert reuse._scratch is not None and reuse.bit_len.numel() == B and reuse.framed == bool(framed)
+            scratch, stride, ws = reuse._scratch
+            dst, byte_off, bit_off, bit_len, status = reuse.buf, reuse.byte_offset, reuse.bit_offset, reuse.bit_len, reuse.status
+        else:
+            stride = self.max_encoded_bytes(N)
+            scratch = torch.empty(B * stride + 16, dtype=torch.uint8, device=self.device)
+            cap = int(capacity) if capacity is not None else B * (stride + (5 if framed else 0))
+            dst = torch.empty(cap + 16, dtype=torch.uint8, device=self.device)
+            ws = torch.empty(max(1, int(lib.scl_encode_packed_workspace_bytes(self._h, B))), dtype=torch.uint8, device=self.device)
+            byte_off = torch.empty(B + 1, dtype=torch.int64, device=self.device)
+            bit_off = torch.empty(B, dtype=torch.int64, device=self.device)
+            bit_len = torch.empty(B, dtype=torch.int64, device=self.device)
+            status = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.scl_encode_blocks_packed(self._h, _ptr(data) if N else _ptr(scratch), data.stride(0) if N else 0, _ptr(sizes), N, B, _ptr(scratch), stride,
+                                              _ptr(dst), dst.numel() - 16, 1 if framed else 0, _ptr(byte_off), _ptr(bit_off), _ptr(bit_len), _ptr(model),
+                                              _ptr(status), _ptr(ws), ws.numel(), _stream())
+        _cabi.check(rc, "scl_encode_blocks_packed")
+        return reuse if reuse is not None else EncodedBlocks(dst, bit_off, bit_len, status, 0, byte_off, bool(framed), (scratch, stride, ws))
+
+    def debug_path(self, mode: int):
+        """Test hook (scl_coder_debug_path): 1 = first-generation kernels, 2 = v2 decode with sector stores,
+        3 / 4 = v2 decode always / never pipe-balanced, 0 = default.  Per handle."""
+        _cabi.lib().scl_coder_debug_path(self._h, int(mode))
+
     def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, model=None, out=None, reuse: DecodedBlocks = None) -> DecodedBlocks:
         B = enc.n_blocks
         if reuse is not None:
             out, sizes, used, status = reuse.symbols, reuse.sizes, reuse.bits_consumed, reuse.status
             stride = out.stride(0)
         else:
-            stride = (int(max_block_len) + 31) // 32 * 32 if out is None else out.stride(0)
-            stride = max(stride, 32)
             if out is None:
+                stride = max((int(max_block_len) + 31) // 32 * 32, 32)
                 out = torch.empty((B, stride), dtype=torch.uint8, device=self.device)
+            else:
+                # a caller-supplied destination is used as it is (the row stride is also the capacity the
+                # decoder checks the header's size against), never silently re-strided
+                if not (isinstance(out, torch.Tensor) and out.dtype == torch.uint8 and out.device == self.device and out.dim() == 2):
+                    raise ValueError("out must be a 2-D uint8 tensor on %s" % self.device)
+                if out.shape[0] < B or not out.is_contiguous() or out.shape[1] < 1:
+                    raise ValueError("out must be contiguous with at least %d rows" % B)
+                stride = out.shape[1]
             sizes = torch.empty(B, dtype=torch.int32, device=self.device)
             used = torch.empty(B, dtype=torch.int64, device=self.device)
             status = torch.empty(B, dtype=torch.int32, device=self.device)

@@ -35,9 +35,12 @@ class HostCodecPipeline:
         self._d_dec = [None] * D
         self._d_packed = [torch.empty(self.chunk * self.stride + 64, dtype=torch.uint8, device=self.dev) for _ in range(D)]
         self._d_lens = [torch.empty(self.chunk, dtype=torch.int64, device=self.dev) for _ in range(D)]
+        self._d_byte_off = [torch.empty(self.chunk + 1, dtype=torch.int64, device=self.dev) for _ in range(D)]
+        self._d_bit_off = [torch.empty(self.chunk, dtype=torch.int64, device=self.dev) for _ in range(D)]
         self._h_len = torch.empty(self.B, dtype=torch.int64, pin_memory=True)
         self._h_status = torch.empty(self.B, dtype=torch.int32, pin_memory=True)
         self._h_sizes = torch.empty(self.B, dtype=torch.int32, pin_memory=True)
+        self._h_chunk_bytes = torch.empty(self.n_chunks, dtype=torch.int64, pin_memory=True)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -74,17 +77,17 @@ class HostCodecPipeline:
         d2h_done = [None] * D   # download of the chunk that last used slot s (it reads d_packed[s])
         pending = None
 
-        def download(slot, lo, hi, ev):
-            # the bit lengths of the chunk are on the host once its kernels are done: only then is the
-            # number of bytes to fetch known
+        def download(slot, k, lo, hi, ev):
+            # the chunk's packed size is on the host once its kernel is done: only then is the number of
+            # bytes to fetch known (one 8-byte word per chunk, written by the encode kernel itself)
             nonlocal total
             ev.synchronize()
-            n = int(((self._h_len[lo:hi] + 7) >> 3).sum())
+            n = int(self._h_chunk_bytes[k])
             with torch.cuda.stream(self.s_d2h):
-                host_packed[total : total + n].copy_(self._d_packed[slot][:n], non_blocking=True)
+                host_packed[total : total + n].copy_(self._d_enc[slot].buf[:n], non_blocking=True)
                 d2h_done[slot] = torch.cuda.Event()
                 d2h_done[slot].record()
-            self.d2h_bytes += n + (hi - lo) * 12
+            self.d2h_bytes += n + (hi - lo) * 12 + 8
             total += n
 
         for k in range(self.n_chunks):
@@ -102,23 +105,20 @@ class HostCodecPipeline:
                 self.s_comp.wait_event(up)
                 if d2h_done[slot] is not None:
                     self.s_comp.wait_event(d2h_done[slot])
+                # one launch: symbols in, this chunk's contiguous stream + offsets + total out
                 old = self._d_enc[slot]
-                e = dc.encode_blocks(d_raw, reuse=old if old is not None and old.n_blocks == nb else None)
+                e = dc.encode_blocks_packed(d_raw, reuse=old if old is not None and old.n_blocks == nb else None)
                 self._d_enc[slot] = e
-                nbytes = (e.bit_len + 7) >> 3
-                offs = torch.cumsum(nbytes, 0) - nbytes
-                rc = lib.scl_pack_blocks(_ptr(e.buf), _ptr(e.bit_offset), _ptr(e.bit_len), nb, _ptr(self._d_packed[slot]), _ptr(offs),
-                                         torch.cuda.current_stream().cuda_stream)
-                _cabi.check(rc, "scl_pack_blocks")
                 self._h_len[lo:hi].copy_(e.bit_len, non_blocking=True)
                 self._h_status[lo:hi].copy_(e.status, non_blocking=True)
+                self._h_chunk_bytes[k : k + 1].copy_(e.byte_offset[nb:], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
                 comp_done[slot] = ev
             self.h2d_bytes += nb * self.N
             if pending is not None:
                 download(*pending)
-            pending = (slot, lo, hi, ev)
+            pending = (slot, k, lo, hi, ev)
         if pending is not None:
             download(*pending)
         self._end()
@@ -127,7 +127,11 @@ class HostCodecPipeline:
     # ------------------------------------------------------------------------------------------
     def decode(self, host_packed: torch.Tensor, host_bit_len: torch.Tensor, host_out: torch.Tensor):
         """Inverse of encode(): host_packed/bit_len as produced above -> host_out pinned uint8 [B, N]."""
-        nbytes_all = (host_bit_len + 7) >> 3
+        from . import _cabi
+        from .device import _ptr
+
+        lib = _cabi.lib()
+        nbytes_all = (host_bit_len + 7) >> 3  # host tensors: where each chunk's bytes lie in host_packed
         ends = torch.cumsum(nbytes_all, 0)
         bounds = [0] + [int(ends[min(self.B, (k + 1) * self.chunk) - 1]) for k in range(self.n_chunks)]
         dc = self.dec.device_coder()
@@ -153,8 +157,9 @@ class HostCodecPipeline:
                 self.s_comp.wait_event(up)
                 if d2h_done[slot] is not None:
                     self.s_comp.wait_event(d2h_done[slot])
-                nbytes = (lens + 7) >> 3
-                offs = (torch.cumsum(nbytes, 0) - nbytes) << 3
+                offs = self._d_bit_off[slot][:nb]
+                rc = lib.scl_packed_offsets(_ptr(lens), None, nb, 0, _ptr(self._d_byte_off[slot]), _ptr(offs), torch.cuda.current_stream().cuda_stream)
+                _cabi.check(rc, "scl_packed_offsets")
                 enc = EncodedBlocks(d_c, offs, lens, None, 0)
                 old = self._d_dec[slot]
                 d = dc.decode_blocks(enc, self.N, reuse=old if old is not None and old.sizes.numel() == nb else None)

@@ -246,7 +246,7 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
         if (e->rans) {
             RansHost &rh = *e->rans;
             st = rh.dec32 ? rans32_decode_lane(rh.dec_lut.data(), rh.c, r, row, sym_stride, size, used)
-                          : rans64_decode_lane(rh.gen, rh.c, r, row, sym_stride, size, used);
+                          : rans64_decode_lane(rh.gen, rh.c, r, avail, row, sym_stride, size, used);
             if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         } else if (e->tans) {
             st = tans_decode_lane(e->tdec.data(), e->tans->r.c, r, row, sym_stride, size, used);

@@ -1,0 +1,177 @@
+"""GPU tier (-m gpu): the contiguous-output encode (scl_encode_blocks_packed) -- the fused kernel for the
+second-generation rANS / tANS path and the encode + scan + copy sequence for every other kernel family --
+against the slot encoder + pack()/frame() (whose bytes the other GPU tests pin to BitArray.tobytes(), to the
+reference's EncodedBlockWriter format and to the oracle), against the oracle directly, and through the decoders.
+Reference behaviour matched: scl/core/encoded_stream.py:150-175 (write_block), rANS.py:199-208."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scl_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+    from stanford_compression_library_b200 import _cabi
+
+    _cabi.lib()
+    yield
+
+
+def _codec(name):
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+    from stanford_compression_library_b200.compressors.tANS import tANSDecoder, tANSEncoder, tANSParams
+    from stanford_compression_library_b200.workloads import zipf_frequencies
+
+    fr = zipf_frequencies()
+    if name == "rans_default":
+        p = rANSParams(fr)
+        return rANSEncoder(p), rANSDecoder(p)
+    if name == "rans_nbo8":
+        p = rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)
+        return rANSEncoder(p), rANSDecoder(p)
+    if name == "rans_generic64":  # 64-bit state: generic kernels -> the encode + scan + copy sequence
+        p = rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 16)
+        return rANSEncoder(p), rANSDecoder(p)
+    if name == "tans":
+        p = tANSParams(fr, RANGE_FACTOR=1)
+        return tANSEncoder(p), tANSDecoder(p)
+    if name == "range":
+        p = RangeCoderParams()
+        return RangeEncoder(p, fr), RangeDecoder(p, fr)
+    ap = AECParams()
+    uni = Frequencies({b: 1 for b in range(256)})
+    return (ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)),
+            ArithmeticDecoder(ap, AdaptiveIIDFreqModel(uni, ap.MAX_ALLOWED_TOTAL_FREQ)))
+
+
+def _check_against_slots(enc, dec, data, framed):
+    B, N = data.shape
+    e = enc.encode_blocks(data).check()
+    p = enc.encode_blocks_packed(data, framed=framed).check()
+    torch.cuda.synchronize()
+    assert torch.equal(p.bit_len, e.bit_len)
+    if framed:
+        want, woffs = e.frame()
+        total = int(p.byte_offset[-1])
+        assert total == want.numel() and torch.equal(p.byte_offset, woffs)
+        assert torch.equal(p.buf[:total], want)
+    else:
+        want = e.pack()
+        total = int(p.byte_offset[-1])
+        assert total == e.total_bytes() and torch.equal(p.byte_offset, want.byte_offset)
+        assert torch.equal(p.bit_offset, want.bit_offset)
+        assert torch.equal(p.buf[:total], want.buf[:total])
+    d = dec.decode_blocks(p, N).check()  # straight from the packed / framed buffer
+    assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e.bit_len)
+    return p
+
+
+@pytest.mark.parametrize("framed", [False, True], ids=["packed", "framed"])
+@pytest.mark.parametrize("name", ["rans_default", "rans_nbo8", "tans", "rans_generic64", "range", "aec"])
+@pytest.mark.parametrize("shape", [(1, 4096), (31, 200), (33, 64), (1000, 1030), (4737, 320)], ids=lambda s: "%dx%d" % s)
+def test_packed_encode_equals_slots_plus_pack(name, shape, framed):
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    B, N = shape
+    if name == "aec":
+        N = min(N, 512)
+    enc, dec = _codec(name)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=B + N, device="cuda:0")
+    data[0, :] = 255  # rarest symbol: the longest possible stream next to ordinary ones
+    if B > 2:
+        data[B // 2, :] = 0  # and the shortest
+    _check_against_slots(enc, dec, data, framed)
+
+
+@pytest.mark.parametrize("kw", [{}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)], ids=["default", "nbo8_rf12"])
+def test_packed_encode_many_rounds_vs_oracle(kw):
+    """More tasks than one round of the persistent grid holds (the look-back then crosses rounds), a block
+    count that is not a multiple of 32, reuse of the output object; bytes compared with the ORACLE's own
+    concatenation for a strided sample and with the slot path for everything."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    B, N = 148 * 28 * 32 * 2 + 32 * 57 + 13, 128
+    params = rANSParams(zipf_frequencies(), **kw)
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=3, device="cuda:0")
+    p = _check_against_slots(enc, dec, data, False)
+    # second call into the same object: identical bytes (workspace reset, no stale look-back state)
+    snap = p.buf[: int(p.byte_offset[-1])].clone()
+    p2 = enc.encode_blocks_packed(data, reuse=p).check()
+    assert p2 is p and torch.equal(p.buf[: int(p.byte_offset[-1])], snap)
+    oracle = so.Oracle.rans(zipf_freq_list(), **kw)
+    host = data.cpu().numpy()
+    offs = p.byte_offset.cpu().numpy()
+    buf = p.buf.cpu().numpy()
+    for b in list(range(0, B, 9973)) + [B - 1]:
+        ref_bytes, ref_bits = oracle.encode_block(host[b])
+        assert int(p.bit_len[b]) == ref_bits
+        assert buf[offs[b] : offs[b + 1]].tobytes() == ref_bytes.tobytes()
+
+
+def test_packed_encode_destination_too_small():
+    """A record that would end past dst is dropped and flagged (OverflowError), earlier records are intact."""
+    from stanford_compression_library_b200.compressors.rANS import rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities
+
+    B, N = 64, 1024
+    enc = rANSEncoder(rANSParams(zipf_frequencies()))
+    data = sample_blocks(zipf_probabilities(), B, N, seed=8, device="cuda:0")
+    full = enc.encode_blocks_packed(data).check()
+    offs = full.byte_offset.cpu().numpy()
+    cap = int(offs[40]) + 5  # room for 40 records and a bit
+    small = enc.encode_blocks_packed(data, capacity=cap)
+    st = small.status.cpu().numpy()
+    assert (st[:40] == 0).all() and (st[40:] == 3).all()
+    assert torch.equal(small.buf[: int(offs[40])], full.buf[: int(offs[40])])
+    with pytest.raises(OverflowError):
+        small.check()
+
+
+def test_packed_bad_symbol_takes_no_room():
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.rANS import rANSEncoder, rANSParams
+
+    fr = Frequencies({b: 16 for b in range(0, 256, 2)})  # odd byte values are not in the alphabet
+    enc = rANSEncoder(rANSParams(fr))
+    data = (torch.randint(0, 128, (96, 256), device="cuda:0", dtype=torch.int32) * 2).to(torch.uint8)
+    data[17, 100] = 3
+    p = enc.encode_blocks_packed(data)
+    st = p.status.cpu().numpy()
+    assert st[17] == 1 and (np.delete(st, 17) == 0).all()
+    offs = p.byte_offset.cpu().numpy()
+    assert offs[18] == offs[17]
+    with pytest.raises(KeyError):
+        p.check()
+    good = enc.encode_blocks(data).pack()
+    for b in (16, 18, 95):
+        n = (int(p.bit_len[b]) + 7) // 8
+        go = int(good.byte_offset[b])
+        assert torch.equal(p.buf[offs[b] : offs[b] + n], good.buf[go : go + n])
+
+
+def test_packed_offsets_scan():
+    from stanford_compression_library_b200.device import EncodedBlocks
+
+    rng = np.random.default_rng(5)
+    for B in (1, 2047, 2048, 2049, 70001):
+        lens = rng.integers(0, 40000, size=B).astype(np.int64)
+        e = EncodedBlocks(torch.zeros(16, dtype=torch.uint8, device="cuda:0"), None, torch.from_numpy(lens).cuda(), None, 0)
+        for framed in (False, True):
+            byte_off, bit_off = e.packed_offsets(framed)
+            sz = 4 + (lens + 3 + 7) // 8 if framed else (lens + 7) // 8
+            want = np.concatenate([[0], np.cumsum(sz)])
+            assert byte_off.cpu().numpy().tolist() == want.tolist()
+            lead = (32 + 3 + (8 - (lens + 3) % 8) % 8) if framed else 0
+            assert bit_off.cpu().numpy().tolist() == (8 * want[:-1] + lead).tolist()

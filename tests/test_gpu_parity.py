@@ -28,6 +28,13 @@ def _cuda():
     yield
 
 
+def _force(mode, *coders):
+    """kernel-selection test hook, per handle (scl_coder_debug_path): 1 = first-generation kernels, 2 = v2 decode with
+    sector stores, 3 / 4 = v2 decode always / never pipe-balanced, 0 = default"""
+    for c in coders:
+        c.device_coder().debug_path(mode)
+
+
 def _F(freqs):
     from stanford_compression_library_b200 import Frequencies
 
@@ -231,22 +238,21 @@ def test_range_kernel_generations_agree(name, shape):
     data = torch.from_numpy(host).cuda()
     params = RangeCoderParams()
     enc, dec = RangeEncoder(params, _F(fl)), RangeDecoder(params, _F(fl))
-    lib = _cabi.lib()
     try:
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         e1 = enc.encode_blocks(data).check()
-        p1 = e1.pack()
-        lib.scl_debug_force_v1(0)
+        p1 = e1.pack(bytewise=True)
+        _force(0, enc, dec)
         e2 = enc.encode_blocks(data).check()
         p2 = e2.pack()
         assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
         assert torch.equal(p1.buf, p2.buf)
         d2 = dec.decode_blocks(e1, N).check()      # v2 decoder on v1 output (slots)
         d3 = dec.decode_blocks(p2, N).check()      # v2 decoder on packed streams (byte-granular offsets)
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         d1 = dec.decode_blocks(e2, N).check()      # v1 decoder on v2 output
     finally:
-        lib.scl_debug_force_v1(0)
+        _force(0, enc, dec)
     for d in (d1, d2, d3):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
         assert int(d.sizes.min()) == N == int(d.sizes.max())
@@ -442,15 +448,9 @@ def test_pack_and_frame_kernel_generations_agree(coder):
         enc = ArithmeticEncoder(ap, AdaptiveIIDFreqModel(_F([1] * 256), ap.MAX_ALLOWED_TOTAL_FREQ))
         data, sizes = data[:, :1024].contiguous(), torch.clamp(sizes, max=1024)
     e = enc.encode_blocks(data, sizes=sizes).check()
-    lib = _cabi.lib()
-    try:
-        lib.scl_debug_force_v1(1)
-        p1, (f1, o1) = e.pack(), e.frame()
-        lib.scl_debug_force_v1(0)
-        p2, (f2, o2) = e.pack(), e.frame()
-        pp1 = p2.pack()  # packing an already packed (byte-aligned, contiguous) buffer is the identity
-    finally:
-        lib.scl_debug_force_v1(0)
+    p1, (f1, o1) = e.pack(bytewise=True), e.frame(bytewise=True)
+    p2, (f2, o2) = e.pack(), e.frame()
+    pp1 = p2.pack()  # packing an already packed (byte-aligned, contiguous) buffer is the identity
     assert torch.equal(p1.buf, p2.buf) and torch.equal(p1.bit_offset, p2.bit_offset)
     assert torch.equal(f1, f2) and torch.equal(o1, o2)
     assert torch.equal(pp1.buf, p2.buf)
@@ -550,27 +550,26 @@ def test_rans_kernel_generations_agree(kw, shape):
     enc, dec = rANSEncoder(params), rANSDecoder(params)
     data = sample_blocks(zipf_probabilities(), B, N, seed=11, device="cuda:0")
     data[0, :] = 255  # rarest symbol: worst-case bits per symbol
-    lib = _cabi.lib()
     try:
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         e1 = enc.encode_blocks(data).check()
-        p1 = e1.pack()
-        lib.scl_debug_force_v1(0)
+        p1 = e1.pack(bytewise=True)
+        _force(0, enc, dec)
         e2 = enc.encode_blocks(data).check()
         p2 = e2.pack()
         assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
         assert torch.equal(p1.buf, p2.buf)
         d2 = dec.decode_blocks(e1, N).check()  # v2 decoder (TMA tile stores) on v1 output
-        lib.scl_debug_force_v1(2)
+        _force(2, enc, dec)
         d3 = dec.decode_blocks(e1, N).check()  # v2 decoder with per-lane sector stores
-        lib.scl_debug_force_v1(3)
+        _force(3, enc, dec)
         d4 = dec.decode_blocks(e1, N).check()  # v2 decoder, pipe-balanced instruction selection (large-batch form)
-        lib.scl_debug_force_v1(4)
+        _force(4, enc, dec)
         d5 = dec.decode_blocks(e1, N).check()  # v2 decoder, plain form
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         d1 = dec.decode_blocks(e2, N).check()  # v1 decoder on v2 output
     finally:
-        lib.scl_debug_force_v1(0)
+        _force(0, enc, dec)
     for d in (d1, d2, d3, d4, d5):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
         assert int(d.sizes.min()) == N == int(d.sizes.max())
@@ -594,23 +593,22 @@ def test_tans_kernel_generations_agree(rf):
     enc, dec = tANSEncoder(params), tANSDecoder(params)
     data = sample_blocks(zipf_probabilities(), B, N, seed=12, device="cuda:0")
     data[0, :] = 255
-    lib = _cabi.lib()
     try:
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         e1 = enc.encode_blocks(data).check()
-        p1 = e1.pack()
-        lib.scl_debug_force_v1(0)
+        p1 = e1.pack(bytewise=True)
+        _force(0, enc, dec)
         e2 = enc.encode_blocks(data).check()
         assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(p1.buf, e2.pack().buf)
         d2 = dec.decode_blocks(e1, N).check()
-        lib.scl_debug_force_v1(3)
+        _force(3, enc, dec)
         d3 = dec.decode_blocks(e1, N).check()  # pipe-balanced form
-        lib.scl_debug_force_v1(4)
+        _force(4, enc, dec)
         d4 = dec.decode_blocks(e1, N).check()  # plain form
-        lib.scl_debug_force_v1(1)
+        _force(1, enc, dec)
         d1 = dec.decode_blocks(e2, N).check()
     finally:
-        lib.scl_debug_force_v1(0)
+        _force(0, enc, dec)
     for d in (d1, d2, d3, d4):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
     oracle = so.Oracle.tans(zipf_freq_list(), RANGE_FACTOR=rf)
@@ -738,7 +736,6 @@ def test_aec_kernel_generations_agree():
     from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel, FixedFreqModel
     from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_probabilities
 
-    lib = _cabi.lib()
     B, N = 700, 1024
     data = sample_blocks(zipf_probabilities(), B, N, seed=41, device="cuda:0")
     data[0, :] = 255
@@ -752,17 +749,17 @@ def test_aec_kernel_generations_agree():
         params = AECParams(PRECISION=P)
         enc, dec = ArithmeticEncoder(params, mk(params)), ArithmeticDecoder(params, mk(params))
         try:
-            lib.scl_debug_force_v1(1)
+            _force(1, enc, dec)
             e1 = enc.encode_blocks(data, sizes=sizes).check()
-            p1 = e1.pack()
-            lib.scl_debug_force_v1(0)
+            p1 = e1.pack(bytewise=True)
+            _force(0, enc, dec)
             e2 = enc.encode_blocks(data, sizes=sizes).check()
             assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(p1.buf, e2.pack().buf)
             d2 = dec.decode_blocks(e1, N).check()
-            lib.scl_debug_force_v1(1)
+            _force(1, enc, dec)
             d1 = dec.decode_blocks(e2, N).check()
         finally:
-            lib.scl_debug_force_v1(0)
+            _force(0, enc, dec)
         mask = torch.arange(N, device="cuda:0")[None, :] < sizes[:, None]
         for d in (d1, d2):
             assert torch.equal(d.sizes, sizes)

@@ -581,3 +581,22 @@ def test_emu_order_k_table_size_limit():
     for n_sym, k in ((40, 1), (3, 6), (2, 10), (256, 1)):
         with pytest.raises(NotImplementedError):
             make(n_sym, k)
+
+
+def test_generic_rans_decode_is_bounded_on_a_zero_state():
+    """A malformed stream whose state field is 0 (or decodes to 0) can never reach L by shifting in the
+    zero bits the reader returns past the end: the reference raises ValueError from bitarray_to_uint on
+    an empty slice (rANS.py:256); the generic lane must stop with TRUNCATED instead of spinning."""
+    from stanford_compression_library_b200._cabi import CODER_RANS, SclParams
+
+    freq = np.array([3, 3, 2], dtype=np.uint64)
+    p = SclParams(coder=CODER_RANS, data_block_size_bits=32, num_bits_out=1, range_factor=1 << 16, num_state_bits=so.ref_get_bit_width((8 << 16) * 2 - 1))
+    coder = EmuCoder(p, None, freq)
+    coder.force_generic()
+    buf = np.zeros(64, dtype=np.uint8)
+    buf[3] = 1  # 32-bit size header = 1, every other bit 0 => state 0
+    sym, sizes, used, st = coder.decode(buf, [0], [8 * 48], 8)
+    assert st[0] == 4  # SCL_ST_TRUNCATED
+    # and with no bit_len given the bound is the end of the buffer
+    sym, sizes, used, st = coder.decode(buf, [0], None, 8)
+    assert st[0] == 4
