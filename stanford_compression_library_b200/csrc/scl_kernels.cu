@@ -210,11 +210,16 @@ __device__ __forceinline__ void tma_tile_2d(void *smem_dst, const CUtensorMap *t
 // the packed buffer depends on every earlier block's size, so a task still encodes into its scratch slots;
 // then (i) the warp sums its 32 record sizes (__reduce_add_sync), (ii) the last warp of a CTA to finish a round
 // adds up the CTA's tasks -- they are consecutive -- and resolves the cross-CTA exclusive prefix by decoupled
-// look-back over one word per (round, CTA) (scl_pack.cuh), (iii) every warp copies its 32 streams to their
-// final byte offsets (pack_block_warp).  Step (iii) of a task is DEFERRED until the warp has encoded its next
-// task: by then the prefix is long resolved, so no warp ever waits on a neighbour, and the copy (pure memory
-// traffic) runs under the other warps' arithmetic.  Depends on the in-order dispatch of CTAs (a CTA only waits
-// for lower-numbered CTAs of the same round, or for earlier rounds), like every single-pass scan.
+// look-back over one word per (round, CTA) (scl_pack.cuh), (iii) the streams are copied to their final byte
+// offsets (pack_block_warp_a16).  The CTA is WARP-SPECIALISED: the coding warps never copy while they have
+// symbols left; kCopyWarps extra warps (the CTA has room for 32, the coder uses at most 28) do nothing else,
+// taking resolved tasks from a ticket counter.  The copy is pure memory traffic with a bit shift, the coding is
+// arithmetic, so the two overlap on the SM, and the copy's registers (several chunks in flight per lane) stay
+// out of the coding loop's allocation.  A coding warp that has run out of tasks joins the copy pool, so the
+// last round's streams -- which nothing is left to overlap with -- are moved by the whole CTA.
+// Depends on the in-order dispatch of CTAs (a CTA only waits for lower-numbered CTAs of the same round, or
+// for earlier rounds), like every single-pass scan.
+constexpr uint32_t kCopyWarps = 4;
 struct PackedOut {
     uint8_t *dst;            // packed destination
     uint64_t dst_bytes;      // its capacity
@@ -222,11 +227,13 @@ struct PackedOut {
     uint64_t *cta_state;     // [rounds * gridDim.x] look-back words, zeroed before the launch
     uint32_t framed;
 };
-struct PackCtl {  // per CTA, shared memory; [round & 1]
-    unsigned long long warp_tot[2][kMaxWarps];   // record bytes of each warp's task
-    unsigned long long warp_excl[2][kMaxWarps];  // byte offset of each warp's task in dst
-    uint32_t excl_tag[2][kMaxWarps];             // round + 1 once warp_excl is valid
-    uint32_t arrive[2];
+struct PackCtl {  // per CTA, shared memory
+    unsigned long long warp_tot[2][kMaxWarps];   // [round & 1] record bytes of each coding warp's task
+    unsigned long long warp_excl[2][kMaxWarps];  // [round & 1] byte offset of each task in dst, valid once `resolved` > round
+    uint32_t arrive[2];                          // [round & 1] coding warps that have finished the round
+    uint32_t resolved;                           // rounds whose offsets are known (monotonic)
+    uint32_t copy_ticket;                        // next task to copy: ticket T = round * W + warp slot (monotonic)
+    uint32_t copy_done;                          // tasks copied so far (monotonic)
 };
 
 template <bool FRAMED>
@@ -254,25 +261,64 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
             nb = 0;
         }
     }
-    __syncwarp();  // the slots were written lane by lane; from here on every lane reads every slot
+    // where this lane's stream lies in the scratch buffer (it ends at its slot's end), and a hint to L2: the
+    // slots were written one task ago, i.e. ~400 MB of other traffic ago
+    const uint64_t src_off = (b + 1) * io.out_stride * 8 - bits;
     for (uint32_t l = 0; l < 32; ++l) {
         const uint32_t nb_l = __shfl_sync(0xffffffffu, nb, l);
+        if (l + 1 < 32) {  // fetch the NEXT stream into L2 while this one is copied: one line per lane, no registers held
+            const uint32_t nb_n = __shfl_sync(0xffffffffu, nb, l + 1);
+            const uint64_t so_n = __shfl_sync(0xffffffffu, src_off, l + 1);
+            const uint8_t *p0 = io.out + ((so_n >> 3) & ~127ull);
+            if (nb_n)
+                for (uint32_t o = lane * 128; o < nb_n + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        }
         if (!nb_l) continue;
         const uint64_t bits_l = __shfl_sync(0xffffffffu, bits, l), at_l = __shfl_sync(0xffffffffu, at, l);
-        const uint64_t src_off = (task * 32 + l + 1) * io.out_stride * 8 - bits_l;  // the stream ends at its slot's end
-        pack_block_warp<FRAMED, false>(io.out, src_off, bits_l, po.dst + at_l, lane);
+        const uint64_t so_l = __shfl_sync(0xffffffffu, src_off, l);
+        pack_block_warp_a16<FRAMED>(io.out, so_l, bits_l, po.dst + at_l, lane);
+    }
+}
+
+// The copy pool: take tickets until the CTA's tasks are exhausted.  Ticket T = (round T / W, warp slot T % W).
+__device__ __forceinline__ void packed_copy_pool(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
+                                                 uint32_t n_tasks, uint32_t lane) {
+    while (true) {
+        uint32_t T = 0;
+        if (lane == 0) T = atomicAdd(&ctl.copy_ticket, 1u);
+        T = __shfl_sync(0xffffffffu, T, 0);
+        const uint32_t r = T / W, slot = T - r * W;
+        const uint64_t task = (uint64_t)r * total_warps + blockIdx.x * W + slot;
+        if (task >= n_tasks) return;  // tickets run through the rounds in order: nothing valid after the first invalid one
+        if (lane == 0) {
+            const volatile uint32_t *res = &ctl.resolved;
+            while (*res <= r) __nanosleep(200);
+        }
+        __syncwarp();
+        __threadfence_block();
+        const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][slot];
+        if (po.framed)
+            packed_copy_task<true>(io, po, task, base, lane);
+        else
+            packed_copy_task<false>(io, po, task, base, lane);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            atomicAdd(&ctl.copy_done, 1u);
+        }
     }
 }
 
 template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+__global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
                           uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, PackedOut po) {
     __shared__ PackCtl ctl;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // round the dynamic window up to 2 KiB so that ring addresses can be composed with OR
     uint8_t *smem = smem_raw + ((2048u - (smem_u32(smem_raw) & 2047u)) & 2047u);
-    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // W = coding warps; a PACKED launch carries kCopyWarps more (warp >= W), which own no tiles and no ring
+    const uint32_t W = (blockDim.x >> 5) - (PACKED ? kCopyWarps : 0u), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
     const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
     const uint8_t *s_tab = smem + W * kEncWarpSmem;
@@ -286,9 +332,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
         for (uint32_t i = 0; i < W * kTileStages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbars + i)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (PACKED && threadIdx.x < 2 * kMaxWarps) {
-        (&ctl.excl_tag[0][0])[threadIdx.x] = 0;
-        if (threadIdx.x < 2) ctl.arrive[threadIdx.x] = 0;
+    if (PACKED && threadIdx.x == 0) {
+        ctl.arrive[0] = ctl.arrive[1] = 0;
+        ctl.resolved = ctl.copy_ticket = ctl.copy_done = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -305,24 +351,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     uint32_t tile_seq = 0;  // tiles consumed by this warp so far (selects stage and mbarrier parity)
     const uint32_t swz = (lane >> 1) & 3;
 
-    // PACKED: wait for the byte offset of this warp's task of round `r` (published by the CTA's last warp of that
-    // round), then copy the task's streams there
-    auto packed_finish = [&](uint32_t r, uint32_t task) {
-        if (lane == 0) {
-            const volatile uint32_t *tag = &ctl.excl_tag[r & 1][warp];
-            while (*tag != r + 1) __nanosleep(100);
-        }
-        __syncwarp();
-        __threadfence_block();
-        const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][warp];
-        if (po.framed)
-            packed_copy_task<true>(io, po, task, base, lane);
-        else
-            packed_copy_task<false>(io, po, task, base, lane);
-    };
-
     uint32_t round = 0;
-    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
+    // a copy warp (PACKED, warp >= W) has no tasks: it goes straight to the pool below
+    for (uint32_t task = (PACKED && warp >= W) ? n_tasks : blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         if (lane == 0) {
@@ -416,16 +447,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
                     if (lane == 0) st_relaxed_gpu(po.cta_state + g, kLbPrefix | (excl + A));
                 }
                 if (lane == 0 && first + nvalid == n_tasks) po.byte_off[io.n_blocks] = excl + A;  // the very last round: grand total
+                // warp_excl[par] still serves the copy of round - 2: wait until all of it (and everything before) is done.
+                // Also the back-pressure: the coder never runs more than two rounds ahead of the copy pool.
+                if (round >= 2 && lane == 0) {
+                    const volatile uint32_t *done = &ctl.copy_done;
+                    while (*done < (round - 1) * W) __nanosleep(200);
+                }
+                __syncwarp();
                 if (lane < nvalid) *(volatile unsigned long long *)&ctl.warp_excl[par][lane] = excl + incl - t;
                 __threadfence_block();
                 __syncwarp();
-                if (lane < nvalid) *(volatile uint32_t *)&ctl.excl_tag[par][lane] = round + 1;
+                if (lane == 0) *(volatile uint32_t *)&ctl.resolved = round + 1;
             }
-            // (iii) deferred by one task: copy the PREVIOUS task's streams to their final place
-            if (round) packed_finish(round - 1, task - total_warps);
         }
     }
-    if (PACKED && round) packed_finish(round - 1, blockIdx.x * W + warp + (round - 1) * total_warps);
+    if (PACKED) packed_copy_pool(ctl, io, po, W, total_warps, n_tasks, lane);  // out of symbols: help move the last rounds
 }
 
 // Decode.  Output goes through a per-warp 32 x 64-byte tile in shared memory (64-byte swizzle, so
@@ -1446,7 +1482,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     do {                                                                                                                           \
         e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
-        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, warps * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, po);    \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + (PK ? kCopyWarps : 0)) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, po); \
     } while (0)
     if (rc.check_sym) {
         if (packed)

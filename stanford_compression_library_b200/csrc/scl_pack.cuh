@@ -107,6 +107,86 @@ __device__ __forceinline__ void pack_block_warp(const uint8_t *__restrict__ src,
         d[i] = (uint8_t)pack_payload_byte<FRAMED, NC>(src, off, nbits, num_pad, lead, i);
 }
 
+// The same copy for a source this kernel wrote itself (the fused encoder's scratch slots), tuned for ONE warp
+// that has to move a whole task (32 streams, ~100 KB) while the SM's other warps are busy coding: the source
+// base is 16-byte aligned, so a chunk's five words come from two aligned 128-bit loads (2 x 4 L1 wavefronts per
+// 512 bytes instead of 5 x 4 for word loads), the word offset inside the pair is the same for every chunk of a
+// stream (template W0), and U chunks per lane are in flight before the first one is used -- a single warp must
+// keep a few KB outstanding to make progress against ~1 us of memory latency.
+// Reads up to 16 bytes past the 16-byte group that holds the stream's last bit.
+template <int W0>
+__device__ __forceinline__ uint4 pack_chunk_from_pair(const uint4 &A, const uint4 &B, uint32_t sh) {
+    const uint32_t x[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    uint32_t W[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) W[j] = bswap32(x[W0 + j]);
+    uint4 o;
+    o.x = bswap32(funnel_l(W[1], W[0], sh));
+    o.y = bswap32(funnel_l(W[2], W[1], sh));
+    o.z = bswap32(funnel_l(W[3], W[2], sh));
+    o.w = bswap32(funnel_l(W[4], W[3], sh));
+    return o;
+}
+
+__device__ __forceinline__ uint4 ld_plain128(const uint4 *p) {  // volatile asm: the loads of a batch stay together, ahead of its stores
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_plain128(uint8_t *p, const uint4 &v) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int W0, int U>
+__device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uint32_t sh, uint8_t *__restrict__ dd, uint32_t n_chunks, uint32_t lane) {
+    const uint32_t last = n_chunks - 1;
+    for (uint32_t c0 = lane; c0 < n_chunks; c0 += 32 * U) {
+        uint4 A[U], B[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // all 2U loads first (a clamped index instead of a predicate keeps them unconditional)
+            const uint32_t ch = min(c0 + 32 * u, last);
+            A[u] = ld_plain128(a + ch);
+            B[u] = ld_plain128(a + ch + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t ch = c0 + 32 * u;
+            if (ch < n_chunks) st_plain128(dd + 16 * ch, pack_chunk_from_pair<W0>(A[u], B[u], sh));
+        }
+    }
+}
+
+template <bool FRAMED>
+__device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ src, uint64_t off, uint64_t nbits, uint8_t *__restrict__ d,
+                                                    uint32_t lane) {
+    constexpr int U = 4;
+    const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
+    const uint64_t lead = FRAMED ? 3 + num_pad : 0;
+    const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
+    if (FRAMED) {
+        if (lane < 4) d[lane] = (uint8_t)(payload_bytes >> (8 * (3 - lane)));
+        d += 4;
+    }
+    uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (FRAMED && 8 * head < lead) head += 16;
+    if (head > payload_bytes) head = payload_bytes;
+    const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
+    for (uint64_t i = lane; i < head; i += 32) d[i] = (uint8_t)pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, i);
+    if (n_chunks) {
+        const uint64_t S0 = off + 8 * head - lead;  // source bit of chunk 0's first bit; chunk ch starts 128 * ch bits later
+        const uint4 *a = (const uint4 *)src + (S0 >> 7);
+        const uint32_t sh = (uint32_t)(S0 & 31);
+        switch ((uint32_t)(S0 >> 5) & 3u) {  // the same for every lane: no divergence
+        case 0: pack_chunks_a16<0, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
+        case 1: pack_chunks_a16<1, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
+        case 2: pack_chunks_a16<2, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
+        default: pack_chunks_a16<3, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
+        }
+    }
+    for (uint64_t i = head + 16 * n_chunks + lane; i < payload_bytes; i += 32)
+        d[i] = (uint8_t)pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, i);
+}
+
 // ---- decoupled look-back ----------------------------------------------------------------------------------
 // state[i] = flag << 62 | value: flag 0 = not there yet, 1 = the producer's own total, 2 = inclusive prefix up to
 // and including producer i.  One 64-bit word carries flag and value together, so relaxed accesses suffice.

@@ -39,3 +39,22 @@ def sample_blocks(weights, n_blocks: int, block_len: int, seed: int, device, chu
         u = torch.rand((b1 - b0, block_len), generator=g, device=device, dtype=torch.float32)
         out[b0:b1] = torch.searchsorted(cdf, u, right=True).clamp_(max=len(weights) - 1).to(torch.uint8)
     return out
+
+
+def sample_stream_blocks(weights, lo: int, hi: int, block_len: int, device, chunk_blocks: int = 16384, base_seed: int = 0) -> torch.Tensor:
+    """Blocks [lo, hi) of ONE global synthetic stream: chunk k of `chunk_blocks` blocks is drawn from its own
+    generator (seed base_seed + k), so a rank's shard holds the same bytes whatever the number of ranks the
+    stream is split over (strong scaling: the 8 GiB of BASELINE configs[4] at 1, 2, 4 or 8 GPUs)."""
+    f = torch.tensor(weights, dtype=torch.float64, device=device)
+    cdf = torch.cumsum(f / f.sum(), 0).to(torch.float32)
+    cdf[-1] = 2.0
+    out = torch.empty((hi - lo, block_len), dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    for k in range(lo // chunk_blocks, (hi + chunk_blocks - 1) // chunk_blocks):
+        g.manual_seed(base_seed + k)
+        u = torch.rand((chunk_blocks, block_len), generator=g, device=device, dtype=torch.float32)
+        sym = torch.searchsorted(cdf, u, right=True).clamp_(max=len(weights) - 1).to(torch.uint8)
+        c0 = k * chunk_blocks
+        a, b = max(lo, c0), min(hi, c0 + chunk_blocks)
+        out[a - lo : b - lo] = sym[a - c0 : b - c0]
+    return out
