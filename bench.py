@@ -40,6 +40,16 @@ HEADLINE = "default"
 _REAL_STDOUT = None
 
 
+_T0 = time.time()
+
+
+def progress(msg):
+    """stage markers on stderr (stdout carries only the JSON line)"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench +%.1fs] %s\n" % (time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
 def emit(line):
     out = _REAL_STDOUT or sys.stdout
     out.write(json.dumps(line) + "\n")
@@ -348,7 +358,10 @@ def main():
     total_blocks = args.global_blocks if args.scaling == "strong" else args.blocks_per_gpu * world
     lo, hi = shard_range(total_blocks, rank, world)  # this rank's contiguous block range of the global stream
     B = hi - lo
+    progress("generating %d blocks on the device" % B)
     data = sample_stream_blocks(zipf_probabilities(), lo, hi, N, dev)  # the same global bytes at every N
+    torch.cuda.synchronize()
+    progress("data ready")
     peak, peak_src = measured_peak_gbs()
     sampler = ClockSampler(local_rank)
 
@@ -364,6 +377,7 @@ def main():
         enc, dec = rANSEncoder(params), rANSDecoder(params)
         nB = data.shape[0]
         do_enc = (lambda reuse: enc.encode_blocks_packed(data, capacity=nB * N + (1 << 20), reuse=reuse)) if packed else (lambda reuse: enc.encode_blocks(data, reuse=reuse))
+        progress("variant %s, %d blocks, %s: first pass" % (name, nB, "packed" if packed else "slots"))
         e = do_enc(None)
         d = dec.decode_blocks(e, N)
         e.check(), d.check()
@@ -373,6 +387,7 @@ def main():
         if parity:  # GPU bits == CPU oracle bits, on this rank's own shard, before anything is timed
             ok, checked, bad = parity_check(fl, VARIANTS[name], data, e, parity)
             par = (ok, checked, bad)
+            progress("parity vs oracle: %s (%d blocks)" % (ok, checked))
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         for _ in range(warmup):
             do_enc(e)
@@ -468,6 +483,7 @@ def main():
     # download stream over a ring of staging slots.  Every byte crosses PCIe inside the timed region.
     from stanford_compression_library_b200.pipeline import HostCodecPipeline
 
+    progress("e2e: pinning host buffers")
     host_in = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
     host_in.copy_(data)
     host_out = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
@@ -485,8 +501,10 @@ def main():
         d2h += pipe.d2h_bytes
         return total
 
+    progress("e2e: first step")
     total_c = e2e_step()
     barrier()
+    progress("e2e: timed steps")
     assert total_c == head["C"] and torch.equal(host_out, host_in), "e2e round trip failed"
     host_out.zero_()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -506,6 +524,7 @@ def main():
     del pipe, host_out, host_c
     torch.cuda.empty_cache()
 
+    progress("e2e done")
     # total compressed size of the global stream (all-gather of 8 x u64)
     sizes, my_off = gather_compressed_sizes(head["C"])
 
@@ -527,9 +546,11 @@ def main():
         so.build()
         threads = host_threads()
         nb = min(B, 1024 * threads)
+        progress("cpu baseline (C port, %d threads)" % threads)
         cpu = cpu_baseline(fl, VARIANTS[HEADLINE], data[:nb].cpu().numpy(), threads, HEADLINE)
         if not args.no_python_reference:
             # the reference's own Python coder on the same batch, its bits compared with the GPU's
+            progress("python reference leg")
             n_py = min(B, 2 * threads)
             rows = data[:n_py].cpu().numpy()
             py, streams = python_reference_leg(fl, VARIANTS[HEADLINE], [r.tolist() for r in rows], threads)
@@ -541,6 +562,7 @@ def main():
                 assert py["gpu_bits_equal"], "GPU bitstream differs from the Python reference's"
             cpu["python_reference"] = py
 
+    progress("done")
     if rank == 0:
         line = {
             "metric": METRIC, "value": hs["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -71,6 +71,84 @@ class GpuCoderBase:
         """Decode B independent streams into uint8 [B, >=max_block_len]."""
         return self.device_coder().decode_blocks(enc, max_block_len, out=out, reuse=reuse)
 
+    # ---- the reference's stream-level entry points, batched -----------------------------------
+    # DataEncoder.encode / DataDecoder.decode (data_encoder_decoder.py:56-69, 131-144) call encode_block /
+    # decode_block once per block; here `blocks_per_batch` blocks are pulled from the stream and coded by ONE
+    # launch (the framing of EncodedBlockWriter included), which is what a device needs.  Same bytes, same
+    # asserts.  Coders whose blocks are not independent (an adaptive model carried from block to block, as the
+    # reference's arithmetic coder does) keep the per-block loop: `_blocks_independent()`.
+    blocks_per_batch = 4096
+
+    def _blocks_independent(self) -> bool:
+        return True
+
+    def _blocks_to_array(self, blocks):
+        """list of DataBlocks -> (uint8 [n, max_len] zero-padded, sizes int32 [n]); KeyError for unknown symbols"""
+        self.device_coder()
+        n = len(blocks)
+        sizes = np.fromiter((b.size for b in blocks), dtype=np.int32, count=n)
+        out = np.zeros((n, max(1, int(sizes.max()) if n else 1)), dtype=np.uint8)
+        for i, b in enumerate(blocks):
+            d = b.data_list
+            if self._native and isinstance(d, np.ndarray) and d.dtype == np.uint8:
+                out[i, : d.size] = d
+                continue
+            seq = d.tolist() if hasattr(d, "tolist") else d
+            try:
+                out[i, : len(seq)] = np.fromiter((self._sym2byte[x] for x in seq), dtype=np.uint8, count=len(seq))
+            except KeyError as e:
+                raise KeyError(e.args[0]) from None
+        return out, sizes
+
+    def encode(self, data_stream, block_size: int, encode_writer):
+        if self.blocks_per_batch <= 1 or not self._blocks_independent() or not hasattr(encode_writer, "write_encoded_blocks"):
+            return super().encode(data_stream, block_size, encode_writer)
+        while True:
+            blocks = data_stream.get_block_batch(block_size, self.blocks_per_batch)
+            if not blocks:
+                break
+            data, sizes = self._blocks_to_array(blocks)
+            ragged = bool((sizes != data.shape[1]).any())
+            enc = self.encode_blocks_packed(torch.from_numpy(data), sizes=torch.from_numpy(sizes) if ragged else None, framed=True).check()
+            encode_writer.write_encoded_blocks(enc)
+
+    def _peek_sizes(self, enc: EncodedBlocks):
+        """block sizes from the stream headers of a batch (host side, vectorised): needed to size the output"""
+        nbits = self._size_bits()
+        host = enc.buf.cpu().numpy()
+        offs = enc.bit_offset.cpu().numpy().astype(np.int64)
+        lens = enc.bit_len.cpu().numpy().astype(np.int64)
+        if nbits > 32:
+            raise NotImplementedError("DATA_BLOCK_SIZE_BITS > 32 in the batched stream decoder")
+        if (lens < nbits).any():
+            raise ValueError("non-empty bitarray expected")
+        first = offs >> 3
+        idx = first[:, None] + np.arange(5)[None, :]
+        b = host[np.minimum(idx, host.size - 1)].astype(np.uint64)
+        word = (b[:, 0] << np.uint64(32)) | (b[:, 1] << np.uint64(24)) | (b[:, 2] << np.uint64(16)) | (b[:, 3] << np.uint64(8)) | b[:, 4]
+        sh = (np.uint64(40) - np.uint64(nbits) - (offs & 7).astype(np.uint64))
+        return ((word >> sh) & np.uint64((1 << nbits) - 1)).astype(np.int64)
+
+    def decode(self, encode_reader, output_stream):
+        if self.blocks_per_batch <= 1 or not self._blocks_independent() or not hasattr(encode_reader, "get_encoded_blocks"):
+            return super().decode(encode_reader, output_stream)
+        dev = self.device_coder().device
+        while True:
+            enc = encode_reader.get_encoded_blocks(device=dev, max_blocks=self.blocks_per_batch)
+            if enc is None or enc.n_blocks == 0:
+                break
+            sizes = self._peek_sizes(enc)
+            limit = self._max_symbols_for_bits(int(enc.bit_len.max()))
+            if int(sizes.max()) > limit:
+                raise ValueError("a block header declares %d symbols, more than its stream can hold (corrupt file?)" % int(sizes.max()))
+            dec = self.decode_blocks(enc, max(1, int(sizes.max()))).check()
+            if not bool((dec.bits_consumed == enc.bit_len).all()):
+                raise AssertionError("num_bits_consumed != len(encoded_block)")  # data_encoder_decoder.py:141
+            sym = dec.symbols.cpu().numpy()
+            got = dec.sizes.cpu().numpy()
+            for b in range(sym.shape[0]):
+                output_stream.write_block(self._row_to_block(sym[b, : got[b]]))
+
     # ---- reference single-block API --------------------------------------------------------
     def _encode_one(self, data_block: DataBlock, model=None) -> BitArray:
         t = self._block_to_tensor(data_block)
@@ -143,22 +221,24 @@ def encode_uint8_file(encoder, input_file_path: str, encoded_file_path: str, blo
             writer.write_encoded_blocks(enc)
 
 
-def decode_uint8_file(decoder, encoded_file_path: str, output_file_path: str, block_size: int = 10000):
+def decode_uint8_file(decoder, encoded_file_path: str, output_file_path: str, block_size: int = 10000, blocks_per_batch: int = 65536):
     """Batched counterpart of `DataDecoder.decode_file` for byte files written by the reference's
-    `EncodedBlockWriter` (or by `encode_uint8_file`)."""
+    `EncodedBlockWriter` (or by `encode_uint8_file`): the file is read and decoded `blocks_per_batch` records at
+    a time, so device and host memory stay bounded whatever the file size."""
     from ..core.encoded_stream import EncodedBlockReader
 
     with EncodedBlockReader(encoded_file_path) as reader, open(output_file_path, "wb") as out:
-        enc = reader.get_encoded_blocks(device=decoder.device_coder().device)
-        if enc.n_blocks == 0:
-            return
-        dec = decoder.decode_blocks(enc, block_size).check()
-        if not bool((dec.bits_consumed == enc.bit_len).all()):
-            raise AssertionError("num_bits_consumed != len(encoded_block)")  # data_encoder_decoder.py:141
-        sym = dec.symbols.cpu().numpy()
-        sizes = dec.sizes.cpu().numpy()
-        if (sizes == sym.shape[1]).all():
-            out.write(sym.tobytes())
-        else:
-            for b in range(sym.shape[0]):
-                out.write(sym[b, : sizes[b]].tobytes())
+        while True:
+            enc = reader.get_encoded_blocks(device=decoder.device_coder().device, max_blocks=blocks_per_batch)
+            if enc is None or enc.n_blocks == 0:
+                return
+            dec = decoder.decode_blocks(enc, block_size).check()
+            if not bool((dec.bits_consumed == enc.bit_len).all()):
+                raise AssertionError("num_bits_consumed != len(encoded_block)")  # data_encoder_decoder.py:141
+            sym = dec.symbols.cpu().numpy()
+            sizes = dec.sizes.cpu().numpy()
+            if (sizes == sym.shape[1]).all():
+                out.write(sym.tobytes())
+            else:
+                for b in range(sym.shape[0]):
+                    out.write(sym[b, : sizes[b]].tobytes())

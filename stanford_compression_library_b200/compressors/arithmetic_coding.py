@@ -53,6 +53,13 @@ class _AecCoder(GpuCoderBase):
                                model_order=int(getattr(self.freq_model, "k", 0)) if self.freq_model.CABI_MODEL == _cabi.MODEL_ORDER_K else 0,
                                max_allowed_total_freq=int(self.freq_model.max_allowed_total_freq))
 
+    def _blocks_independent(self) -> bool:
+        # the reference carries the (mutated) model from one encode_block call to the next (arithmetic_coding.py:118,
+        # data_encoder_decoder.py:23-27): only a model that never changes makes the blocks of a stream independent
+        from .probability_models import FixedFreqModel
+
+        return isinstance(self.freq_model, FixedFreqModel)
+
     def _max_symbols_for_bits(self, nbits: int) -> int:
         # an adaptive model can drive the cost of a repeated symbol towards zero bits: no bound from the
         # stream length, only the flat allocation cap

@@ -31,6 +31,17 @@ class DataStream(abc.ABC):
             data.append(s)
         return DataBlock(data) if data else None
 
+    def get_block_batch(self, block_size: int, max_blocks: int):
+        """Up to `max_blocks` consecutive blocks as a list of DataBlocks ([] when the stream is exhausted): what the
+        batched `DataEncoder.encode` pulls per launch.  Streams override it with a bulk read where they can."""
+        out = []
+        while len(out) < max_blocks:
+            b = self.get_block(block_size)
+            if b is None:
+                break
+            out.append(b)
+        return out
+
     @abc.abstractmethod
     def write_symbol(self, s):
         pass
@@ -73,6 +84,11 @@ class ListDataStream(DataStream):
         data = self.input_list[self.current_ind : self.current_ind + block_size]
         self.current_ind += len(data)
         return DataBlock(data) if data else None
+
+    def get_block_batch(self, block_size: int, max_blocks: int):
+        data = self.input_list[self.current_ind : self.current_ind + block_size * max_blocks]
+        self.current_ind += len(data)
+        return [DataBlock(data[i : i + block_size]) for i in range(0, len(data), block_size)]
 
     def write_symbol(self, s):
         assert self.current_ind <= len(self.input_list)
@@ -117,6 +133,10 @@ class TextFileDataStream(FileDataStream):
         s = self.file_obj.read(block_size)
         return DataBlock(list(s)) if s else None
 
+    def get_block_batch(self, block_size: int, max_blocks: int):
+        s = self.file_obj.read(block_size * max_blocks)
+        return [DataBlock(list(s[i : i + block_size])) for i in range(0, len(s), block_size)]
+
     def write_symbol(self, s):
         self.file_obj.write(s)
 
@@ -136,6 +156,13 @@ class Uint8FileDataStream(FileDataStream):
     def get_block(self, block_size: int):
         s = self.file_obj.read(block_size)
         return DataBlock(list(s)) if s else None
+
+    def get_block_batch(self, block_size: int, max_blocks: int):
+        got = self.get_blocks(block_size, max_blocks)
+        if got is None:
+            return []
+        data, sizes = got
+        return [DataBlock(data[b, : sizes[b]]) for b in range(data.shape[0])]  # numpy rows: no per-symbol Python objects
 
     def get_blocks(self, block_size: int, max_blocks: int):
         """Up to `max_blocks` blocks at once: (uint8 [n, block_size] zero-padded, sizes int32 [n]) or None."""

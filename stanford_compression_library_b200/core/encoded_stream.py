@@ -91,14 +91,35 @@ class EncodedBlockReader:
         padded.frombytes(payload_bytes)
         return Padder.remove_byte_padding(padded)
 
-    def get_encoded_blocks(self, device="cuda"):
-        """Read ALL remaining blocks and hand them to the device as one `EncodedBlocks`
-        (bit offsets point straight into the file image: no per-block host work beyond the header walk)."""
+    def get_encoded_blocks(self, device="cuda", max_blocks: int = None):
+        """Read up to `max_blocks` of the remaining blocks (default: all of them) and hand them to the device as one
+        `EncodedBlocks` (bit offsets point straight into the file image: no per-block host work beyond the header
+        walk).  Returns None at the end of the file."""
         import torch
 
         from ..device import EncodedBlocks
 
-        raw = np.frombuffer(self.file_reader.read(), dtype=np.uint8)
+        if max_blocks is None:
+            raw = np.frombuffer(self.file_reader.read(), dtype=np.uint8)
+            if raw.size == 0:
+                return None
+        else:
+            # walk the headers of the next `max_blocks` records without reading more of the file than they span
+            start = self.file_reader.tell()
+            pos, n = start, 0
+            while n < max_blocks:
+                self.file_reader.seek(pos)
+                hb = self.file_reader.read(HeaderHandler.NUM_HEADER_BYTES)
+                if len(hb) == 0:
+                    break
+                assert len(hb) == HeaderHandler.NUM_HEADER_BYTES, "truncated encoded file"
+                pos += HeaderHandler.NUM_HEADER_BYTES + HeaderHandler.get_payload_size(hb)
+                n += 1
+            if n == 0:
+                return None
+            self.file_reader.seek(start)
+            raw = np.frombuffer(self.file_reader.read(pos - start), dtype=np.uint8)
+            assert raw.size == pos - start, "truncated encoded file"
         offs, lens, pos = [], [], 0
         while pos < raw.size:
             size = int.from_bytes(raw[pos : pos + 4].tobytes(), "big")

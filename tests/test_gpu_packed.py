@@ -210,3 +210,73 @@ def test_rans_cfg5_shard_shape_packed_vs_oracle(kw):
     e = enc.encode_blocks(data).check()
     want = e.pack()
     assert torch.equal(want.buf[:total], p.buf[:total]) and torch.equal(want.byte_offset, p.byte_offset)
+
+
+@pytest.mark.parametrize("name", ["rans_default", "tans", "range"])
+def test_stream_level_encode_decode_are_batched_and_byte_identical(name, tmp_path):
+    """DataEncoder.encode / DataDecoder.decode (data_encoder_decoder.py:56-69, 131-144) on a byte file that spans
+    several batches on BOTH legs: the batched loops (one fused, framed launch per `blocks_per_batch` blocks) write
+    exactly the bytes of the reference's block-at-a-time loop, and read them back; so do the bounded
+    encode_uint8_file / decode_uint8_file helpers."""
+    from stanford_compression_library_b200.compressors._gpu_base import decode_uint8_file, encode_uint8_file
+    from stanford_compression_library_b200.core.data_stream import Uint8FileDataStream
+    from stanford_compression_library_b200.core.encoded_stream import EncodedBlockReader, EncodedBlockWriter
+    from stanford_compression_library_b200.workloads import zipf_probabilities
+
+    rng = np.random.default_rng(17)
+    raw = rng.choice(256, size=53 * 1000 + 123, p=np.array(zipf_probabilities())).astype(np.uint8).tobytes()
+    src = tmp_path / "in.bin"
+    src.write_bytes(raw)
+    enc, dec = _codec(name)
+    outs = {}
+    for tag, per_batch in (("loop", 1), ("batched", 7)):
+        enc.blocks_per_batch = per_batch
+        path = str(tmp_path / ("enc_%s.bin" % tag))
+        with Uint8FileDataStream(str(src), "rb") as fds, EncodedBlockWriter(path) as w:
+            enc.encode(fds, block_size=1000, encode_writer=w)
+        outs[tag] = open(path, "rb").read()
+    assert outs["loop"] == outs["batched"] and len(outs["loop"]) > 0
+    path2 = str(tmp_path / "enc_file_api.bin")
+    encode_uint8_file(enc, str(src), path2, block_size=1000, blocks_per_batch=11)
+    assert open(path2, "rb").read() == outs["loop"]
+    for tag, per_batch in (("loop", 1), ("batched", 5)):
+        dec.blocks_per_batch = per_batch
+        back = str(tmp_path / ("dec_%s.bin" % tag))
+        with EncodedBlockReader(path2) as r, Uint8FileDataStream(back, "wb") as ods:
+            dec.decode(r, ods)
+        assert open(back, "rb").read() == raw
+    back = str(tmp_path / "dec_file_api.bin")
+    decode_uint8_file(dec, path2, back, block_size=1000, blocks_per_batch=9)
+    assert open(back, "rb").read() == raw
+
+
+def test_stream_level_encode_text_symbols_batched(tmp_path):
+    """the batched loop with a non-byte alphabet (characters): symbols are mapped to bytes per batch"""
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.core.data_stream import TextFileDataStream
+    from stanford_compression_library_b200.core.encoded_stream import EncodedBlockReader, EncodedBlockWriter
+
+    rng = np.random.default_rng(3)
+    text = "".join(rng.choice(list("abcde \n"), size=4321, p=[0.3, 0.2, 0.15, 0.1, 0.1, 0.1, 0.05]))
+    src = tmp_path / "t.txt"
+    src.write_text(text)
+    params = rANSParams(Frequencies({"a": 30, "b": 20, "c": 15, "d": 10, "e": 10, " ": 10, "\n": 5}))
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    outs = {}
+    for tag, per_batch in (("loop", 1), ("batched", 4)):
+        enc.blocks_per_batch = per_batch
+        path = str(tmp_path / ("t_%s.bin" % tag))
+        with TextFileDataStream(str(src), "r") as fds, EncodedBlockWriter(path) as w:
+            enc.encode(fds, block_size=500, encode_writer=w)
+        outs[tag] = open(path, "rb").read()
+    assert outs["loop"] == outs["batched"]
+    dec.blocks_per_batch = 3
+    back = str(tmp_path / "t_back.txt")
+    with EncodedBlockReader(str(tmp_path / "t_batched.bin")) as r, TextFileDataStream(back, "w") as ods:
+        dec.decode(r, ods)
+    assert open(back).read() == text
+    with pytest.raises(KeyError):  # a character outside the alphabet: the reference's freq_dict[s] KeyError
+        (tmp_path / "bad.txt").write_text("abcz")
+        with TextFileDataStream(str(tmp_path / "bad.txt"), "r") as fds, EncodedBlockWriter(str(tmp_path / "bad.bin")) as w:
+            enc.encode(fds, block_size=500, encode_writer=w)
