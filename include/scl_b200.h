@@ -69,9 +69,10 @@ extern "C" {
 /* frequency models for the arithmetic coder (scl/compressors/probability_models.py) */
 #define SCL_MODEL_FIXED 0        /* FixedFreqModel        :57-67 */
 #define SCL_MODEL_ADAPTIVE_IID 1 /* AdaptiveIIDFreqModel  :70-92 */
-#define SCL_MODEL_ORDER_K 2      /* AdaptiveOrderKFreqModel :95-168, order = scl_params.model_order; this backend
-                                    keeps the table in shared memory: n_sym^k * (n_sym + 1) <= 1600 words
-                                    (else SCL_E_UNSUPPORTED) */
+#define SCL_MODEL_ORDER_K 2      /* AdaptiveOrderKFreqModel :95-168, order = scl_params.model_order.  The table of a block
+                                    lives in shared memory while n_sym^k * (n_sym + 1) <= 1600 words; larger ones (a byte
+                                    alphabet at k = 1) are worked on in place in HBM -- d_model is then mandatory --
+                                    for up to n_sym^k = 512 contexts (else SCL_E_UNSUPPORTED) */
 
 typedef struct scl_coder scl_coder; /* opaque: parameters + device tables */
 
@@ -215,6 +216,12 @@ int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *d
  * chosen by batch size); 0 = default.  Keeps every code path parity-tested.  Set it before issuing
  * work on the handle; it is read at launch time. */
 void scl_coder_debug_path(scl_coder *c, int mode);
+
+/* Diagnostic hook, per handle: with a device buffer of n_words uint64 (>= SMs * 32 * 40, zeroed by the caller) the
+ * fused packed encoder leaves per-warp timestamps there (%globaltimer, ns): start, the end of each coding round,
+ * and the copy pool's task count / first start / last end / busy and waiting time (tools/trace_packed.py prints
+ * the timeline).  NULL switches it off (the default); the kernels test one pointer per round, nothing per symbol. */
+void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words);
 
 const char *scl_last_cuda_error(void);
 const char *scl_version(void);

@@ -94,8 +94,10 @@ class _AecCoder(GpuCoderBase):
         return self.device_coder().decode_blocks(enc, max_block_len, model=self._batch_model(enc.n_blocks), out=out, reuse=reuse)
 
     def _batch_model(self, n_blocks):
-        table = self.freq_model._to_table()
-        if table[-1] == 0 and all(v == 1 for v in table[:-1]):
+        m = self.freq_model
+        in_hbm = len(m.alphabet) ** m.k * (len(m.alphabet) + 1) > 1600  # csrc kAecCtxMaxWords: the table is the lanes' working storage
+        table = m._to_table()
+        if not in_hbm and table[-1] == 0 and all(v == 1 for v in table[:-1]):
             return None  # untouched model: the kernels start from all ones / context 0 themselves
         return self._model_tensor(n_blocks)
 

@@ -59,8 +59,10 @@ class AdaptiveOrderKFreqModel(FreqModelBase):
     """Order-k context model (probability_models.py:95-168): counts of (k+1)-tuples, all ones at
     the start, the past k symbols (as alphabet indices, initially all 0) select the row used for the
     next symbol.  Same attributes as the reference (`freqs_kplus1_tuple`, `past_k`, `freqs_current`).
-    On the device the whole table lives in shared memory, one copy per block being coded
-    (csrc/scl_aec.cuh AecCtxPolicy), so len(alphabet)^k * (len(alphabet) + 1) must be <= 1600.
+    On the device the table of one block lives in shared memory while len(alphabet)^k * (len(alphabet) + 1)
+    <= 1600 words (csrc/scl_aec.cuh AecCtxPolicy); larger tables -- a byte alphabet at k = 1 is 65 536 counters --
+    stay in HBM, one copy per block being coded, with only the row totals in shared memory (AecCtxGlobalPolicy;
+    len(alphabet)^k <= 512 contexts).
 
     As in the reference there is no halving that works: when one count reaches
     max_allowed_total_freq the reference's `np.max(count // 2, 1)` raises; here the coder raises

@@ -19,6 +19,12 @@
 
 #include "scl_fast.cuh"
 
+#ifndef __CUDACC__
+struct ulonglong2 {
+    unsigned long long x, y;
+};
+#endif
+
 namespace scl {
 
 constexpr uint32_t kAecModelWords = 8 + 128;  // G[16] + C[256] as u16 pairs
@@ -249,6 +255,64 @@ struct AecCtxPolicy {
         for (uint32_t i = 0; i < n_ctx * n_sym; ++i) model[i] = word(i);
         model[n_ctx * n_sym] = ctx;
     }
+};
+
+// The same model when the table does not fit shared memory (a byte alphabet at k = 1 is 256 rows of 256 counters):
+// the lane works IN PLACE on its block's model table in HBM -- the uint64 [n_ctx * n_sym counts][context] table of
+// the C-ABI (scl_coder_model_words), which therefore must be supplied -- and only the n_ctx row totals live in
+// shared memory (`tot`, one word per row, [row][lane] interleave like every per-lane structure here).  Cumulative
+// counts are linear scans of the current row, two counters per 16-byte load (an L2-resident row at the batch
+// sizes this is meant for).  Counts are taken modulo 2^32 (a count >= max_allowed_total_freq <= 2^30 has already
+// made the coder stop, as the reference does).
+struct AecCtxGlobalPolicy {
+    uint64_t *tab;  // this block's table
+    saddr_t tot;    // row totals: row r at tot + r * tstride
+    uint32_t tstride, n_sym, n_ctx, ctx, max_total;
+    SCL_HD uint32_t total() const { return lds32(tot + (saddr_t)(ctx * tstride)); }
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const {
+        const uint64_t *row = tab + (uint64_t)ctx * n_sym;
+        uint32_t c = 0, j = 0;
+        if (((((uintptr_t)row) & 15) == 0)) {
+            for (; j + 2 <= idx; j += 2) {
+                const ulonglong2 v = *(const ulonglong2 *)(row + j);
+                c += (uint32_t)v.x + (uint32_t)v.y;
+            }
+        }
+        for (; j < idx; ++j) c += (uint32_t)row[j];
+        cum = c;
+        f = (uint32_t)row[idx];
+    }
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        const uint64_t *row = tab + (uint64_t)ctx * n_sym;
+        uint32_t idx = 0, below = 0;
+        f = (uint32_t)row[0];
+        while (idx + 1 < n_sym && below + f <= v) {  // inclusive prefix <= v: the symbol lies further right
+            below += f;
+            idx += 1;
+            f = (uint32_t)row[idx];
+        }
+        cum = below;
+        return idx;
+    }
+    SCL_HD uint32_t update(uint32_t idx) {
+        uint64_t *at = tab + (uint64_t)ctx * n_sym + idx;
+        const uint64_t cnt = *at + 1;
+        *at = cnt;
+        const saddr_t tw = tot + (saddr_t)(ctx * tstride);
+        sts32(tw, lds32(tw) + 1);
+        ctx = (uint32_t)(((uint64_t)ctx * n_sym + idx) % n_ctx);
+        return cnt >= max_total ? SCL_ST_TOTAL_FREQ : SCL_ST_OK;
+    }
+    SCL_HD void load() {  // row totals from the table, context from its last word
+        for (uint32_t r = 0; r < n_ctx; ++r) {
+            const uint64_t *row = tab + (uint64_t)r * n_sym;
+            uint32_t sum = 0;
+            for (uint32_t j = 0; j < n_sym; ++j) sum += (uint32_t)row[j];
+            sts32(tot + (saddr_t)(r * tstride), sum);
+        }
+        ctx = (uint32_t)(tab[(uint64_t)n_ctx * n_sym] % n_ctx);
+    }
+    SCL_HD void store() const { tab[(uint64_t)n_ctx * n_sym] = ctx; }
 };
 
 // ---- closed-form renormalisation ------------------------------------------------------------

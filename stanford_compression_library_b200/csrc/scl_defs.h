@@ -80,10 +80,12 @@ struct alignas(16) AecTab {
     uint8_t idx2sym[256];
 };
 constexpr uint32_t kAecCtxMaxWords = 1600;  // order-k model: n_ctx * (n_sym + 1) words per lane = 200 KB of shared memory per warp
+constexpr uint32_t kAecCtxGlobalMaxRows = 512;  // larger tables stay in HBM (AecCtxGlobalPolicy); their row totals: 64 KB of shared memory per warp
 struct AecConst {
     uint32_t P, DBSB, n_sym, model;
     uint64_t max_total;      // FreqModelBase.max_allowed_total_freq
     uint32_t order_k, n_ctx; // AdaptiveOrderKFreqModel: k and n_sym^k (1 for the other models)
+    uint32_t ctx_global;     // order-k table too large for shared memory: the lanes work on the caller's model table in HBM
 };
 
 }  // namespace scl

@@ -226,7 +226,15 @@ struct PackedOut {
     uint64_t *byte_off;      // [n_blocks + 1] record offsets, [n_blocks] = total
     uint64_t *cta_state;     // [rounds * gridDim.x] look-back words, zeroed before the launch
     uint32_t framed;
+    uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
 };
+constexpr uint32_t kTraceWords = 40;  // per warp: [0] start, [1 + r] end of coding round r (r < 19), [20] tasks copied, [21] first copy
+                                      // start, [22] last copy end, [23] ns spent copying, [24] ns spent waiting for a resolved round
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 struct PackCtl {  // per CTA, shared memory
     unsigned long long warp_tot[2][kMaxWarps];   // [round & 1] record bytes of each coding warp's task
     unsigned long long warp_excl[2][kMaxWarps];  // [round & 1] byte offset of each task in dst, valid once `resolved` > round
@@ -290,9 +298,13 @@ __device__ __forceinline__ void packed_copy_pool(PackCtl &ctl, const BlockIo &io
         const uint32_t r = T / W, slot = T - r * W;
         const uint64_t task = (uint64_t)r * total_warps + blockIdx.x * W + slot;
         if (task >= n_tasks) return;  // tickets run through the rounds in order: nothing valid after the first invalid one
+        uint64_t *tr = po.trace ? po.trace + ((uint64_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * kTraceWords : nullptr;
+        uint64_t t0 = 0, t1 = 0;
         if (lane == 0) {
+            if (tr) t0 = globaltimer_ns();
             const volatile uint32_t *res = &ctl.resolved;
             while (*res <= r) __nanosleep(200);
+            if (tr) t1 = globaltimer_ns();
         }
         __syncwarp();
         __threadfence_block();
@@ -305,6 +317,14 @@ __device__ __forceinline__ void packed_copy_pool(PackCtl &ctl, const BlockIo &io
         if (lane == 0) {
             __threadfence_block();
             atomicAdd(&ctl.copy_done, 1u);
+            if (tr) {
+                const uint64_t t2 = globaltimer_ns();
+                if (tr[20] == 0) tr[21] = t1;
+                tr[20] += 1;
+                tr[22] = t2;
+                tr[23] += t2 - t1;
+                tr[24] += t1 - t0;
+            }
         }
     }
 }
@@ -351,6 +371,7 @@ __global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 
     uint32_t tile_seq = 0;  // tiles consumed by this warp so far (selects stage and mbarrier parity)
     const uint32_t swz = (lane >> 1) & 3;
 
+    if (PACKED && po.trace && lane == 0) po.trace[((uint64_t)blockIdx.x * 32 + warp) * kTraceWords] = globaltimer_ns();
     uint32_t round = 0;
     // a copy warp (PACKED, warp >= W) has no tasks: it goes straight to the pool below
     for (uint32_t task = (PACKED && warp >= W) ? n_tasks : blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
@@ -423,6 +444,7 @@ __global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 
         if (PACKED) {
             // (i) this task's total; (ii) arrive at the CTA's round; the last warp to arrive resolves the round
             const uint32_t T = __reduce_add_sync(0xffffffffu, rec_bytes);
+            if (po.trace && lane == 0 && round < 19) po.trace[((uint64_t)blockIdx.x * 32 + warp) * kTraceWords + 1 + round] = globaltimer_ns();
             const uint32_t first = round * total_warps + blockIdx.x * W;  // first task of this CTA's round
             const uint32_t nvalid = n_tasks - first < W ? n_tasks - first : W;
             const uint32_t par = round & 1;
@@ -1046,6 +1068,64 @@ __global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_decode_kernel(co
     io.status[b] = st;
 }
 
+// The order-k model with its table in HBM (AecCtxGlobalPolicy): one warp per CTA-slot of 32 blocks, the lanes'
+// row totals in shared memory ([row][lane]); `model` is mandatory and is the table itself.
+constexpr uint32_t kAecCtxGlobalWarps = 2;
+__device__ __forceinline__ AecCtxGlobalPolicy aec_ctx_global_setup(uint8_t *smem, const AecConst &c, uint64_t *my_model) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AecCtxGlobalPolicy pol;
+    pol.tab = my_model;
+    pol.tot = saddr_of(smem + warp * (c.n_ctx * 128)) + lane * 4;
+    pol.tstride = 128;
+    pol.n_sym = c.n_sym;
+    pol.n_ctx = c.n_ctx;
+    pol.ctx = 0;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    return pol;
+}
+
+__global__ void __launch_bounds__(kAecCtxGlobalWarps * 32) aec_ctx_global_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    AecCtxGlobalPolicy pol = aec_ctx_global_setup(s_dyn, c, model + b * ((uint64_t)c.n_ctx * c.n_sym + 1));
+    pol.load();
+    uint64_t bits = 0;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    pol.store();
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kAecCtxGlobalWarps * 32) aec_ctx_global_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io, uint64_t *model) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    stage_table(&s_tab, g_tab, sizeof(AecTab), &mbar);
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    AecCtxGlobalPolicy pol = aec_ctx_global_setup(s_dyn, c, model + b * ((uint64_t)c.n_ctx * c.n_sym + 1));
+    pol.load();
+    uint64_t used = 0;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    pol.store();
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
 // ------------------------------------------------------------------------------------------------
 // stream packing: bit-granular copy of each block's stream to a byte-aligned destination (scl_pack.cuh)
 // ------------------------------------------------------------------------------------------------
@@ -1198,6 +1278,8 @@ struct scl_coder {
     // test hook (scl_coder_debug_path): 1 = first-generation kernels, 2 = v2 decode with per-lane sector stores,
     // 3 / 4 = v2 decode always / never in the pipe-balanced form.  Per handle: no process-global state.
     int debug_mode = 0;
+    uint64_t *d_trace = nullptr;  // scl_coder_debug_trace
+    uint64_t trace_words = 0;
 };
 
 static thread_local char g_cuda_err[256] = "";
@@ -1443,6 +1525,12 @@ extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
     if (c) c->debug_mode = mode;
 }
 static inline bool force_v1(const scl_coder *c) { return c->debug_mode == 1; }
+extern "C" void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words) {
+    if (c) {
+        c->d_trace = d_trace;
+        c->trace_words = n_words;
+    }
+}
 
 static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
     size_t avail = 227 * 1024 - 1024 - fixed;  // 227 KiB per CTA minus slack for static smem / barriers
@@ -1473,6 +1561,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     PackedOut po{};
     if (packed) {
         po = *packed;
+        po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
         const uint64_t rounds = (n_tasks + (uint64_t)grid * warps - 1) / ((uint64_t)grid * warps);
         cudaError_t e = cudaMemsetAsync(po.cta_state, 0, rounds * grid * sizeof(uint64_t), s);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
@@ -1622,6 +1711,14 @@ static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t
         range_encode_kernel<<<grid, kThreads, 0, s>>>(c->d_range, c->range->c, io);
         return check_launch("range_encode_kernel");
     }
+    if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K && c->aec->c.ctx_global) {
+        if (!d_model) return SCL_E_INVALID;  // the table is the lanes' working storage
+        const uint32_t g2 = (uint32_t)((n_blocks + kAecCtxGlobalWarps * 32 - 1) / (kAecCtxGlobalWarps * 32));
+        const size_t smem = (size_t)kAecCtxGlobalWarps * c->aec->c.n_ctx * 128;
+        SCL_CUDA(cudaFuncSetAttribute(aec_ctx_global_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aec_ctx_global_encode_kernel<<<g2, kAecCtxGlobalWarps * 32, smem, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_ctx_global_encode_kernel");
+    }
     if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K) {
         const uint32_t warps = aec_ctx_warps(c->aec->c);
         uint32_t g2 = (uint32_t)((n_blocks + warps * 32 - 1) / (warps * 32));
@@ -1695,7 +1792,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);
@@ -1758,6 +1855,14 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         SCL_CUDA(cudaFuncSetAttribute(range_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->range_lut_bytes));
         range_decode_kernel<<<grid, kThreads, c->range_lut_bytes, s>>>(c->d_range, c->d_range_lut, c->range_lut_bytes, c->range->c, io);
         return check_launch("range_decode_kernel");
+    }
+    if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K && c->aec->c.ctx_global) {
+        if (!d_model) return SCL_E_INVALID;
+        const uint32_t g2 = (uint32_t)((n_blocks + kAecCtxGlobalWarps * 32 - 1) / (kAecCtxGlobalWarps * 32));
+        const size_t smem = (size_t)kAecCtxGlobalWarps * c->aec->c.n_ctx * 128;
+        SCL_CUDA(cudaFuncSetAttribute(aec_ctx_global_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aec_ctx_global_decode_kernel<<<g2, kAecCtxGlobalWarps * 32, smem, s>>>(c->d_aec, c->aec->c, io, d_model);
+        return check_launch("aec_ctx_global_decode_kernel");
     }
     if (c->aec && c->aec->c.model == SCL_MODEL_ORDER_K) {
         const uint32_t warps = aec_ctx_warps(c->aec->c);

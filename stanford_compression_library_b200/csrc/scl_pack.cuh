@@ -137,10 +137,28 @@ __device__ __forceinline__ void st_plain128(uint8_t *p, const uint4 &v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int W0, int U>
-__device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uint32_t sh, uint8_t *__restrict__ dd, uint32_t n_chunks, uint32_t lane) {
+// chunk batches of one stream; `first_batch_hook` runs after the FIRST batch's loads have been issued and before
+// anything waits for them (the caller parks its own independent loads' consumers there)
+template <int W0, int U, class Hook>
+__device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uint32_t sh, uint8_t *__restrict__ dd, uint32_t n_chunks, uint32_t lane,
+                                                Hook first_batch_hook) {  // n_chunks >= 1
     const uint32_t last = n_chunks - 1;
-    for (uint32_t c0 = lane; c0 < n_chunks; c0 += 32 * U) {
+    {   // first batch: every lane takes part (clamped indices), the hook sits between its loads and its stores
+        uint4 A[U], B[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t ch = min(lane + 32 * u, last);
+            A[u] = ld_plain128(a + ch);
+            B[u] = ld_plain128(a + ch + 1);
+        }
+        first_batch_hook();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t ch = lane + 32 * u;
+            if (ch < n_chunks) st_plain128(dd + 16 * ch, pack_chunk_from_pair<W0>(A[u], B[u], sh));
+        }
+    }
+    for (uint32_t c0 = lane + 32 * U; c0 < n_chunks; c0 += 32 * U) {
         uint4 A[U], B[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {  // all 2U loads first (a clamped index instead of a predicate keeps them unconditional)
@@ -171,20 +189,32 @@ __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ 
     if (FRAMED && 8 * head < lead) head += 16;
     if (head > payload_bytes) head = payload_bytes;
     const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
-    for (uint64_t i = lane; i < head; i += 32) d[i] = (uint8_t)pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, i);
-    if (n_chunks) {
-        const uint64_t S0 = off + 8 * head - lead;  // source bit of chunk 0's first bit; chunk ch starts 128 * ch bits later
-        const uint4 *a = (const uint4 *)src + (S0 >> 7);
-        const uint32_t sh = (uint32_t)(S0 & 31);
-        switch ((uint32_t)(S0 >> 5) & 3u) {  // the same for every lane: no divergence
-        case 0: pack_chunks_a16<0, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
-        case 1: pack_chunks_a16<1, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
-        case 2: pack_chunks_a16<2, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
-        default: pack_chunks_a16<3, U>(a, sh, d + head, (uint32_t)n_chunks, lane); break;
-        }
+    // The bytes before the first and after the last whole chunk (< 32 each, one per lane) are independent of the
+    // chunks: their loads go out first, their stores wait in the hook until the first chunk batch is in flight, so
+    // a stream costs one or two memory latencies, not four.
+    const uint64_t tail0 = head + 16 * n_chunks;
+    const bool has_head = lane < head, has_tail = tail0 + lane < payload_bytes;
+    uint32_t hv = 0, tv = 0;
+    if (has_head) hv = pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, lane);
+    if (has_tail) tv = pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, tail0 + lane);
+    auto edges = [&]() {
+        if (has_head) d[lane] = (uint8_t)hv;
+        if (has_tail) d[tail0 + lane] = (uint8_t)tv;
+    };
+    if (n_chunks == 0) {
+        edges();
+        return;
     }
-    for (uint64_t i = head + 16 * n_chunks + lane; i < payload_bytes; i += 32)
-        d[i] = (uint8_t)pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, i);
+    const uint64_t S0 = off + 8 * head - lead;  // source bit of chunk 0's first bit; chunk ch starts 128 * ch bits later
+    const uint4 *a = (const uint4 *)src + (S0 >> 7);
+    const uint32_t sh = (uint32_t)(S0 & 31);
+    switch ((uint32_t)(S0 >> 5) & 3u) {  // the same for every lane: no divergence
+    case 0: pack_chunks_a16<0, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
+    case 1: pack_chunks_a16<1, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
+    case 2: pack_chunks_a16<2, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
+    default: pack_chunks_a16<3, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
+    }
+    // (head <= 31 and the tail is < 32 bytes -- 16 left over plus a partial chunk -- so one byte per lane covers both)
 }
 
 // ---- decoupled look-back ----------------------------------------------------------------------------------

@@ -306,12 +306,15 @@ struct AecHost {
         if (p.model != SCL_MODEL_ORDER_K && p.model_order != 0) return SCL_E_INVALID;
         c.order_k = p.model_order;
         c.n_ctx = 1;
-        if (p.model == SCL_MODEL_ORDER_K) {  // per-lane table in shared memory: n_sym^k * (n_sym + 1) words
+        c.ctx_global = 0;
+        if (p.model == SCL_MODEL_ORDER_K) {
+            // per-lane table of n_sym^k * (n_sym + 1) words in shared memory when it fits; else the lanes work on the
+            // caller's table in HBM with the row totals in shared memory (n_sym^k <= kAecCtxGlobalMaxRows rows)
             for (uint32_t j = 0; j < p.model_order && n_sym > 1; ++j) {
+                if ((uint64_t)c.n_ctx * n_sym > kAecCtxGlobalMaxRows) return SCL_E_UNSUPPORTED;
                 c.n_ctx *= n_sym;
-                if ((uint64_t)c.n_ctx * (n_sym + 1) > kAecCtxMaxWords) return SCL_E_UNSUPPORTED;
             }
-            if ((uint64_t)c.n_ctx * (n_sym + 1) > kAecCtxMaxWords) return SCL_E_UNSUPPORTED;
+            c.ctx_global = (uint64_t)c.n_ctx * (n_sym + 1) > kAecCtxMaxWords ? 1u : 0u;
         }
         memset(&t, 0, sizeof(t));
         for (uint32_t i = 0; i < n_sym; ++i) {

@@ -251,6 +251,12 @@ class DeviceCoder:
         3 / 4 = v2 decode always / never pipe-balanced, 0 = default.  Per handle."""
         _cabi.lib().scl_coder_debug_path(self._h, int(mode))
 
+    def debug_trace(self, trace: torch.Tensor = None):
+        """Diagnostic hook (scl_coder_debug_trace): an int64 device tensor of >= SMs * 32 * 40 zeros receives the fused
+        packed encoder's per-warp timestamps; None switches it off.  Keep the tensor alive while it is set."""
+        self._trace = trace
+        _cabi.lib().scl_coder_debug_trace(self._h, _ptr(trace), 0 if trace is None else trace.numel())
+
     def decode_blocks(self, enc: EncodedBlocks, max_block_len: int, model=None, out=None, reuse: DecodedBlocks = None) -> DecodedBlocks:
         B = enc.n_blocks
         if reuse is not None:

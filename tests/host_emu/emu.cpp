@@ -173,6 +173,17 @@ static AecCtxPolicy make_ctx_policy(uint32_t *words, const AecConst &c) {
     pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
     return pol;
 }
+static AecCtxGlobalPolicy make_ctx_global_policy(uint32_t *totals, const AecConst &c, uint64_t *table) {
+    AecCtxGlobalPolicy pol;
+    pol.tab = table;
+    pol.tot = saddr_of(totals);
+    pol.tstride = 4;
+    pol.n_sym = c.n_sym;
+    pol.n_ctx = c.n_ctx;
+    pol.ctx = 0;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    return pol;
+}
 extern "C" {
 int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const uint32_t *sizes, uint32_t block_len, uint64_t n_blocks,
                       uint8_t *out, uint64_t out_stride, uint64_t *bit_off, uint64_t *bit_len, uint64_t *model, uint32_t *status) {
@@ -204,6 +215,13 @@ int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const ui
             w.init(slot, slot + out_stride);
             if (e->range) {
                 st = range_encode_lane(e->range->t, e->range->c, row, sym_stride, n, w, bits);
+            } else if (e->aec->c.model == SCL_MODEL_ORDER_K && e->aec->c.ctx_global) {
+                if (!model) return SCL_E_INVALID;
+                std::vector<uint32_t> totals(e->aec->c.n_ctx);
+                AecCtxGlobalPolicy pol = make_ctx_global_policy(totals.data(), e->aec->c, model + b * e->aec->model_words());
+                pol.load();
+                st = aec2_encode_lane(pol, e->aec->t, e->aec->c, row, sym_stride, n, w, bits);
+                pol.store();
             } else if (e->aec->c.model == SCL_MODEL_ORDER_K) {
                 alignas(16) uint32_t words[kAecCtxMaxWords];
                 AecCtxPolicy pol = make_ctx_policy(words, e->aec->c);
@@ -253,6 +271,13 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
             if (st == SCL_ST_OK && used > avail) st = SCL_ST_TRUNCATED;
         } else if (e->range) {
             st = range_decode_lane(e->range->t, e->range->c, e->range->lut.data(), r, avail, row, sym_stride, size, used);
+        } else if (e->aec->c.model == SCL_MODEL_ORDER_K && e->aec->c.ctx_global) {
+            if (!model) return SCL_E_INVALID;
+            std::vector<uint32_t> totals(e->aec->c.n_ctx);
+            AecCtxGlobalPolicy pol = make_ctx_global_policy(totals.data(), e->aec->c, model + b * e->aec->model_words());
+            pol.load();
+            st = aec2_decode_lane(pol, e->aec->t, e->aec->c, r, avail, row, sym_stride, size, used);
+            pol.store();
         } else if (e->aec->c.model == SCL_MODEL_ORDER_K) {
             alignas(16) uint32_t words[kAecCtxMaxWords];
             AecCtxPolicy pol = make_ctx_policy(words, e->aec->c);

@@ -416,8 +416,65 @@ def test_aec_order_k_count_limit_and_table_limit():
     with pytest.raises(AssertionError):  # a count reaches 20: the reference's update_model raises (probability_models.py:164-168)
         enc.encode_block(DataBlock([0] * 40))
     enc = ArithmeticEncoder(params, AdaptiveOrderKFreqModel(list(range(40)), 1, params.MAX_ALLOWED_TOTAL_FREQ))
-    with pytest.raises(NotImplementedError):  # 40 * 41 words per block do not fit shared memory
+    enc.encode_block(DataBlock([0, 1, 2]))  # 40 * 41 words do not fit shared memory: the table stays in HBM
+    enc = ArithmeticEncoder(params, AdaptiveOrderKFreqModel(list(range(23)), 2, params.MAX_ALLOWED_TOTAL_FREQ))
+    with pytest.raises(NotImplementedError):  # 529 contexts: more than the 512 rows of totals kept in shared memory
         enc.encode_block(DataBlock([0, 1, 2]))
+
+
+def _orderk_large_cases():
+    import json
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orderk_large_v1.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    out = []
+    for c in meta["cases"]:
+        c = dict(c)
+        c["data"], c["enc"], c["final"] = z["c%d_data" % c["id"]], z["c%d_enc" % c["id"]], z["c%d_final" % c["id"]]
+        out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("c", _orderk_large_cases(), ids=lambda c: "%d-%s" % (c["id"], c["note"][:34].replace(" ", "_")))
+def test_aec_order_k_large_tables_match_reference_golden(c):
+    """AdaptiveOrderKFreqModel over a BYTE alphabet at k = 1 (and other tables too large for shared memory), on the
+    device, against vectors from the unmodified reference (oracle/gen_golden_orderk_large.py; probability_models.py:95-160):
+    bits, num_bits_consumed on stream + garbage, the model object's final counts and context -- through the drop-in
+    classes; then a batch of blocks, each from its own copy of the model, against the oracle."""
+    from stanford_compression_library_b200 import BitArray, DataBlock
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveOrderKFreqModel
+
+    n_sym, k, p = len(c["freqs"]), c["model"]["k"], c["params"]
+    params = AECParams(DATA_BLOCK_SIZE_BITS=p["DATA_BLOCK_SIZE_BITS"], PRECISION=p["PRECISION"])
+    enc = ArithmeticEncoder(params, AdaptiveOrderKFreqModel(list(range(n_sym)), k, c["model"]["max_total"]))
+    dec = ArithmeticDecoder(params, AdaptiveOrderKFreqModel(list(range(n_sym)), k, c["model"]["max_total"]))
+    want_final = c["final"].astype(np.int64).tolist() + [c["model"]["final_ctx"]]
+    ba = enc.encode_block(DataBlock(c["data"].tolist()))
+    assert len(ba) == c["nbits"] and ba.tobytes() == c["enc"].tobytes()
+    assert enc.freq_model._to_table() == want_final
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    block, used = dec.decode_block(BitArray.from_packed(packed, total))
+    assert block.data_list == c["data"].tolist() and used == c["consumed"]
+    assert dec.freq_model._to_table() == want_final
+    # batched: B blocks, each starting from a copy of a fresh model
+    B, N = 40, min(300, max(8, c["n"]))
+    rng = np.random.default_rng(c["id"])
+    host = rng.integers(0, n_sym, size=(B, N)).astype(np.uint8)
+    host[:, 1::2] = host[:, 0::2][:, : host[:, 1::2].shape[1]]  # repeated symbols: contexts matter
+    enc2 = ArithmeticEncoder(params, AdaptiveOrderKFreqModel(list(range(n_sym)), k, c["model"]["max_total"]))
+    dec2 = ArithmeticDecoder(params, AdaptiveOrderKFreqModel(list(range(n_sym)), k, c["model"]["max_total"]))
+    data = torch.from_numpy(host).cuda()
+    e = enc2.encode_blocks(data).check()
+    d = dec2.decode_blocks(e, N).check()
+    assert torch.equal(d.symbols[:, :N], data)
+    oracle = so.Oracle.aec([1] * n_sym, DATA_BLOCK_SIZE_BITS=p["DATA_BLOCK_SIZE_BITS"], PRECISION=p["PRECISION"], model=so.MODEL_ORDER_K, k=k,
+                           max_allowed_total_freq=c["model"]["max_total"])
+    fresh = np.array([1] * (n_sym ** (k + 1)) + [0], dtype=np.uint64)
+    for b in (0, 1, B - 1):
+        ref, ref_bits = oracle.encode_block(host[b], model_freq=fresh.copy())
+        assert int(e.bit_len[b]) == ref_bits and e.block(b).tobytes() == ref.tobytes()
 
 
 @pytest.mark.parametrize("coder", ["rans_default", "rans_nbo8", "range", "aec"])

@@ -519,7 +519,8 @@ def test_emu_aec2_vs_oracle_random(seed):
 
 
 # ---- order-k context model (csrc/scl_aec.cuh AecCtxPolicy) ------------------------------------
-@pytest.mark.parametrize("n_sym,k", [(1, 2), (2, 0), (2, 1), (2, 7), (3, 3), (4, 2), (7, 1), (16, 1), (39, 1), (256, 0)])
+@pytest.mark.parametrize("n_sym,k", [(1, 2), (2, 0), (2, 1), (2, 7), (3, 3), (4, 2), (7, 1), (16, 1), (39, 1), (256, 0),
+                                     (40, 1), (16, 2), (2, 9), (256, 1)])  # second row: tables kept in HBM (AecCtxGlobalPolicy)
 def test_emu_order_k_vs_oracle_random(n_sym, k):
     """two consecutive batches through the same model tables (the reference's model object is never
     reset between encode_block calls), every stream and every final table against the oracle"""
@@ -576,11 +577,62 @@ def test_emu_order_k_table_size_limit():
                         model=_cabi.MODEL_ORDER_K, model_order=k, max_allowed_total_freq=1 << 30)
         return EmuCoder(prm, None, [1] * n_sym)
 
-    make(3, 5)  # 243 * 4 = 972 words
-    make(39, 1)  # 39 * 40 = 1560 words
-    for n_sym, k in ((40, 1), (3, 6), (2, 10), (256, 1)):
+    make(3, 5)  # 243 * 4 = 972 words: shared memory
+    make(39, 1)  # 39 * 40 = 1560 words: shared memory
+    for n_sym, k in ((40, 1), (256, 1), (2, 9), (16, 2), (22, 2)):  # table in HBM, <= 512 rows of totals in shared memory
+        make(n_sym, k)
+    for n_sym, k in ((3, 6), (2, 10), (256, 2), (23, 2)):  # more than 512 contexts
         with pytest.raises(NotImplementedError):
             make(n_sym, k)
+
+
+def _orderk_large_cases():
+    import json
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orderk_large_v1.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    out = []
+    for c in meta["cases"]:
+        c = dict(c)
+        c["data"], c["enc"], c["final"] = z["c%d_data" % c["id"]], z["c%d_enc" % c["id"]], z["c%d_final" % c["id"]]
+        out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("c", _orderk_large_cases(), ids=lambda c: "%d-%s" % (c["id"], c["note"][:34].replace(" ", "_")))
+def test_orderk_large_tables_match_reference_golden(c):
+    """AdaptiveOrderKFreqModel with tables too large for shared memory (a BYTE alphabet at k = 1 among them), vectors
+    from the unmodified reference (oracle/gen_golden_orderk_large.py): the oracle and the product's lane code
+    (AecCtxGlobalPolicy, working in place on the model table) reproduce the reference's bits, its final count table
+    and context, and its num_bits_consumed on stream + garbage."""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    n_sym, k, p = len(c["freqs"]), c["model"]["k"], c["params"]
+    want_final = c["final"].astype(np.uint64).tolist() + [c["model"]["final_ctx"]]
+    fresh = np.array([1] * (n_sym ** (k + 1)) + [0], dtype=np.uint64)
+    oracle = so.Oracle.aec([1] * n_sym, DATA_BLOCK_SIZE_BITS=p["DATA_BLOCK_SIZE_BITS"], PRECISION=p["PRECISION"], model=so.MODEL_ORDER_K, k=k,
+                           max_allowed_total_freq=c["model"]["max_total"])
+    m = fresh.copy()
+    ref_bytes, ref_bits = oracle.encode_block(c["data"], model_freq=m)
+    assert ref_bits == c["nbits"] and ref_bytes.tobytes() == c["enc"].tobytes()
+    assert m.tolist() == want_final
+    prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=p["DATA_BLOCK_SIZE_BITS"], num_bits_out=0, range_factor=0, num_state_bits=0,
+                    precision=p["PRECISION"], model=_cabi.MODEL_ORDER_K, model_order=k, max_allowed_total_freq=c["model"]["max_total"])
+    coder = EmuCoder(prm, None, [1] * n_sym)
+    m = fresh.copy()[None]
+    out, off, ln, st = coder.encode(c["data"].reshape(1, -1), model=m)
+    assert st[0] == 0 and int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    assert m[0].tolist() == want_final
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    bits = np.concatenate([np.ones(3, dtype=np.uint8), np.unpackbits(packed)[:total]])
+    buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
+    m = fresh.copy()[None]
+    sym, sizes, used, st = coder.decode(buf, [3], [total], c["n"], model=m)
+    assert st[0] == 0 and int(sizes[0]) == c["n"] and sym[0, : c["n"]].tolist() == c["data"].tolist()
+    assert int(used[0]) == c["consumed"] and m[0].tolist() == want_final
 
 
 def test_generic_rans_decode_is_bounded_on_a_zero_state():
