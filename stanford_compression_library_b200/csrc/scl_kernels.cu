@@ -450,6 +450,13 @@ __global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 
             const uint32_t par = round & 1;
             uint32_t old = 0;
             if (lane == 0) {
+                // warp_tot[par] / arrive[par] still belong to round - 2 until that round is resolved (its last warp may be
+                // waiting for the copy pool): nobody arrives at this round before.  This is also how the pool's
+                // back-pressure reaches every coding warp, not just the resolving one.
+                if (round >= 2) {
+                    const volatile uint32_t *res = &ctl.resolved;
+                    while (*res < round - 1) __nanosleep(200);
+                }
                 *(volatile unsigned long long *)&ctl.warp_tot[par][warp] = T;
                 __threadfence_block();
                 old = atomicAdd(&ctl.arrive[par], 1u);

@@ -94,6 +94,21 @@ def test_packed_encode_equals_slots_plus_pack(name, shape, framed):
     _check_against_slots(enc, dec, data, framed)
 
 
+def test_packed_encode_sixteen_rounds_short_blocks():
+    """Many rounds of the persistent grid with very little coding per round (64-symbol blocks): the copy pool falls
+    behind, so the coding warps meet the back-pressure (a round cannot be entered before the round two back is
+    resolved) -- the regime of the 8 GiB single-GPU bench.  Bytes against the slot path + pack()."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities
+
+    B, N = 148 * 28 * 32 * 16 + 77, 64
+    params = rANSParams(zipf_frequencies())
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=4, device="cuda:0")
+    for _ in range(3):
+        _check_against_slots(enc, dec, data, False)
+
+
 @pytest.mark.parametrize("kw", [{}, dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)], ids=["default", "nbo8_rf12"])
 def test_packed_encode_many_rounds_vs_oracle(kw):
     """More tasks than one round of the persistent grid holds (the look-back then crosses rounds), a block
