@@ -248,10 +248,9 @@ template <bool FRAMED>
 __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const PackedOut &po, uint64_t task, uint64_t base, uint32_t lane) {
     const uint64_t b = task * 32 + lane;
     const bool active = b < io.n_blocks;
-    uint64_t bits = 0;
-    uint32_t nb = 0;
+    uint32_t bits = 0, nb = 0;  // a failed or absent block: no bits, no room
     if (active && io.status[b] == SCL_ST_OK) {
-        bits = io.bit_len[b];
+        bits = (uint32_t)io.bit_len[b];  // < 2^31 on this path
         nb = (uint32_t)packed_size(bits, FRAMED);
     }
     uint32_t incl = nb;
@@ -260,31 +259,32 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
         const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= (uint32_t)o) incl += u;
     }
-    const uint64_t at = base + (incl - nb);
     if (active) {
+        const uint64_t at = base + (incl - nb);
         po.byte_off[b] = at;
         io.bit_off[b] = 8 * at + packed_lead_bits(bits, FRAMED);
         if (nb && at + nb > po.dst_bytes) {
             io.status[b] = SCL_ST_OVERFLOW;
-            nb = 0;
+            bits = 0;  // dropped (nb keeps its place in the layout)
         }
     }
-    // where this lane's stream lies in the scratch buffer (it ends at its slot's end), and a hint to L2: the
-    // slots were written one task ago, i.e. ~400 MB of other traffic ago
-    const uint64_t src_off = (b + 1) * io.out_stride * 8 - bits;
+    // Stream l of the task: ends at its slot's end in the scratch buffer, goes to `at`; both advance uniformly, so
+    // one shuffle per stream (its bit count) is all the lanes exchange.  The NEXT stream is requested into L2 while
+    // this one is copied (one line per lane, no registers held): the slots were written ~400 MB of traffic ago.
+    const uint64_t stride_bits = io.out_stride * 8;
+    uint64_t slot_end = (task * 32 + 1) * stride_bits, at = base;
+    uint32_t bits_l = __shfl_sync(0xffffffffu, bits, 0), nb_l = __shfl_sync(0xffffffffu, nb, 0);
     for (uint32_t l = 0; l < 32; ++l) {
-        const uint32_t nb_l = __shfl_sync(0xffffffffu, nb, l);
-        if (l + 1 < 32) {  // fetch the NEXT stream into L2 while this one is copied: one line per lane, no registers held
-            const uint32_t nb_n = __shfl_sync(0xffffffffu, nb, l + 1);
-            const uint64_t so_n = __shfl_sync(0xffffffffu, src_off, l + 1);
-            const uint8_t *p0 = io.out + ((so_n >> 3) & ~127ull);
-            if (nb_n)
-                for (uint32_t o = lane * 128; o < nb_n + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        const uint32_t bits_n = __shfl_sync(0xffffffffu, bits, (l + 1) & 31), nb_n = __shfl_sync(0xffffffffu, nb, (l + 1) & 31);
+        if (l + 1 < 32 && bits_n) {
+            const uint8_t *p0 = io.out + (((slot_end + stride_bits - bits_n) >> 3) & ~127ull);
+            for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
-        if (!nb_l) continue;
-        const uint64_t bits_l = __shfl_sync(0xffffffffu, bits, l), at_l = __shfl_sync(0xffffffffu, at, l);
-        const uint64_t so_l = __shfl_sync(0xffffffffu, src_off, l);
-        pack_block_warp_a16<FRAMED>(io.out, so_l, bits_l, po.dst + at_l, lane);
+        if (bits_l) pack_block_warp_a16<FRAMED>(io.out, slot_end - bits_l, bits_l, po.dst + at, lane);
+        at += nb_l;
+        slot_end += stride_bits;
+        bits_l = bits_n;
+        nb_l = nb_n;
     }
 }
 

@@ -174,29 +174,44 @@ __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uin
     }
 }
 
+// 8 stream bits starting at stream position `pos` (which may be negative, or reach past the end: those bits read
+// as 0), straight-line: two aligned words, one funnel shift, two masks.  Needs the word holding bit off + pos and the
+// one after it to be readable (a slot keeps >= 32 spare bits in front of its stream and the buffer 16 bytes behind).
+__device__ __forceinline__ uint32_t stream_byte_masked(const uint8_t *__restrict__ src, uint64_t off, int32_t pos, uint32_t nbits) {
+    const uint64_t S = off + (int64_t)pos;
+    const uint32_t *w = (const uint32_t *)src + (S >> 5);
+    const uint32_t v = funnel_l(bswap32(w[1]), bswap32(w[0]), (uint32_t)S & 31u) >> 24;
+    uint32_t keep = 0xFFu;
+    if (pos < 0) keep = pos <= -8 ? 0u : (0xFFu >> (uint32_t)(-pos));
+    const int32_t r = (int32_t)nbits - pos;  // stream bits available from `pos` on
+    if (r < 8) keep &= r <= 0 ? 0u : ~(0xFFu >> (uint32_t)r);
+    return v & keep;
+}
+
+// nbits < 2^31 (the fast encoders bound block_len * 16 bits by that): everything inside a stream is 32-bit arithmetic
 template <bool FRAMED>
-__device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ src, uint64_t off, uint64_t nbits, uint8_t *__restrict__ d,
+__device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ src, uint64_t off, uint32_t nbits, uint8_t *__restrict__ d,
                                                     uint32_t lane) {
     constexpr int U = 4;
-    const uint32_t num_pad = FRAMED ? (uint32_t)((8 - (nbits + 3) % 8) % 8) : 0u;
-    const uint64_t lead = FRAMED ? 3 + num_pad : 0;
-    const uint64_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7) >> 3;
+    const uint32_t num_pad = FRAMED ? ((8u - (nbits + 3u) % 8u) % 8u) : 0u;
+    const uint32_t lead = FRAMED ? 3u + num_pad : 0u;
+    const uint32_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7u) >> 3;
     if (FRAMED) {
         if (lane < 4) d[lane] = (uint8_t)(payload_bytes >> (8 * (3 - lane)));
         d += 4;
     }
-    uint64_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    uint32_t head = (16u - ((uint32_t)(uintptr_t)d & 15u)) & 15u;
     if (FRAMED && 8 * head < lead) head += 16;
     if (head > payload_bytes) head = payload_bytes;
-    const uint64_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0;
+    const uint32_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0u;
     // The bytes before the first and after the last whole chunk (< 32 each, one per lane) are independent of the
-    // chunks: their loads go out first, their stores wait in the hook until the first chunk batch is in flight, so
-    // a stream costs one or two memory latencies, not four.
-    const uint64_t tail0 = head + 16 * n_chunks;
+    // chunks: their loads go out first, their stores wait until the first chunk batch is in flight, so a stream
+    // costs one or two memory latencies, not four.
+    const uint32_t tail0 = head + 16 * n_chunks;
     const bool has_head = lane < head, has_tail = tail0 + lane < payload_bytes;
     uint32_t hv = 0, tv = 0;
-    if (has_head) hv = pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, lane);
-    if (has_tail) tv = pack_payload_byte<FRAMED, false>(src, off, nbits, num_pad, lead, tail0 + lane);
+    if (has_head) hv = stream_byte_masked(src, off, (int32_t)(8 * lane) - (int32_t)lead, nbits) | ((FRAMED && lane == 0) ? (num_pad << 5) : 0u);
+    if (has_tail) tv = stream_byte_masked(src, off, (int32_t)(8 * (tail0 + lane)) - (int32_t)lead, nbits) | ((FRAMED && tail0 + lane == 0) ? (num_pad << 5) : 0u);
     auto edges = [&]() {
         if (has_head) d[lane] = (uint8_t)hv;
         if (has_tail) d[tail0 + lane] = (uint8_t)tv;
@@ -207,12 +222,12 @@ __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ 
     }
     const uint64_t S0 = off + 8 * head - lead;  // source bit of chunk 0's first bit; chunk ch starts 128 * ch bits later
     const uint4 *a = (const uint4 *)src + (S0 >> 7);
-    const uint32_t sh = (uint32_t)(S0 & 31);
+    const uint32_t sh = (uint32_t)S0 & 31u;
     switch ((uint32_t)(S0 >> 5) & 3u) {  // the same for every lane: no divergence
-    case 0: pack_chunks_a16<0, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
-    case 1: pack_chunks_a16<1, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
-    case 2: pack_chunks_a16<2, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
-    default: pack_chunks_a16<3, U>(a, sh, d + head, (uint32_t)n_chunks, lane, edges); break;
+    case 0: pack_chunks_a16<0, U>(a, sh, d + head, n_chunks, lane, edges); break;
+    case 1: pack_chunks_a16<1, U>(a, sh, d + head, n_chunks, lane, edges); break;
+    case 2: pack_chunks_a16<2, U>(a, sh, d + head, n_chunks, lane, edges); break;
+    default: pack_chunks_a16<3, U>(a, sh, d + head, n_chunks, lane, edges); break;
     }
     // (head <= 31 and the tail is < 32 bytes -- 16 left over plus a partial chunk -- so one byte per lane covers both)
 }
