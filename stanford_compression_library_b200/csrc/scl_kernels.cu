@@ -226,6 +226,8 @@ struct PackedOut {
     uint64_t *byte_off;      // [n_blocks + 1] record offsets, [n_blocks] = total
     uint64_t *cta_state;     // [rounds * gridDim.x] look-back words, zeroed before the launch
     uint32_t framed;
+    uint32_t copy_warps;     // dedicated copy warps of the CTA (kCopyWarps)
+    uint32_t prefetch_l1;    // experiment knob: request the next stream into L1 instead of L2
     uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
 };
 constexpr uint32_t kTraceWords = 40;  // per warp: [0] start, [1 + r] end of coding round r (r < 19), [20] tasks copied, [21] first copy
@@ -278,7 +280,10 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
         const uint32_t bits_n = __shfl_sync(0xffffffffu, bits, (l + 1) & 31), nb_n = __shfl_sync(0xffffffffu, nb, (l + 1) & 31);
         if (l + 1 < 32 && bits_n) {
             const uint8_t *p0 = io.out + (((slot_end + stride_bits - bits_n) >> 3) & ~127ull);
-            for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+            if (po.prefetch_l1)
+                for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + o));
+            else
+                for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
         if (bits_l) pack_block_warp_a16<FRAMED>(io.out, slot_end - bits_l, bits_l, po.dst + at, lane);
         at += nb_l;
@@ -330,15 +335,15 @@ __device__ __forceinline__ void packed_copy_pool(PackCtl &ctl, const BlockIo &io
 }
 
 template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
-__global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 1)
+__global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
-                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, PackedOut po) {
+                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, uint32_t sync_rounds, PackedOut po) {
     __shared__ PackCtl ctl;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // round the dynamic window up to 2 KiB so that ring addresses can be composed with OR
     uint8_t *smem = smem_raw + ((2048u - (smem_u32(smem_raw) & 2047u)) & 2047u);
     // W = coding warps; a PACKED launch carries kCopyWarps more (warp >= W), which own no tiles and no ring
-    const uint32_t W = (blockDim.x >> 5) - (PACKED ? kCopyWarps : 0u), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t W = (blockDim.x >> 5) - (PACKED ? po.copy_warps : 0u), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *tiles = smem + warp * (kTileStages * kTileBytes);
     const saddr_t ring = saddr_of(smem + W * (kTileStages * kTileBytes) + warp * (kEncRingWords * 128)) + lane * 4;
     const uint8_t *s_tab = smem + W * kEncWarpSmem;
@@ -489,6 +494,12 @@ __global__ void __launch_bounds__((kMaxWarps + (PACKED ? kCopyWarps : 0)) * 32, 
                 if (lane == 0) *(volatile uint32_t *)&ctl.resolved = round + 1;
             }
         }
+        // Keep the CTA's coding warps within `sync_rounds` rounds of each other: a warp's 32 rows and 32 streams sit in
+        // one or two 2 MiB pages, consecutive warps share them, so a CTA in step touches a handful of pages while
+        // warps that have drifted rounds apart touch dozens (measured at 2M blocks: tools/measure_chunking.py).
+        // Only between rounds that every coding warp of the CTA has (the last round may be partial).
+        if (sync_rounds && (round + 1) % sync_rounds == 0 && (uint64_t)(round + 1) * total_warps + blockIdx.x * W + (W - 1) < n_tasks)
+            asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
     if (PACKED) packed_copy_pool(ctl, io, po, W, total_warps, n_tasks, lane);  // out of symbols: help move the last rounds
 }
@@ -504,7 +515,7 @@ constexpr uint32_t kDecTileBytes = 32 * kTileCols;
 template <int KIND, uint32_t NBO, bool BAL>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     fast_decode_v2_kernel(const __grid_constant__ CUtensorMap out_map, uint32_t use_tiles, const uint32_t *__restrict__ g_lut,
-                          uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
+                          uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks, uint32_t sync_rounds) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,7 +529,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     typename std::conditional<KIND == 0, RansStepper<NBO, BAL>, TansStepper<BAL>>::type S;
     S.init(saddr_of(s_lut), c);
 
-    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
+    uint32_t round = 0;
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         DecLaneV2 D;
@@ -583,6 +595,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             io.status[b] = st;
         }
         __syncwarp();
+        // keep the CTA's warps in step (see fast_encode_v2_kernel): page locality of rows and streams
+        if (sync_rounds && (round + 1) % sync_rounds == 0 && (uint64_t)(round + 1) * total_warps + blockIdx.x * W + (W - 1) < n_tasks)
+            asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
 }
 
@@ -1531,7 +1546,12 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
 extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
     if (c) c->debug_mode = mode;
 }
-static inline bool force_v1(const scl_coder *c) { return c->debug_mode == 1; }
+// debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder,
+// bit 5 = its next-stream prefetch goes to L1, bits 6-7 = CTA round barrier every 1 / 2 rounds (default: kSyncRounds)
+static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
+static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
+constexpr uint32_t kSyncRounds = 0;
+static inline uint32_t sync_rounds_of(const scl_coder *c) { return (c->debug_mode & 64) ? 1u : (c->debug_mode & 128) ? 2u : kSyncRounds; }
 extern "C" void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words) {
     if (c) {
         c->d_trace = d_trace;
@@ -1563,11 +1583,16 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
         return -1;
     uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
     size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048 + (packed ? 2048 : 0);  // PACKED: the static PackCtl block
-    pick_launch(n_tasks, c->n_sm, max_warps_for(kEncWarpSmem, fixed), &grid, &warps);
+    const uint32_t copy_warps = packed ? ((c->debug_mode & 16) ? 8u : kCopyWarps) : 0u;
+    uint32_t max_w = max_warps_for(kEncWarpSmem, fixed);
+    if (max_w > 32 - copy_warps) max_w = 32 - copy_warps;
+    pick_launch(n_tasks, c->n_sm, max_w, &grid, &warps);
     size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t) + 2048;
     PackedOut po{};
     if (packed) {
         po = *packed;
+        po.copy_warps = copy_warps;
+        po.prefetch_l1 = (c->debug_mode & 32) ? 1u : 0u;
         po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
         const uint64_t rounds = (n_tasks + (uint64_t)grid * warps - 1) / ((uint64_t)grid * warps);
         cudaError_t e = cudaMemsetAsync(po.cta_state, 0, rounds * grid * sizeof(uint64_t), s);
@@ -1578,7 +1603,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     do {                                                                                                                           \
         e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
-        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + (PK ? kCopyWarps : 0)) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, po); \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, sync_rounds_of(c), po); \
     } while (0)
     if (rc.check_sym) {
         if (packed)
@@ -1606,7 +1631,7 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     memset(&omap, 0, sizeof(omap));
     uint32_t use_tiles = 0;
     PFN_tmapEncodeTiled enc = tmap_encoder();
-    if (enc && io.sym_stride >= kTileCols && c->debug_mode != 2) {
+    if (enc && io.sym_stride >= kTileCols && dbg_path(c) != 2) {
         cuuint64_t gdim[2] = {io.sym_stride, io.n_blocks};
         cuuint64_t gstr[1] = {io.sym_stride};
         cuuint32_t box[2] = {kTileCols, 32};
@@ -1616,11 +1641,11 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     }
     // pipe-balanced instruction selection pays when the SMs are full (>= 2 rounds of warps); small batches are
     // latency-bound and keep the shorter dependency chain
-    const bool bal = c->debug_mode == 3 ? true : c->debug_mode == 4 ? false : n_tasks >= 24u * c->n_sm;
+    const bool bal = dbg_path(c) == 3 ? true : dbg_path(c) == 4 ? false : n_tasks >= 24u * c->n_sm;
     auto kern = bal ? fast_decode_v2_kernel<KIND, NBO, true> : fast_decode_v2_kernel<KIND, NBO, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks);
+    kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks, sync_rounds_of(c));
     return check_launch("fast_decode_v2_kernel");
 }
 
@@ -1799,7 +1824,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, kCopyWarps, 0u, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);
