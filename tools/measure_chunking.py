@@ -42,6 +42,7 @@ def main():
     d = dec.decode_blocks(e, N).check()
     assert torch.equal(d.symbols[:, :N], data)
     stride = e.out_stride
+    abs_off = e.bit_offset.clone()  # the chunked encodes below rewrite e.bit_offset relative to each chunk
     out = {"blocks": B}
     for chunk in (B, 1048576, 524288, 262144, 131072):
         if chunk > B:
@@ -63,7 +64,8 @@ def main():
 
         te = timeit(enc_chunks)
         e.check()
-        rel_off = e.bit_offset - (torch.arange(B, device="cuda:0", dtype=torch.int64) // chunk) * (chunk * stride * 8)
+        rel_off = abs_off - (torch.arange(B, device="cuda:0", dtype=torch.int64) // chunk) * (chunk * stride * 8)
+        d.symbols.zero_()
         td = timeit(dec_chunks)
         assert torch.equal(d.symbols[:, :N], data)
         out["launches_of_%d" % chunk] = {"encode_slots_ms": te, "decode_ms": td, "encode_ms_per_GiB": te / (B * N / 2**30), "decode_ms_per_GiB": td / (B * N / 2**30)}
