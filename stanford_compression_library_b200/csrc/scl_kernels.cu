@@ -80,6 +80,8 @@ struct BlockIo {  // per-launch I/O description shared by all encode kernels
     uint64_t *bit_off;
     uint64_t *bit_len;
     uint32_t *status;
+    uint64_t block0;  // second-generation rANS / tANS launches of a split batch: index of this launch's first block in `out`
+                      // (sym, bit_off, bit_len, status already point at that block; slots and reported offsets are global)
 };
 struct DecodeIo {
     const uint8_t *in;
@@ -226,6 +228,7 @@ struct PackedOut {
     uint64_t *byte_off;      // [n_blocks + 1] record offsets, [n_blocks] = total
     uint64_t *cta_state;     // [rounds * gridDim.x] look-back words, zeroed before the launch
     uint32_t framed;
+    uint64_t g_base;         // look-back index of this launch's (round 0, CTA 0): a split batch continues the numbering
     uint32_t copy_warps;     // dedicated copy warps of the CTA (kCopyWarps)
     uint32_t prefetch_l1;    // experiment knob: request the next stream into L1 instead of L2
     uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
@@ -274,7 +277,7 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
     // one shuffle per stream (its bit count) is all the lanes exchange.  The NEXT stream is requested into L2 while
     // this one is copied (one line per lane, no registers held): the slots were written ~400 MB of traffic ago.
     const uint64_t stride_bits = io.out_stride * 8;
-    uint64_t slot_end = (task * 32 + 1) * stride_bits, at = base;
+    uint64_t slot_end = (io.block0 + task * 32 + 1) * stride_bits, at = base;
     uint32_t bits_l = __shfl_sync(0xffffffffu, bits, 0), nb_l = __shfl_sync(0xffffffffu, nb, 0);
     for (uint32_t l = 0; l < 32; ++l) {
         const uint32_t bits_n = __shfl_sync(0xffffffffu, bits, (l + 1) & 31), nb_n = __shfl_sync(0xffffffffu, nb, (l + 1) & 31);
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             }
         }
         EncLaneV2 L;
-        uint8_t *slot = io.out + (active ? b : 0) * io.out_stride;
+        uint8_t *slot = io.out + (io.block0 + (active ? b : 0)) * io.out_stride;
         L.init((uint32_t)c.L, ring, slot, slot + io.out_stride);
         for (uint32_t t = 0; t < n_tiles; ++t, ++tile_seq) {
             const uint32_t st = tile_seq % kTileStages;
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             if (L.bad) st = SCL_ST_BAD_SYMBOL;
             if (L.ovf) st = SCL_ST_OVERFLOW;
             io.bit_len[b] = bits;
-            if (!PACKED) io.bit_off[b] = (b + 1) * io.out_stride * 8 - bits;
+            if (!PACKED) io.bit_off[b] = (io.block0 + b + 1) * io.out_stride * 8 - bits;
             io.status[b] = st;
             if (PACKED && st == SCL_ST_OK) rec_bytes = (uint32_t)packed_size(bits, po.framed != 0);
         }
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
                 const uint64_t t = lane < nvalid ? *(const volatile unsigned long long *)&ctl.warp_tot[par][lane] : 0ull;
                 const uint64_t incl = warp_incl_scan_u64(t, lane);
                 const uint64_t A = __shfl_sync(0xffffffffu, incl, 31);
-                const int64_t g = (int64_t)round * gridDim.x + blockIdx.x;
+                const int64_t g = (int64_t)po.g_base + (int64_t)round * gridDim.x + blockIdx.x;
                 if (lane == 0) st_relaxed_gpu(po.cta_state + g, (g ? kLbAgg : kLbPrefix) | A);
                 uint64_t excl = 0;
                 if (g) {
@@ -1547,7 +1550,8 @@ extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
     if (c) c->debug_mode = mode;
 }
 // debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder,
-// bit 5 = its next-stream prefetch goes to L1, bits 6-7 = CTA round barrier every 1 / 2 rounds (default: kSyncRounds)
+// bit 5 = its next-stream prefetch goes to L1, bits 6-7 = CTA round barrier every 1 / 2 rounds (default: kSyncRounds),
+// bit 8 = split batches at 64 MiB of rows instead of 4 GiB (so that tests reach the multi-launch path)
 static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
 static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
 constexpr uint32_t kSyncRounds = 0;
@@ -1568,25 +1572,31 @@ static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
 // look-back words a packed launch may need: one per (round, CTA); rounds * grid <= tasks + grid
 static uint64_t packed_state_words(uint64_t n_blocks) { return (n_blocks + 31) / 32 + 4096; }
 
+// A launch whose symbol rows span more than 4 GiB runs ~1.4x slower per block than the same work in launches of
+// <= 4 GiB (decode 1.27 vs 0.87 ms per GiB at 2M x 4 KiB blocks, same DRAM bytes, issue slots 44 % vs 64 %:
+// profiles/r2g_*): big batches are split into launches of whole rounds below that span.
+constexpr uint64_t kLaunchSpanBytes = 1ull << 32;
+static uint64_t tasks_per_launch(const scl_coder *c, uint64_t n_tasks, uint64_t row_bytes, uint64_t tasks_per_round) {
+    const uint64_t span = (c->debug_mode & 256) ? (64ull << 20) : kLaunchSpanBytes;  // test hook: split at 64 MiB
+    if (n_tasks * 32 * row_bytes <= span) return n_tasks;
+    uint64_t t = span / row_bytes / 32 / tasks_per_round * tasks_per_round;
+    return t < tasks_per_round ? tasks_per_round : t;
+}
+
 template <int KIND, uint32_t NBO>
 static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void *tab8, const uint32_t *tab2, uint32_t tab2_bytes,
                             const BlockIo &io, const PackedOut *packed, cudaStream_t s) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return -1;
-    CUtensorMap tmap;
-    cuuint64_t gdim[2] = {io.block_len, io.n_blocks};
-    cuuint64_t gstr[1] = {io.sym_stride};
-    cuuint32_t box[2] = {kTileCols, 32};
-    cuuint32_t estr[2] = {1, 1};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return -1;
-    uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
+    const uint32_t n_tasks_all = (uint32_t)((io.n_blocks + 31) / 32);
+    uint32_t grid, warps;
     size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048 + (packed ? 2048 : 0);  // PACKED: the static PackCtl block
     const uint32_t copy_warps = packed ? ((c->debug_mode & 16) ? 8u : kCopyWarps) : 0u;
     uint32_t max_w = max_warps_for(kEncWarpSmem, fixed);
     if (max_w > 32 - copy_warps) max_w = 32 - copy_warps;
-    pick_launch(n_tasks, c->n_sm, max_w, &grid, &warps);
+    pick_launch(n_tasks_all, c->n_sm, max_w, &grid, &warps);
+    const uint64_t per_round = (uint64_t)grid * warps;
+    const uint64_t chunk_tasks = tasks_per_launch(c, n_tasks_all, io.sym_stride, per_round);
     size_t smem = (size_t)warps * kEncWarpSmem + kEncTabBytes + tab2_bytes + (warps * kTileStages + 1) * sizeof(uint64_t) + 2048;
     PackedOut po{};
     if (packed) {
@@ -1594,59 +1604,101 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
         po.copy_warps = copy_warps;
         po.prefetch_l1 = (c->debug_mode & 32) ? 1u : 0u;
         po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
-        const uint64_t rounds = (n_tasks + (uint64_t)grid * warps - 1) / ((uint64_t)grid * warps);
+        // one look-back word per (round, CTA) of the WHOLE batch: the launches of a split batch are whole rounds, so the
+        // numbering (and with it the running prefix) simply continues from launch to launch
+        const uint64_t rounds = (n_tasks_all + per_round - 1) / per_round;
         cudaError_t e = cudaMemsetAsync(po.cta_state, 0, rounds * grid * sizeof(uint64_t), s);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     }
-    cudaError_t e;
+    for (uint64_t t0 = 0; t0 < n_tasks_all; t0 += chunk_tasks) {
+        const uint64_t b0 = t0 * 32;
+        BlockIo cio = io;
+        cio.sym = io.sym + b0 * io.sym_stride;
+        cio.n_blocks = io.n_blocks - b0 < chunk_tasks * 32 ? io.n_blocks - b0 : chunk_tasks * 32;
+        cio.bit_off = io.bit_off + b0;
+        cio.bit_len = io.bit_len + b0;
+        cio.status = io.status + b0;
+        cio.block0 = io.block0 + b0;
+        const uint32_t n_tasks = (uint32_t)((cio.n_blocks + 31) / 32);
+        CUtensorMap tmap;
+        cuuint64_t gdim[2] = {cio.block_len, cio.n_blocks};
+        cuuint64_t gstr[1] = {cio.sym_stride};
+        cuuint32_t box[2] = {kTileCols, 32};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)cio.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return t0 ? SCL_E_CUDA : -1;  // (-1: nothing launched yet, the caller may fall back to the first generation)
+        if (packed) {
+            po.byte_off = packed->byte_off + b0;
+            po.g_base = (t0 / per_round) * grid;
+        }
+        cudaError_t e;
 #define SCL_LAUNCH_ENC(CHK, PK)                                                                                                    \
     do {                                                                                                                           \
         e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
-        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, io, n_tasks, sync_rounds_of(c), po); \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, cio, n_tasks, sync_rounds_of(c), po); \
     } while (0)
-    if (rc.check_sym) {
-        if (packed)
-            SCL_LAUNCH_ENC(true, true);
-        else
-            SCL_LAUNCH_ENC(true, false);
-    } else {
-        if (packed)
-            SCL_LAUNCH_ENC(false, true);
-        else
-            SCL_LAUNCH_ENC(false, false);
-    }
+        if (rc.check_sym) {
+            if (packed)
+                SCL_LAUNCH_ENC(true, true);
+            else
+                SCL_LAUNCH_ENC(true, false);
+        } else {
+            if (packed)
+                SCL_LAUNCH_ENC(false, true);
+            else
+                SCL_LAUNCH_ENC(false, false);
+        }
 #undef SCL_LAUNCH_ENC
-    return check_launch("fast_encode_v2_kernel");
+        int rc2 = check_launch("fast_encode_v2_kernel");
+        if (rc2) return rc2;
+    }
+    return SCL_E_OK;
 }
 
 template <int KIND, uint32_t NBO>
 static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint32_t *lut, uint32_t lut_bytes, const DecodeIo &io,
                             cudaStream_t s) {
-    uint32_t n_tasks = (uint32_t)((io.n_blocks + 31) / 32), grid, warps;
-    pick_launch(n_tasks, c->n_sm, max_warps_for(kDecWarpSmem + kDecTileBytes, lut_bytes), &grid, &warps);
+    const uint32_t n_tasks_all = (uint32_t)((io.n_blocks + 31) / 32);
+    uint32_t grid, warps;
+    pick_launch(n_tasks_all, c->n_sm, max_warps_for(kDecWarpSmem + kDecTileBytes, lut_bytes), &grid, &warps);
+    const uint64_t chunk_tasks = tasks_per_launch(c, n_tasks_all, io.sym_stride, (uint64_t)grid * warps);  // see launch_encode_v2
     size_t smem = (size_t)warps * (kDecWarpSmem + kDecTileBytes) + lut_bytes;
-    // output tensor map for the TMA tile stores: rows = blocks, inner = the row capacity
-    CUtensorMap omap;
-    memset(&omap, 0, sizeof(omap));
-    uint32_t use_tiles = 0;
-    PFN_tmapEncodeTiled enc = tmap_encoder();
-    if (enc && io.sym_stride >= kTileCols && dbg_path(c) != 2) {
-        cuuint64_t gdim[2] = {io.sym_stride, io.n_blocks};
-        cuuint64_t gstr[1] = {io.sym_stride};
-        cuuint32_t box[2] = {kTileCols, 32};
-        cuuint32_t estr[2] = {1, 1};
-        use_tiles = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)io.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    }
     // pipe-balanced instruction selection pays when the SMs are full (>= 2 rounds of warps); small batches are
     // latency-bound and keep the shorter dependency chain
-    const bool bal = dbg_path(c) == 3 ? true : dbg_path(c) == 4 ? false : n_tasks >= 24u * c->n_sm;
+    const bool bal = dbg_path(c) == 3 ? true : dbg_path(c) == 4 ? false : n_tasks_all >= 24u * c->n_sm;
     auto kern = bal ? fast_decode_v2_kernel<KIND, NBO, true> : fast_decode_v2_kernel<KIND, NBO, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, io, n_tasks, sync_rounds_of(c));
-    return check_launch("fast_decode_v2_kernel");
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    for (uint64_t t0 = 0; t0 < n_tasks_all; t0 += chunk_tasks) {
+        const uint64_t b0 = t0 * 32;
+        DecodeIo cio = io;  // the coded buffer and its bit offsets stay global; the per-block arrays move to this launch's first block
+        cio.n_blocks = io.n_blocks - b0 < chunk_tasks * 32 ? io.n_blocks - b0 : chunk_tasks * 32;
+        cio.bit_off = io.bit_off + b0;
+        cio.bit_len = io.bit_len ? io.bit_len + b0 : nullptr;
+        cio.sym = io.sym + b0 * io.sym_stride;
+        cio.sizes = io.sizes + b0;
+        cio.consumed = io.consumed + b0;
+        cio.status = io.status + b0;
+        // output tensor map for the TMA tile stores: rows = blocks, inner = the row capacity
+        CUtensorMap omap;
+        memset(&omap, 0, sizeof(omap));
+        uint32_t use_tiles = 0;
+        if (enc && cio.sym_stride >= kTileCols && dbg_path(c) != 2) {
+            cuuint64_t gdim[2] = {cio.sym_stride, cio.n_blocks};
+            cuuint64_t gstr[1] = {cio.sym_stride};
+            cuuint32_t box[2] = {kTileCols, 32};
+            cuuint32_t estr[2] = {1, 1};
+            use_tiles = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)cio.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, cio, (uint32_t)((cio.n_blocks + 31) / 32), sync_rounds_of(c));
+        int rc2 = check_launch("fast_decode_v2_kernel");
+        if (rc2) return rc2;
+    }
+    return SCL_E_OK;
 }
 
 static int launch_range_encode_v2(const scl_coder *c, const BlockIo &io, cudaStream_t s) {
@@ -1824,7 +1876,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, kCopyWarps, 0u, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, 0u, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);

@@ -295,3 +295,36 @@ def test_stream_level_encode_text_symbols_batched(tmp_path):
         (tmp_path / "bad.txt").write_text("abcz")
         with TextFileDataStream(str(tmp_path / "bad.txt"), "r") as fds, EncodedBlockWriter(str(tmp_path / "bad.bin")) as w:
             enc.encode(fds, block_size=500, encode_writer=w)
+
+
+@pytest.mark.parametrize("framed", [False, True], ids=["packed", "framed"])
+def test_split_launches_give_the_same_streams(framed):
+    """Batches whose rows span more than 4 GiB are coded by several launches of whole rounds (the fused encoder's
+    running prefix continues across them).  With the test hook that lowers the span to 64 MiB the same batch is coded
+    in one launch and in four: identical bytes, offsets and decoded symbols, both for the slot and the packed form."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities
+
+    B, N = 148 * 28 * 32 * 3 + 1234, 256
+    params = rANSParams(zipf_frequencies())
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_blocks(zipf_probabilities(), B, N, seed=21, device="cuda:0")
+    e1 = enc.encode_blocks(data).check()
+    p1 = enc.encode_blocks_packed(data, framed=framed).check()
+    d1 = dec.decode_blocks(p1, N).check()
+    try:
+        enc.device_coder().debug_path(256)
+        dec.device_coder().debug_path(256)
+        e2 = enc.encode_blocks(data).check()
+        p2 = enc.encode_blocks_packed(data, framed=framed).check()
+        d2 = dec.decode_blocks(p2, N).check()
+        d3 = dec.decode_blocks(e2, N).check()
+    finally:
+        enc.device_coder().debug_path(0)
+        dec.device_coder().debug_path(0)
+    total = int(p1.byte_offset[-1])
+    assert torch.equal(e1.bit_len, e2.bit_len) and torch.equal(e1.bit_offset, e2.bit_offset)
+    assert torch.equal(e1.pack().buf[: e1.total_bytes()], e2.pack().buf[: e1.total_bytes()])
+    assert torch.equal(p1.byte_offset, p2.byte_offset) and torch.equal(p1.bit_offset, p2.bit_offset) and torch.equal(p1.buf[:total], p2.buf[:total])
+    for d in (d1, d2, d3):
+        assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
