@@ -131,7 +131,11 @@ SCL_HD u32x8 ld_sector32(const uint8_t *p) {
 // symbol's bits (rANS.py:158,196), i.e. earlier bits are less significant in the payload read as
 // a big-endian integer; here earlier bits sink towards the LSB end, which is the same order.
 // `room` = 64 - (valid bits); the oldest 32 valid bits are (hi:lo) >> room.
-struct EncLaneV2 {
+// RAW = the slot is private scratch of the fused packed encoder: words are stored as the numbers they are (no byte
+// swap on the way out; the copy pool that reads them back saves the swap on the way in as well).  RAW = false is
+// the public slot format: big-endian words, i.e. the bytes of the bit stream.
+template <bool RAW>
+struct EncLaneV2T {
     uint32_t x;        // rANS state
     uint32_t lo, hi;   // accumulator
     uint32_t room;     // 64 - valid bits
@@ -210,7 +214,7 @@ struct EncLaneV2 {
             const saddr_t g = ring_slot(rofs);
 #pragma unroll
             for (uint32_t j = 0; j < 8; ++j)  // word base+7-j goes to the lowest address first
-                s.v[j] = bswap32(lds32(g + (7 - j) * 128));
+                s.v[j] = RAW ? lds32(g + (7 - j) * 128) : bswap32(lds32(g + (7 - j) * 128));
             uint8_t *dst = gend - ((rofs >> 5) + 32);  // 4 * (words_drained + 8)
             if (dst >= gbegin)
                 st_sector32(dst, s);
@@ -250,7 +254,7 @@ struct EncLaneV2 {
         for (uint32_t i = rofs >> 7; i < (uint32_t)words; ++i) {
             uint8_t *dst = gend - 4 * ((uint64_t)i + 1);
             if (dst >= gbegin)
-                st_word(dst, bswap32(lds32(ring_slot(i * 128))));
+                st_word(dst, RAW ? lds32(ring_slot(i * 128)) : bswap32(lds32(ring_slot(i * 128))));
             else
                 ovf = 1;
         }
@@ -258,17 +262,18 @@ struct EncLaneV2 {
             uint32_t w = hi >> (room - 32);  // room in (32,64): the valid bits are the top bits of hi
             uint8_t *dst = gend - 4 * (words + 1);
             if (dst >= gbegin)
-                st_word(dst, bswap32(w));
+                st_word(dst, RAW ? w : bswap32(w));
             else
                 ovf = 1;
         }
         return bits;
     }
 };
+typedef EncLaneV2T<false> EncLaneV2;
 
 // Encode one full 16-symbol chunk (the hot path: fully unrolled, spill check after every 2nd symbol).
-template <uint32_t NBO, bool CHECK>
-SCL_HD void enc_chunk16(EncLaneV2 &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v) {
+template <uint32_t NBO, bool CHECK, class Lane>
+SCL_HD void enc_chunk16(Lane &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     // The table entries depend only on the symbols, not on the coder state: fetch a whole word's four
     // entries one word (4 symbols) ahead of their use.  Left to itself the compiler keeps the loads two
@@ -298,8 +303,8 @@ SCL_HD void enc_chunk16(EncLaneV2 &L, saddr_t tab, uint32_t sym_stride, const u3
 // of entry 0; entry s is `sym_stride` bytes further per symbol (128 on the device: 8 replicas of
 // 16 bytes, so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups).
 // The full-chunk path is fully unrolled with the spill check after every second symbol.
-template <uint32_t NBO, bool CHECK>
-SCL_HD void enc_chunk(EncLaneV2 &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v, uint32_t cnt) {
+template <uint32_t NBO, bool CHECK, class Lane>
+SCL_HD void enc_chunk(Lane &L, saddr_t tab, uint32_t sym_stride, const u32x4 &v, uint32_t cnt) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     if (cnt == 16) {
 #pragma unroll
@@ -510,8 +515,8 @@ SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
 //   symbol entry (16 B, 8 bank-rotated replicas) = {thresh, nb0, row - min_shrunk, pad}
 //   enc_table[row + x_shrunk] = next state        dec_packed[x - L] = x_shrunk << 8 | byte
 // ------------------------------------------------------------------------------------------------
-template <bool CHECK>
-SCL_HD void tans_enc_step(EncLaneV2 &L, const u32x4 &e, saddr_t enc_table) {
+template <bool CHECK, class Lane>
+SCL_HD void tans_enc_step(Lane &L, const u32x4 &e, saddr_t enc_table) {
     if (CHECK && e.y == 0xFFFFFFFFu) {
         L.bad = 1;
         return;
@@ -523,8 +528,8 @@ SCL_HD void tans_enc_step(EncLaneV2 &L, const u32x4 &e, saddr_t enc_table) {
     L.x = lds32(enc_table + (saddr_t)(((L.x >> k) + e.z) << 2));  // base_encode_step_table[(s, x_shrunk)]
 }
 
-template <bool CHECK>
-SCL_HD void tans_enc_chunk16(EncLaneV2 &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v) {
+template <bool CHECK, class Lane>
+SCL_HD void tans_enc_chunk16(Lane &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     u32x4 e[4], nx[4];  // per-symbol rows fetched one word ahead of their use, as in enc_chunk16
 #pragma unroll
@@ -546,8 +551,8 @@ SCL_HD void tans_enc_chunk16(EncLaneV2 &L, saddr_t symtab, uint32_t sym_stride, 
     L.drain_check();
 }
 
-template <bool CHECK>
-SCL_HD void tans_enc_chunk(EncLaneV2 &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v, uint32_t cnt) {
+template <bool CHECK, class Lane>
+SCL_HD void tans_enc_chunk(Lane &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v, uint32_t cnt) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
     if (cnt == 16) {
 #pragma unroll

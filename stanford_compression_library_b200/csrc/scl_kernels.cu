@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
                 tma_tile_2d(tiles + st * kTileBytes, &tmap, (int32_t)(t * kTileCols), (int32_t)(task * 32), my_bar + st);
             }
         }
-        EncLaneV2 L;
+        EncLaneV2T<PACKED> L;  // PACKED: the slot is private scratch, written as raw words (no byte swaps, here or in the copy pool)
         uint8_t *slot = io.out + (io.block0 + (active ? b : 0)) * io.out_stride;
         L.init((uint32_t)c.L, ring, slot, slot + io.out_stride);
         for (uint32_t t = 0; t < n_tiles; ++t, ++tile_seq) {

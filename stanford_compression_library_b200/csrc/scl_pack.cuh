@@ -107,80 +107,81 @@ __device__ __forceinline__ void pack_block_warp(const uint8_t *__restrict__ src,
         d[i] = (uint8_t)pack_payload_byte<FRAMED, NC>(src, off, nbits, num_pad, lead, i);
 }
 
-// The same copy for a source this kernel wrote itself (the fused encoder's scratch slots), tuned for ONE warp
-// that has to move a whole task (32 streams, ~100 KB) while the SM's other warps are busy coding: the source
-// base is 16-byte aligned, so a chunk's five words come from two aligned 128-bit loads (2 x 4 L1 wavefronts per
-// 512 bytes instead of 5 x 4 for word loads), the word offset inside the pair is the same for every chunk of a
-// stream (template W0), and U chunks per lane are in flight before the first one is used -- a single warp must
-// keep a few KB outstanding to make progress against ~1 us of memory latency.
+// ---- the fused encoder's copy: scratch slots (RAW words) -> packed records ----------------------------------------
+// Tuned for ONE warp that has to move a whole task (32 streams, ~100 KB) while the SM's other warps are busy coding,
+// i.e. for few instructions and few exposed memory latencies per stream:
+//   * the scratch slots hold the stream as raw 32-bit words (EncLaneV2T<true>): word i is the number whose big-endian
+//     bytes are stream bytes 4i..4i+3, so neither the loads here nor the encoder's drains swap bytes; only the
+//     finished 16-byte chunk is swapped into byte order;
+//   * the source base is 16-byte aligned, so a chunk's five words come from two aligned 128-bit loads, and the word
+//     offset inside the pair is the same for every chunk of a stream (template W0);
+//   * up to U chunks per lane are in flight before the first is used; loads are predicated, addresses are one base
+//     plus immediates; the loads of the bytes at both ends of the stream go out before the first batch and their
+//     stores wait until it is in flight.
 // Reads up to 16 bytes past the 16-byte group that holds the stream's last bit.
 template <int W0>
-__device__ __forceinline__ uint4 pack_chunk_from_pair(const uint4 &A, const uint4 &B, uint32_t sh) {
+__device__ __forceinline__ uint4 pack_chunk_from_pair_raw(const uint4 &A, const uint4 &B, uint32_t sh) {
     const uint32_t x[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-    uint32_t W[5];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) W[j] = bswap32(x[W0 + j]);
     uint4 o;
-    o.x = bswap32(funnel_l(W[1], W[0], sh));
-    o.y = bswap32(funnel_l(W[2], W[1], sh));
-    o.z = bswap32(funnel_l(W[3], W[2], sh));
-    o.w = bswap32(funnel_l(W[4], W[3], sh));
+    o.x = bswap32(funnel_l(x[W0 + 1], x[W0 + 0], sh));
+    o.y = bswap32(funnel_l(x[W0 + 2], x[W0 + 1], sh));
+    o.z = bswap32(funnel_l(x[W0 + 3], x[W0 + 2], sh));
+    o.w = bswap32(funnel_l(x[W0 + 4], x[W0 + 3], sh));
     return o;
 }
 
-__device__ __forceinline__ uint4 ld_plain128(const uint4 *p) {  // volatile asm: the loads of a batch stay together, ahead of its stores
-    uint4 r;
-    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
+// predicated 128-bit load: the destination keeps its (unused) old value when the predicate is off
+__device__ __forceinline__ void ld_plain128_if(uint4 &r, const uint4 *p, uint32_t off_bytes, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+                 : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+                 : "l"((const uint8_t *)p + off_bytes), "r"((uint32_t)on)
+                 : "memory");
 }
 __device__ __forceinline__ void st_plain128(uint8_t *p, const uint4 &v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// chunk batches of one stream; `first_batch_hook` runs after the FIRST batch's loads have been issued and before
-// anything waits for them (the caller parks its own independent loads' consumers there)
 template <int W0, int U, class Hook>
 __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uint32_t sh, uint8_t *__restrict__ dd, uint32_t n_chunks, uint32_t lane,
                                                 Hook first_batch_hook) {  // n_chunks >= 1
-    const uint32_t last = n_chunks - 1;
-    {   // first batch: every lane takes part (clamped indices), the hook sits between its loads and its stores
+    bool first = true;
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32 * U) {  // c0 is warp-uniform: whole slots of a batch are skipped together
+        const uint4 *ab = a + c0 + lane;
+        uint8_t *db = dd + 16 * (uint64_t)(c0 + lane);
         uint4 A[U], B[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t ch = min(lane + 32 * u, last);
-            A[u] = ld_plain128(a + ch);
-            B[u] = ld_plain128(a + ch + 1);
-        }
-        first_batch_hook();
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t ch = lane + 32 * u;
-            if (ch < n_chunks) st_plain128(dd + 16 * ch, pack_chunk_from_pair<W0>(A[u], B[u], sh));
-        }
-    }
-    for (uint32_t c0 = lane + 32 * U; c0 < n_chunks; c0 += 32 * U) {
-        uint4 A[U], B[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // all 2U loads first (a clamped index instead of a predicate keeps them unconditional)
-            const uint32_t ch = min(c0 + 32 * u, last);
-            A[u] = ld_plain128(a + ch);
-            B[u] = ld_plain128(a + ch + 1);
+            A[u] = make_uint4(0, 0, 0, 0);
+            B[u] = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t ch = c0 + 32 * u;
-            if (ch < n_chunks) st_plain128(dd + 16 * ch, pack_chunk_from_pair<W0>(A[u], B[u], sh));
+            if (c0 + 32 * u < n_chunks) {  // uniform
+                const bool on = c0 + 32 * u + lane < n_chunks;
+                ld_plain128_if(A[u], ab, 512 * u, on);
+                ld_plain128_if(B[u], ab, 512 * u + 16, on);
+            }
+        }
+        if (first) {
+            first_batch_hook();
+            first = false;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (c0 + 32 * u < n_chunks) {
+                if (c0 + 32 * u + lane < n_chunks) st_plain128(db + 512 * u, pack_chunk_from_pair_raw<W0>(A[u], B[u], sh));
+            }
         }
     }
 }
 
 // 8 stream bits starting at stream position `pos` (which may be negative, or reach past the end: those bits read
-// as 0), straight-line: two aligned words, one funnel shift, two masks.  Needs the word holding bit off + pos and the
-// one after it to be readable (a slot keeps >= 32 spare bits in front of its stream and the buffer 16 bytes behind).
-__device__ __forceinline__ uint32_t stream_byte_masked(const uint8_t *__restrict__ src, uint64_t off, int32_t pos, uint32_t nbits) {
+// as 0), straight-line: two aligned RAW words, one funnel shift, two masks.  Needs the word holding bit off + pos and
+// the one after it to be readable (a slot keeps >= 32 spare bits in front of its stream, the buffer 16 bytes behind).
+__device__ __forceinline__ uint32_t stream_byte_masked_raw(const uint8_t *__restrict__ src, uint64_t off, int32_t pos, uint32_t nbits) {
     const uint64_t S = off + (int64_t)pos;
     const uint32_t *w = (const uint32_t *)src + (S >> 5);
-    const uint32_t v = funnel_l(bswap32(w[1]), bswap32(w[0]), (uint32_t)S & 31u) >> 24;
+    const uint32_t v = funnel_l(w[1], w[0], (uint32_t)S & 31u) >> 24;
     uint32_t keep = 0xFFu;
     if (pos < 0) keep = pos <= -8 ? 0u : (0xFFu >> (uint32_t)(-pos));
     const int32_t r = (int32_t)nbits - pos;  // stream bits available from `pos` on
@@ -204,17 +205,23 @@ __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ 
     if (FRAMED && 8 * head < lead) head += 16;
     if (head > payload_bytes) head = payload_bytes;
     const uint32_t n_chunks = (8 * head + 128 <= nbits + lead) ? ((nbits + lead - 8 * head) >> 7) : 0u;
-    // The bytes before the first and after the last whole chunk (< 32 each, one per lane) are independent of the
-    // chunks: their loads go out first, their stores wait until the first chunk batch is in flight, so a stream
-    // costs one or two memory latencies, not four.
-    const uint32_t tail0 = head + 16 * n_chunks;
-    const bool has_head = lane < head, has_tail = tail0 + lane < payload_bytes;
-    uint32_t hv = 0, tv = 0;
-    if (has_head) hv = stream_byte_masked(src, off, (int32_t)(8 * lane) - (int32_t)lead, nbits) | ((FRAMED && lane == 0) ? (num_pad << 5) : 0u);
-    if (has_tail) tv = stream_byte_masked(src, off, (int32_t)(8 * (tail0 + lane)) - (int32_t)lead, nbits) | ((FRAMED && tail0 + lane == 0) ? (num_pad << 5) : 0u);
+    const uint32_t tail0 = head + 16 * n_chunks;  // the bytes after the last whole chunk: < 32 (16 left over + a partial chunk)
+    // The edge bytes are independent of the chunks: their loads go out first, their stores wait until the first chunk
+    // batch is in flight.  Packed records have head <= 15 and at most 16 tail bytes: ONE byte per lane covers both
+    // ends (lanes 0-15 the head, lanes 16-31 the tail); framed records (head <= 31) take two.
+    uint32_t i0, i1 = 0xFFFFFFFFu;
+    if (!FRAMED) {
+        i0 = lane < 16 ? (lane < head ? lane : 0xFFFFFFFFu) : (tail0 + lane - 16 < payload_bytes ? tail0 + lane - 16 : 0xFFFFFFFFu);
+    } else {
+        i0 = lane < head ? lane : 0xFFFFFFFFu;
+        i1 = tail0 + lane < payload_bytes ? tail0 + lane : 0xFFFFFFFFu;
+    }
+    uint32_t v0 = 0, v1 = 0;
+    if (i0 != 0xFFFFFFFFu) v0 = stream_byte_masked_raw(src, off, (int32_t)(8 * i0) - (int32_t)lead, nbits) | ((FRAMED && i0 == 0) ? (num_pad << 5) : 0u);
+    if (FRAMED && i1 != 0xFFFFFFFFu) v1 = stream_byte_masked_raw(src, off, (int32_t)(8 * i1) - (int32_t)lead, nbits) | (i1 == 0 ? (num_pad << 5) : 0u);
     auto edges = [&]() {
-        if (has_head) d[lane] = (uint8_t)hv;
-        if (has_tail) d[tail0 + lane] = (uint8_t)tv;
+        if (i0 != 0xFFFFFFFFu) d[i0] = (uint8_t)v0;
+        if (FRAMED && i1 != 0xFFFFFFFFu) d[i1] = (uint8_t)v1;
     };
     if (n_chunks == 0) {
         edges();
@@ -229,7 +236,6 @@ __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ 
     case 2: pack_chunks_a16<2, U>(a, sh, d + head, n_chunks, lane, edges); break;
     default: pack_chunks_a16<3, U>(a, sh, d + head, n_chunks, lane, edges); break;
     }
-    // (head <= 31 and the tail is < 32 bytes -- 16 left over plus a partial chunk -- so one byte per lane covers both)
 }
 
 // ---- decoupled look-back ----------------------------------------------------------------------------------
