@@ -1522,8 +1522,12 @@ static PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
-// Warps per CTA for a persistent one-CTA-per-SM launch: every warp runs ceil(tasks / (SMs*W))
-// whole tasks, so pick the W that wastes the least of the last round (ties: more warps).
+// Warps per CTA for a persistent one-CTA-per-SM launch.  Every warp runs whole tasks, so a launch is a number of
+// full rounds (n_sm * W tasks each) plus a partial one, and a round's duration grows with the warps that share the
+// SM, but far less than proportionally: measured on the rANS kernels, a round of 14 warps per SM takes 0.31 ms and
+// a round of 28 takes 0.44 ms, i.e. t(W) ~ a + b W with a / b ~ 17.  The W that minimises the modelled time wins
+// (ties: more warps).  Counting only the waste of the last round -- what this did before -- picks 12 warps for
+// 65 536 tasks (37 rounds waste 0.3 % of the last one, 16 rounds of 28 warps waste 1.2 %) and runs 45 % slower.
 static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *grid, uint32_t *warps) {
     if (n_tasks <= (uint32_t)n_sm * 8) {  // tiny batch: spread tasks over SMs, few warps each
         uint32_t w = (n_tasks + n_sm - 1) / n_sm;
@@ -1531,14 +1535,14 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
         *grid = (n_tasks + *warps - 1) / *warps;
         return;
     }
-    double best = -1;
+    const uint64_t kFixed = 17;  // a / b of the round-time model
+    uint64_t best = ~0ull;
     uint32_t bw = max_w;
     for (uint32_t w = 8; w <= max_w; ++w) {
-        uint64_t slots = (uint64_t)n_sm * w;
-        uint64_t rounds = (n_tasks + slots - 1) / slots;
-        double eff = (double)n_tasks / (double)(slots * rounds);
-        if (eff >= best - 1e-9) {
-            best = eff;
+        const uint64_t slots = (uint64_t)n_sm * w, full = n_tasks / slots, rem = n_tasks % slots;
+        const uint64_t cost = full * (kFixed + w) + (rem ? kFixed + (rem + n_sm - 1) / n_sm : 0);
+        if (cost <= best) {
+            best = cost;
             bw = w;
         }
     }
@@ -1551,7 +1555,7 @@ extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
 }
 // debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder,
 // bit 5 = its next-stream prefetch goes to L1, bits 6-7 = CTA round barrier every 1 / 2 rounds (default: kSyncRounds),
-// bit 8 = split batches at 64 MiB of rows instead of 4 GiB (so that tests reach the multi-launch path)
+// bit 8 = split batches at 64 MiB of rows instead of 2^30 blocks (so that tests reach the multi-launch path)
 static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
 static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
 constexpr uint32_t kSyncRounds = 0;
@@ -1572,14 +1576,14 @@ static uint32_t max_warps_for(size_t per_warp, size_t fixed) {
 // look-back words a packed launch may need: one per (round, CTA); rounds * grid <= tasks + grid
 static uint64_t packed_state_words(uint64_t n_blocks) { return (n_blocks + 31) / 32 + 4096; }
 
-// A launch whose symbol rows span more than 4 GiB runs ~1.4x slower per block than the same work in launches of
-// <= 4 GiB (decode 1.27 vs 0.87 ms per GiB at 2M x 4 KiB blocks, same DRAM bytes, issue slots 44 % vs 64 %:
-// profiles/r2g_*): big batches are split into launches of whole rounds below that span.
-constexpr uint64_t kLaunchSpanBytes = 1ull << 32;
+// The kernels index rows with 32-bit TMA coordinates and 32-bit task numbers: batches of more than 2^30 blocks are
+// coded by several launches of whole rounds (the fused encoder's running prefix continues across them).
+constexpr uint64_t kLaunchMaxBlocks = 1ull << 30;
 static uint64_t tasks_per_launch(const scl_coder *c, uint64_t n_tasks, uint64_t row_bytes, uint64_t tasks_per_round) {
-    const uint64_t span = (c->debug_mode & 256) ? (64ull << 20) : kLaunchSpanBytes;  // test hook: split at 64 MiB
-    if (n_tasks * 32 * row_bytes <= span) return n_tasks;
-    uint64_t t = span / row_bytes / 32 / tasks_per_round * tasks_per_round;
+    (void)row_bytes;
+    const uint64_t max_tasks = (c->debug_mode & 256) ? (64ull << 20) / row_bytes / 32 : kLaunchMaxBlocks / 32;  // test hook: split at 64 MiB of rows
+    if (n_tasks <= max_tasks) return n_tasks;
+    const uint64_t t = max_tasks / tasks_per_round * tasks_per_round;
     return t < tasks_per_round ? tasks_per_round : t;
 }
 
@@ -1663,7 +1667,7 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
     const uint32_t n_tasks_all = (uint32_t)((io.n_blocks + 31) / 32);
     uint32_t grid, warps;
     pick_launch(n_tasks_all, c->n_sm, max_warps_for(kDecWarpSmem + kDecTileBytes, lut_bytes), &grid, &warps);
-    const uint64_t chunk_tasks = tasks_per_launch(c, n_tasks_all, io.sym_stride, (uint64_t)grid * warps);  // see launch_encode_v2
+    const uint64_t chunk_tasks = tasks_per_launch(c, n_tasks_all, io.sym_stride, (uint64_t)grid * warps);  // > 2^30 blocks: several launches
     size_t smem = (size_t)warps * (kDecWarpSmem + kDecTileBytes) + lut_bytes;
     // pipe-balanced instruction selection pays when the SMs are full (>= 2 rounds of warps); small batches are
     // latency-bound and keep the shorter dependency chain

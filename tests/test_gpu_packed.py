@@ -299,7 +299,7 @@ def test_stream_level_encode_text_symbols_batched(tmp_path):
 
 @pytest.mark.parametrize("framed", [False, True], ids=["packed", "framed"])
 def test_split_launches_give_the_same_streams(framed):
-    """Batches whose rows span more than 4 GiB are coded by several launches of whole rounds (the fused encoder's
+    """Batches of more than 2^30 blocks are coded by several launches of whole rounds (the fused encoder's
     running prefix continues across them).  With the test hook that lowers the span to 64 MiB the same batch is coded
     in one launch and in four: identical bytes, offsets and decoded symbols, both for the slot and the packed form."""
     from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams

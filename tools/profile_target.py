@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--block-len", type=int, default=4096)
     ap.add_argument("--coder", default="rans", choices=["rans", "rans_nbo8", "tans"])
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--py-chunks", type=int, default=1)
     a = ap.parse_args()
     torch.cuda.set_device(0)
     fr = zipf_frequencies()
@@ -30,6 +31,27 @@ def main():
         enc, dec = rANSEncoder(prm), rANSDecoder(prm)
     B, N = a.blocks, a.block_len
     data = sample_blocks(zipf_probabilities(), B, N, seed=0, device="cuda:0")
+    if a.py_chunks > 1:  # the same batch as `py_chunks` separate calls on views (tools/measure_chunking.py under ncu)
+        from stanford_compression_library_b200.device import DecodedBlocks, EncodedBlocks
+
+        e = enc.encode_blocks(data)
+        d = dec.decode_blocks(e, N)
+        torch.cuda.synchronize()
+        abs_off, stride, chunk = e.bit_offset.clone(), e.out_stride, B // a.py_chunks
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            view = EncodedBlocks(e.buf[lo * stride : hi * stride + 16], e.bit_offset[lo:hi], e.bit_len[lo:hi], e.status[lo:hi], stride)
+            enc.encode_blocks(data[lo:hi], reuse=view)
+        rel = abs_off - (torch.arange(B, device="cuda:0", dtype=torch.int64) // chunk) * (chunk * stride * 8)
+        d.symbols.zero_()
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            view = EncodedBlocks(e.buf[lo * stride : hi * stride + 16], rel[lo:hi], e.bit_len[lo:hi], None, stride)
+            dec.decode_blocks(view, N, reuse=DecodedBlocks(d.symbols[lo:hi], d.sizes[lo:hi], d.bits_consumed[lo:hi], d.status[lo:hi]))
+        torch.cuda.synchronize()
+        assert torch.equal(d.symbols[:, :N], data)
+        print("ok (python-level chunks)", B, a.py_chunks)
+        return
     e = p = d = None
     for _ in range(a.repeat):
         e = enc.encode_blocks(data, reuse=e)
