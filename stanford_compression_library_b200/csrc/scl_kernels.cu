@@ -296,44 +296,74 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
     }
 }
 
-// The copy pool: take tickets until the CTA's tasks are exhausted.  Ticket T = (round T / W, warp slot T % W).
-__device__ __forceinline__ void packed_copy_pool(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
-                                                 uint32_t n_tasks, uint32_t lane) {
-    while (true) {
-        uint32_t T = 0;
-        if (lane == 0) T = atomicAdd(&ctl.copy_ticket, 1u);
-        T = __shfl_sync(0xffffffffu, T, 0);
-        const uint32_t r = T / W, slot = T - r * W;
-        const uint64_t task = (uint64_t)r * total_warps + blockIdx.x * W + slot;
-        if (task >= n_tasks) return;  // tickets run through the rounds in order: nothing valid after the first invalid one
-        uint64_t *tr = po.trace ? po.trace + ((uint64_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * kTraceWords : nullptr;
-        uint64_t t0 = 0, t1 = 0;
-        if (lane == 0) {
-            if (tr) t0 = globaltimer_ns();
-            const volatile uint32_t *res = &ctl.resolved;
-            while (*res <= r) __nanosleep(200);
-            if (tr) t1 = globaltimer_ns();
+// The copy pool.  Ticket T = (round T / W, warp slot T % W); tickets run through the CTA's tasks in order.
+// One task: claim the next ticket and copy it.  `block` = wait for the ticket's round to be resolved (the dedicated
+// copy warps, and coding warps that have run out of symbols); otherwise only a ticket whose round IS resolved is
+// claimed (a coding warp that helps while it waits must never wait for a round it has yet to arrive at).
+// Returns 0 = nothing left at all, 1 = copied one task, 2 = nothing claimable right now.
+// (__noinline__: one copy of the code for its three call sites, registers allocated apart from the coding loop's.)
+__device__ __noinline__ uint32_t packed_copy_one(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
+                                                 uint32_t n_tasks, uint32_t lane, bool block) {
+    uint32_t T = 0, got = 1;
+    if (lane == 0) {
+        if (block) {
+            T = atomicAdd(&ctl.copy_ticket, 1u);
+        } else {
+            T = *(volatile uint32_t *)&ctl.copy_ticket;
+            const uint32_t r = T / W;
+            const uint64_t task = (uint64_t)r * total_warps + blockIdx.x * W + (T - r * W);
+            if (task >= n_tasks)
+                got = 0;
+            else if (*(volatile uint32_t *)&ctl.resolved <= r || atomicCAS(&ctl.copy_ticket, T, T + 1) != T)
+                got = 2;
         }
-        __syncwarp();
+    }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got != 1) return got;
+    T = __shfl_sync(0xffffffffu, T, 0);
+    const uint32_t r = T / W, slot = T - r * W;
+    const uint64_t task = (uint64_t)r * total_warps + blockIdx.x * W + slot;
+    if (task >= n_tasks) return 0;  // tickets run through the rounds in order: nothing valid after the first invalid one
+    uint64_t *tr = po.trace ? po.trace + ((uint64_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * kTraceWords : nullptr;
+    uint64_t t0 = 0, t1 = 0;
+    if (lane == 0) {
+        if (tr) t0 = globaltimer_ns();
+        const volatile uint32_t *res = &ctl.resolved;
+        while (*res <= r) __nanosleep(200);
+        if (tr) t1 = globaltimer_ns();
+    }
+    __syncwarp();
+    __threadfence_block();
+    const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][slot];
+    if (po.framed)
+        packed_copy_task<true>(io, po, task, base, lane);
+    else
+        packed_copy_task<false>(io, po, task, base, lane);
+    __syncwarp();
+    if (lane == 0) {
         __threadfence_block();
-        const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][slot];
-        if (po.framed)
-            packed_copy_task<true>(io, po, task, base, lane);
-        else
-            packed_copy_task<false>(io, po, task, base, lane);
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            atomicAdd(&ctl.copy_done, 1u);
-            if (tr) {
-                const uint64_t t2 = globaltimer_ns();
-                if (tr[20] == 0) tr[21] = t1;
-                tr[20] += 1;
-                tr[22] = t2;
-                tr[23] += t2 - t1;
-                tr[24] += t1 - t0;
-            }
+        atomicAdd(&ctl.copy_done, 1u);
+        if (tr) {
+            const uint64_t t2 = globaltimer_ns();
+            if (tr[20] == 0) tr[21] = t1;
+            tr[20] += 1;
+            tr[22] = t2;
+            tr[23] += t2 - t1;
+            tr[24] += t1 - t0;
         }
+    }
+    return 1;
+}
+
+// Wait until *word >= target, copying resolved tasks meanwhile (a coding warp held up by the pool's back-pressure is
+// the pool's best helper: it turns the wait into the work that ends it).  The whole warp calls this.
+__device__ __forceinline__ void packed_wait_helping(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
+                                                    uint32_t n_tasks, uint32_t lane, const uint32_t *word, uint32_t target) {
+    while (true) {
+        uint32_t v = 0;
+        if (lane == 0) v = *(const volatile uint32_t *)word;
+        if (__shfl_sync(0xffffffffu, v, 0) >= target) return;
+        if (packed_copy_one(ctl, io, po, W, total_warps, n_tasks, lane, false) != 1) __nanosleep(200);
     }
 }
 
@@ -457,14 +487,11 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             const uint32_t nvalid = n_tasks - first < W ? n_tasks - first : W;
             const uint32_t par = round & 1;
             uint32_t old = 0;
+            // warp_tot[par] / arrive[par] still belong to round - 2 until that round is resolved (its last warp may be
+            // waiting for the copy pool): nobody arrives at this round before.  This is also how the pool's
+            // back-pressure reaches every coding warp, not just the resolving one -- and a warp held up here copies.
+            if (round >= 2) packed_wait_helping(ctl, io, po, W, total_warps, n_tasks, lane, &ctl.resolved, round - 1);
             if (lane == 0) {
-                // warp_tot[par] / arrive[par] still belong to round - 2 until that round is resolved (its last warp may be
-                // waiting for the copy pool): nobody arrives at this round before.  This is also how the pool's
-                // back-pressure reaches every coding warp, not just the resolving one.
-                if (round >= 2) {
-                    const volatile uint32_t *res = &ctl.resolved;
-                    while (*res < round - 1) __nanosleep(200);
-                }
                 *(volatile unsigned long long *)&ctl.warp_tot[par][warp] = T;
                 __threadfence_block();
                 old = atomicAdd(&ctl.arrive[par], 1u);
@@ -486,10 +513,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
                 if (lane == 0 && first + nvalid == n_tasks) po.byte_off[io.n_blocks] = excl + A;  // the very last round: grand total
                 // warp_excl[par] still serves the copy of round - 2: wait until all of it (and everything before) is done.
                 // Also the back-pressure: the coder never runs more than two rounds ahead of the copy pool.
-                if (round >= 2 && lane == 0) {
-                    const volatile uint32_t *done = &ctl.copy_done;
-                    while (*done < (round - 1) * W) __nanosleep(200);
-                }
+                if (round >= 2) packed_wait_helping(ctl, io, po, W, total_warps, n_tasks, lane, &ctl.copy_done, (round - 1) * W);
                 __syncwarp();
                 if (lane < nvalid) *(volatile unsigned long long *)&ctl.warp_excl[par][lane] = excl + incl - t;
                 __threadfence_block();
@@ -504,7 +528,9 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
         if (sync_rounds && (round + 1) % sync_rounds == 0 && (uint64_t)(round + 1) * total_warps + blockIdx.x * W + (W - 1) < n_tasks)
             asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
-    if (PACKED) packed_copy_pool(ctl, io, po, W, total_warps, n_tasks, lane);  // out of symbols: help move the last rounds
+    if (PACKED)  // a copy warp, or a coding warp that is out of symbols: move streams until the CTA has none left
+        while (packed_copy_one(ctl, io, po, W, total_warps, n_tasks, lane, true)) {
+        }
 }
 
 // Decode.  Output goes through a per-warp 32 x 64-byte tile in shared memory (64-byte swizzle, so
