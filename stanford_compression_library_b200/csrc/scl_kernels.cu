@@ -1566,7 +1566,9 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
     uint32_t bw = max_w;
     for (uint32_t w = 8; w <= max_w; ++w) {
         const uint64_t slots = (uint64_t)n_sm * w, full = n_tasks / slots, rem = n_tasks % slots;
-        const uint64_t cost = full * (kFixed + w) + (rem ? kFixed + (rem + n_sm - 1) / n_sm : 0);
+        // the partial round fills CTAs one after the other (task = CTA * W + warp): as long as one CTA is full it
+        // lasts as long as a full round, whatever the number of idle SMs
+        const uint64_t cost = full * (kFixed + w) + (rem ? kFixed + (rem < w ? rem : w) : 0);
         if (cost <= best) {
             best = cost;
             bw = w;
