@@ -158,7 +158,7 @@ __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uin
         for (int u = 0; u <= U; ++u) A[u] = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (c0 + 32 * u < n_chunks)  // uniform; group n_chunks itself is loaded too: it closes the last chunk's window
+            if (c0 + 32 * u <= n_chunks)  // uniform; group n_chunks itself is loaded too: it closes the last chunk's window
                 ld_plain128_if(A[u], ab, 512 * u, c0 + 32 * u + lane <= n_chunks);
         ld_plain128_if(A[U], ab, 512 * U - 16 * 31, lane == 31 && c0 + 32 * U <= n_chunks);  // group c0 + 32 U, for lane 31's last window
         if (first) {
