@@ -141,11 +141,6 @@ __device__ __forceinline__ void st_plain128(uint8_t *p, const uint4 &v) {
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One batch = 32 * U consecutive 16-byte groups, one load per lane and group; the group AFTER a lane's own (the
-// high words of its five-word window) is the next lane's register, fetched by shuffle -- half the loads and half the
-// registers of loading every pair twice, so U = 8 fits and a whole 4 KiB of a stream is in flight per batch: most
-// streams of the benchmark shape (3.2 KiB) take ONE memory latency.  Lane 31's neighbour is lane 0's group of the
-// next slot; after the last slot it is one extra group loaded by lane 31 alone.
 template <int W0, int U, class Hook>
 __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uint32_t sh, uint8_t *__restrict__ dd, uint32_t n_chunks, uint32_t lane,
                                                 Hook first_batch_hook) {  // n_chunks >= 1
@@ -153,14 +148,20 @@ __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uin
     for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32 * U) {  // c0 is warp-uniform: whole slots of a batch are skipped together
         const uint4 *ab = a + c0 + lane;
         uint8_t *db = dd + 16 * (uint64_t)(c0 + lane);
-        uint4 A[U + 1];
+        uint4 A[U], B[U];
 #pragma unroll
-        for (int u = 0; u <= U; ++u) A[u] = make_uint4(0, 0, 0, 0);
+        for (int u = 0; u < U; ++u) {
+            A[u] = make_uint4(0, 0, 0, 0);
+            B[u] = make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (c0 + 32 * u <= n_chunks)  // uniform; group n_chunks itself is loaded too: it closes the last chunk's window
-                ld_plain128_if(A[u], ab, 512 * u, c0 + 32 * u + lane <= n_chunks);
-        ld_plain128_if(A[U], ab, 512 * U - 16 * 31, lane == 31 && c0 + 32 * U <= n_chunks);  // group c0 + 32 U, for lane 31's last window
+        for (int u = 0; u < U; ++u) {
+            if (c0 + 32 * u < n_chunks) {  // uniform
+                const bool on = c0 + 32 * u + lane < n_chunks;
+                ld_plain128_if(A[u], ab, 512 * u, on);
+                ld_plain128_if(B[u], ab, 512 * u + 16, on);
+            }
+        }
         if (first) {
             first_batch_hook();
             first = false;
@@ -168,29 +169,7 @@ __device__ __forceinline__ void pack_chunks_a16(const uint4 *__restrict__ a, uin
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (c0 + 32 * u < n_chunks) {
-                // B = the group after this lane's: lane + 1's A[u], or (lane 31) lane 0's A[u + 1] / the extra group
-                uint4 B;
-                const uint4 &N0 = A[u + 1];
-                B.x = __shfl_down_sync(0xffffffffu, A[u].x, 1);
-                const uint32_t wx = u + 1 < U ? __shfl_sync(0xffffffffu, N0.x, 0) : N0.x;
-                if (lane == 31) B.x = wx;
-                B.y = B.z = B.w = 0;
-                if (W0 >= 1) {
-                    B.y = __shfl_down_sync(0xffffffffu, A[u].y, 1);
-                    const uint32_t wy = u + 1 < U ? __shfl_sync(0xffffffffu, N0.y, 0) : N0.y;
-                    if (lane == 31) B.y = wy;
-                }
-                if (W0 >= 2) {
-                    B.z = __shfl_down_sync(0xffffffffu, A[u].z, 1);
-                    const uint32_t wz = u + 1 < U ? __shfl_sync(0xffffffffu, N0.z, 0) : N0.z;
-                    if (lane == 31) B.z = wz;
-                }
-                if (W0 >= 3) {
-                    B.w = __shfl_down_sync(0xffffffffu, A[u].w, 1);
-                    const uint32_t ww = u + 1 < U ? __shfl_sync(0xffffffffu, N0.w, 0) : N0.w;
-                    if (lane == 31) B.w = ww;
-                }
-                if (c0 + 32 * u + lane < n_chunks) st_plain128(db + 512 * u, pack_chunk_from_pair_raw<W0>(A[u], B, sh));
+                if (c0 + 32 * u + lane < n_chunks) st_plain128(db + 512 * u, pack_chunk_from_pair_raw<W0>(A[u], B[u], sh));
             }
         }
     }
@@ -214,7 +193,7 @@ __device__ __forceinline__ uint32_t stream_byte_masked_raw(const uint8_t *__rest
 template <bool FRAMED>
 __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ src, uint64_t off, uint32_t nbits, uint8_t *__restrict__ d,
                                                     uint32_t lane) {
-    constexpr int U = 7;  // 3.5 KiB per batch: one batch for the 3.2 KiB streams of the benchmark shape
+    constexpr int U = 4;
     const uint32_t num_pad = FRAMED ? ((8u - (nbits + 3u) % 8u) % 8u) : 0u;
     const uint32_t lead = FRAMED ? 3u + num_pad : 0u;
     const uint32_t payload_bytes = FRAMED ? (nbits + lead) >> 3 : (nbits + 7u) >> 3;
