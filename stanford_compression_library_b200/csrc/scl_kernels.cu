@@ -230,7 +230,6 @@ struct PackedOut {
     uint32_t framed;
     uint64_t g_base;         // look-back index of this launch's (round 0, CTA 0): a split batch continues the numbering
     uint32_t copy_warps;     // dedicated copy warps of the CTA (kCopyWarps)
-    uint32_t prefetch_l1;    // experiment knob: request the next stream into L1 instead of L2
     uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
 };
 constexpr uint32_t kTraceWords = 40;  // per warp: [0] start, [1 + r] end of coding round r (r < 19), [20] tasks copied, [21] first copy
@@ -283,10 +282,7 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
         const uint32_t bits_n = __shfl_sync(0xffffffffu, bits, (l + 1) & 31), nb_n = __shfl_sync(0xffffffffu, nb, (l + 1) & 31);
         if (l + 1 < 32 && bits_n) {
             const uint8_t *p0 = io.out + (((slot_end + stride_bits - bits_n) >> 3) & ~127ull);
-            if (po.prefetch_l1)
-                for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(p0 + o));
-            else
-                for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+            for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
         if (bits_l) pack_block_warp_a16<FRAMED>(io.out, slot_end - bits_l, bits_l, po.dst + at, lane);
         at += nb_l;
@@ -370,7 +366,7 @@ __device__ __forceinline__ void packed_wait_helping(PackCtl &ctl, const BlockIo 
 template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
 __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
-                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, uint32_t sync_rounds, PackedOut po) {
+                          uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, PackedOut po) {
     __shared__ PackCtl ctl;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // round the dynamic window up to 2 KiB so that ring addresses can be composed with OR
@@ -521,12 +517,6 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
                 if (lane == 0) *(volatile uint32_t *)&ctl.resolved = round + 1;
             }
         }
-        // Keep the CTA's coding warps within `sync_rounds` rounds of each other: a warp's 32 rows and 32 streams sit in
-        // one or two 2 MiB pages, consecutive warps share them, so a CTA in step touches a handful of pages while
-        // warps that have drifted rounds apart touch dozens (measured at 2M blocks: tools/measure_chunking.py).
-        // Only between rounds that every coding warp of the CTA has (the last round may be partial).
-        if (sync_rounds && (round + 1) % sync_rounds == 0 && (uint64_t)(round + 1) * total_warps + blockIdx.x * W + (W - 1) < n_tasks)
-            asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
     if (PACKED)  // a copy warp, or a coding warp that is out of symbols: move streams until the CTA has none left
         while (packed_copy_one(ctl, io, po, W, total_warps, n_tasks, lane, true)) {
@@ -544,7 +534,7 @@ constexpr uint32_t kDecTileBytes = 32 * kTileCols;
 template <int KIND, uint32_t NBO, bool BAL>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     fast_decode_v2_kernel(const __grid_constant__ CUtensorMap out_map, uint32_t use_tiles, const uint32_t *__restrict__ g_lut,
-                          uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks, uint32_t sync_rounds) {
+                          uint32_t lut_bytes, RansConst c, DecodeIo io, uint32_t n_tasks) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -558,8 +548,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
     typename std::conditional<KIND == 0, RansStepper<NBO, BAL>, TansStepper<BAL>>::type S;
     S.init(saddr_of(s_lut), c);
 
-    uint32_t round = 0;
-    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         DecLaneV2 D;
@@ -624,9 +613,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
             io.status[b] = st;
         }
         __syncwarp();
-        // keep the CTA's warps in step (see fast_encode_v2_kernel): page locality of rows and streams
-        if (sync_rounds && (round + 1) % sync_rounds == 0 && (uint64_t)(round + 1) * total_warps + blockIdx.x * W + (W - 1) < n_tasks)
-            asm volatile("bar.sync 1, %0;" ::"r"(W * 32) : "memory");
     }
 }
 
@@ -1581,13 +1567,11 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
 extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
     if (c) c->debug_mode = mode;
 }
-// debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder,
-// bit 5 = its next-stream prefetch goes to L1, bits 6-7 = CTA round barrier every 1 / 2 rounds (default: kSyncRounds),
-// bit 8 = split batches at 64 MiB of rows instead of 2^30 blocks (so that tests reach the multi-launch path)
+// debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder
+// (measured slower: tools/sweep_knobs.py), bit 8 = split batches at 64 MiB of rows instead of 2^30 blocks (so that
+// tests reach the multi-launch path)
 static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
 static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
-constexpr uint32_t kSyncRounds = 0;
-static inline uint32_t sync_rounds_of(const scl_coder *c) { return (c->debug_mode & 64) ? 1u : (c->debug_mode & 128) ? 2u : kSyncRounds; }
 extern "C" void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words) {
     if (c) {
         c->d_trace = d_trace;
@@ -1634,7 +1618,6 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     if (packed) {
         po = *packed;
         po.copy_warps = copy_warps;
-        po.prefetch_l1 = (c->debug_mode & 32) ? 1u : 0u;
         po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
         // one look-back word per (round, CTA) of the WHOLE batch: the launches of a split batch are whole rounds, so the
         // numbering (and with it the running prefix) simply continues from launch to launch
@@ -1669,7 +1652,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     do {                                                                                                                           \
         e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
-        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, cio, n_tasks, sync_rounds_of(c), po); \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, cio, n_tasks, po); \
     } while (0)
         if (rc.check_sym) {
             if (packed)
@@ -1726,7 +1709,7 @@ static int launch_decode_v2(const scl_coder *c, const RansConst &rc, const uint3
             use_tiles = enc(&omap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)cio.sym, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
-        kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, cio, (uint32_t)((cio.n_blocks + 31) / 32), sync_rounds_of(c));
+        kern<<<grid, warps * 32, smem, s>>>(omap, use_tiles, lut, lut_bytes, rc, cio, (uint32_t)((cio.n_blocks + 31) / 32));
         int rc2 = check_launch("fast_decode_v2_kernel");
         if (rc2) return rc2;
     }
@@ -1908,7 +1891,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, 0u, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);

@@ -1,5 +1,6 @@
-"""Experiment knobs of the second-generation rANS kernels (scl_coder_debug_path high bits): CTA round barrier,
-copy-warp count, prefetch level.  Diagnostic; one JSON line per (blocks, mode).
+"""Experiment knobs of the second-generation rANS kernels (scl_coder_debug_path high bits).  The CTA round barrier and
+the L1 prefetch this tool was written for measured no effect (profiles/r2f_sweep.jsonl) and are gone from the kernels;
+what is left is the copy-warp count of the packed encoder.  Diagnostic; one JSON line per (blocks, mode).
     python tools/sweep_knobs.py [--blocks 262144 2097152]"""
 import argparse
 import json
@@ -44,14 +45,14 @@ def main():
         d = dec.decode_blocks(p, N).check()
         ref = p.buf[: int(p.byte_offset[-1])].clone()
         gib = B * N / 2**30
-        for mode in (0, SYNC1, SYNC2):
+        for mode in (0,):
             enc.device_coder().debug_path(mode)
             dec.device_coder().debug_path(mode)
             te = timeit(lambda: enc.encode_blocks(data, reuse=e))
             td = timeit(lambda: dec.decode_blocks(p, N, reuse=d))
             assert torch.equal(d.symbols[:, :N], data)
             print(json.dumps({"blocks": B, "mode": mode, "encode_slots_ms_per_GiB": te / gib, "decode_ms_per_GiB": td / gib}), flush=True)
-        for mode in (0, L1, COPY8, COPY8 | L1, SYNC1, SYNC1 | L1, SYNC2 | L1, SYNC1 | COPY8 | L1):
+        for mode in (0, COPY8):
             enc.device_coder().debug_path(mode)
             tp = timeit(lambda: enc.encode_blocks_packed(data, capacity=B * N, reuse=p))
             p.check()
