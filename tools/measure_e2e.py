@@ -29,7 +29,27 @@ def main():
     host_out = torch.empty((B, N), dtype=torch.uint8, pin_memory=True)
     host_c = torch.empty(B * N, dtype=torch.uint8, pin_memory=True)
     del data
-    for chunk, depth in ((32768, 2), (32768, 3), (16384, 3), (8192, 3), (8192, 4), (4096, 4)):
+    # kernel time of one chunk-sized launch (what the pipeline's compute stream runs per chunk)
+    for nb in (8192, 16384, 32768, 65536):
+        d = torch.empty((nb, N), dtype=torch.uint8, device="cuda:0").copy_(host_in[:nb])
+        p = enc.encode_blocks_packed(d)
+        o = dec.decode_blocks(p, N)
+        ts = []
+        for fn in (lambda: enc.encode_blocks_packed(d, reuse=p), lambda: dec.decode_blocks(p, N, reuse=o)):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            ts.append(best)
+        print(json.dumps(dict(chunk_blocks=nb, encode_packed_kernel_ms=ts[0], decode_kernel_ms=ts[1], h2d_ms_at_55GBps=nb * N / 55e6)), flush=True)
+        del d, p, o
+    for chunk, depth in ((65536, 3), (32768, 3), (16384, 3), (16384, 4), (8192, 4)):
         pipe = HostCodecPipeline(enc, dec, N, B, chunk_blocks=chunk, depth=depth)
         total, lens = pipe.encode(host_in, host_c)
         pipe.decode(host_c, lens, host_out)

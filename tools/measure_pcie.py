@@ -48,6 +48,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
     node = numa_of_gpu(local)
     bound = None

@@ -1,5 +1,5 @@
 """One launch of each second-generation rANS kernel at a given batch size, for ncu:
-    ncu --set full --clock-control none --import-source on -k regex:fast_ -o out python tools/profile_target.py --blocks 262144
+    ncu --set full --clock-control none --import-source on -k regex:"fast_|pack_v2|range_" -o out python tools/profile_target.py --blocks 262144 --with-pack
 Launch order: encode (slots), encode (packed, fused), decode (from the packed stream).  --repeat N repeats the triple."""
 import argparse
 import os
@@ -17,7 +17,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=262144)
     ap.add_argument("--block-len", type=int, default=4096)
-    ap.add_argument("--coder", default="rans", choices=["rans", "rans_nbo8", "tans"])
+    ap.add_argument("--coder", default="rans", choices=["rans", "rans_nbo8", "tans", "range"])
+    ap.add_argument("--with-pack", action="store_true", help="also run the standalone compaction / framing kernels on the slot output")
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--py-chunks", type=int, default=1)
     a = ap.parse_args()
@@ -26,6 +27,11 @@ def main():
     if a.coder == "tans":
         prm = tANSParams(fr, RANGE_FACTOR=1)
         enc, dec = tANSEncoder(prm), tANSDecoder(prm)
+    elif a.coder == "range":
+        from stanford_compression_library_b200.compressors.range_coder import RangeCoderParams, RangeDecoder, RangeEncoder
+
+        prm = RangeCoderParams()
+        enc, dec = RangeEncoder(prm, fr), RangeDecoder(prm, fr)
     else:
         prm = rANSParams(fr) if a.coder == "rans" else rANSParams(fr, NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12)
         enc, dec = rANSEncoder(prm), rANSDecoder(prm)
@@ -57,6 +63,9 @@ def main():
         e = enc.encode_blocks(data, reuse=e)
         p = enc.encode_blocks_packed(data, capacity=B * N, reuse=p)
         d = dec.decode_blocks(p, N, reuse=d)
+    if a.with_pack:
+        e.pack()
+        e.frame()
     torch.cuda.synchronize()
     e.check(), p.check(), d.check()
     assert torch.equal(d.symbols[:, :N], data)
