@@ -213,7 +213,7 @@ int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *d
  * first-generation kernels (per-lane direct global access) instead of the TMA/ring kernels; 2 =
  * second-generation decode with per-lane sector stores instead of TMA tile stores; 3 / 4 =
  * second-generation decode always / never in its pipe-balanced instruction selection (normally
- * chosen by batch size); 0 = default.  Keeps every code path parity-tested.  Set it before issuing
+ * chosen by batch size); 5 = the arithmetic coder keeps 16-bit counters where it would take 8-bit ones; 0 = default.  Keeps every code path parity-tested.  Set it before issuing
  * work on the handle; it is read at launch time. */
 void scl_coder_debug_path(scl_coder *c, int mode);
 
@@ -222,6 +222,13 @@ void scl_coder_debug_path(scl_coder *c, int mode);
  * and the copy pool's task count / first start / last end / busy and waiting time (tools/trace_packed.py prints
  * the timeline).  NULL switches it off (the default); the kernels test one pointer per round, nothing per symbol. */
 void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words);
+
+/* Diagnostic: re-run only the copy stage of a finished scl_encode_blocks_packed call (same buffers, left as that call
+ * left them) with `warps_per_cta` warps on each SM and no coder beside them -- how fast is the copy pool alone?
+ * (tools/measure_copy_only.py).  Second-generation rANS / tANS handles only. */
+int scl_debug_copy_only(const scl_coder *c, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride, uint8_t *d_dst,
+                        uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset, uint64_t *d_bit_offset,
+                        uint64_t *d_bit_len, uint32_t *d_status, uint32_t warps_per_cta, void *stream);
 
 const char *scl_last_cuda_error(void);
 const char *scl_version(void);

@@ -80,6 +80,8 @@ def lib():
     L.scl_histogram_blocks.argtypes = [vp, u64, vp, u32, u64, vp, vp, vp]
     L.scl_coder_debug_path.restype = None
     L.scl_coder_debug_path.argtypes = [vp, i32]
+    L.scl_debug_copy_only.restype = i32
+    L.scl_debug_copy_only.argtypes = [vp, u64, vp, u64, vp, u64, u32, vp, vp, vp, vp, u32, vp]
     L.scl_coder_debug_trace.restype = None
     L.scl_coder_debug_trace.argtypes = [vp, vp, u64]
     L.scl_last_cuda_error.restype = ctypes.c_char_p
@@ -90,7 +92,7 @@ def lib():
 
 EXPORTS = [
     "scl_coder_create", "scl_coder_destroy", "scl_coder_max_encoded_bytes", "scl_coder_model_words", "scl_coder_path", "scl_encode_blocks",
-    "scl_decode_blocks", "scl_packed_offsets", "scl_encode_packed_workspace_bytes", "scl_encode_blocks_packed", "scl_pack_blocks", "scl_frame_blocks", "scl_tans_tables_to_host", "scl_histogram_blocks", "scl_coder_debug_path", "scl_coder_debug_trace", "scl_last_cuda_error", "scl_version",
+    "scl_decode_blocks", "scl_packed_offsets", "scl_encode_packed_workspace_bytes", "scl_encode_blocks_packed", "scl_pack_blocks", "scl_frame_blocks", "scl_tans_tables_to_host", "scl_histogram_blocks", "scl_coder_debug_path", "scl_coder_debug_trace", "scl_debug_copy_only", "scl_last_cuda_error", "scl_version",
 ]
 
 

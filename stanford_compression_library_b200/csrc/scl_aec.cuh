@@ -199,6 +199,236 @@ struct AecIidPolicy {
     }
 };
 
+// ---- the same model at half the shared memory: 8-bit counters ----------------------------------------------
+// profiles/r1s: the arithmetic coder is latency-bound with 11-12 resident warps per SM, and what caps the residency
+// is the model (136 words = 17 KiB per warp).  With one BYTE per counter it is 8 + 64 words (9 KiB per warp, 20
+// warps per SM).  A counter that passes 255 wraps and its high part moves to a short per-lane list held in a
+// register (`big`: up to kAecBigMax entries of sym : 8 | high : 4) -- exact, and almost never populated: at cfg4
+// (1 KiB blocks from 256 ones) the most frequent Zipf symbol reaches ~205.  The host selects this model only when
+// the list cannot overflow: every initial count <= 255 and (sum of initial counts + block length) / 256 <= kAecBigMax
+// symbols can ever reach 256.  Group totals stay 16-bit (the whole table sums to < 65 536 under that bound).
+// All paths that involve `big` are slow generic loops on purpose.
+constexpr uint32_t kAecModel8Words = 8 + 64;  // G[16] as u16 pairs + C[256] as bytes
+constexpr uint32_t kAecBigMax = 5;
+
+SCL_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {  // c + sum of a.u8[i] * b.u8[i]
+#ifdef __CUDA_ARCH__
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFFu) * ((b >> (8 * i)) & 0xFFu);
+    return c;
+#endif
+}
+
+struct AecModel8 {
+    saddr_t w;
+    uint32_t stride;
+    saddr_t masks;
+    uint32_t mstride;
+    uint64_t big;  // kAecBigMax x 12 bits: sym | high << 8, high >= 1 for a live entry
+    uint32_t ovf;
+    SCL_HD uint32_t word(uint32_t i) const { return lds32(w + (saddr_t)(i * stride)); }
+    SCL_HD void set_word(uint32_t i, uint32_t v) const { sts32(w + (saddr_t)(i * stride), v); }
+    SCL_HD uint32_t hi_of(uint32_t idx) const {
+        if (big == 0) return 0;
+        uint32_t h = 0;
+        for (uint32_t k = 0; k < kAecBigMax; ++k) {
+            const uint32_t e = (uint32_t)(big >> (12 * k)) & 0xFFFu;
+            if (e && (e & 0xFFu) == idx) h = e >> 8;
+        }
+        return h;
+    }
+    SCL_HD void big_inc(uint32_t idx) {  // the counter of idx wrapped: its high part grows by one
+        int free_k = -1;
+        for (uint32_t k = 0; k < kAecBigMax; ++k) {
+            const uint32_t e = (uint32_t)(big >> (12 * k)) & 0xFFFu;
+            if (e && (e & 0xFFu) == idx) {
+                big += 1ull << (12 * k + 8);
+                return;
+            }
+            if (!e && free_k < 0) free_k = (int)k;
+        }
+        if (free_k < 0) {
+            ovf = 1;  // cannot happen under the host's bound
+            return;
+        }
+        big |= (uint64_t)(idx | 0x100u) << (12 * free_k);
+    }
+    SCL_HD uint32_t lo_of(uint32_t idx) const { return (word(8 + (idx >> 2)) >> (8 * (idx & 3))) & 0xFFu; }
+    SCL_HD uint32_t count(uint32_t idx) const { return lo_of(idx) + (hi_of(idx) << 8); }
+    // sum of the first t (0..16) group totals (16-bit pairs in words 0..7): as AecModel::masked_sum
+    SCL_HD uint32_t group_prefix(uint32_t t) const {
+        const u32x4 m = lds128(masks + (saddr_t)(t * mstride));
+        uint32_t s = 0;
+        s = dp2a_lo(word(0), m.x, s);
+        s = dp2a_hi(word(1), m.x, s);
+        s = dp2a_lo(word(2), m.y, s);
+        s = dp2a_hi(word(3), m.y, s);
+        s = dp2a_lo(word(4), m.z, s);
+        s = dp2a_hi(word(5), m.z, s);
+        s = dp2a_lo(word(6), m.w, s);
+        s = dp2a_hi(word(7), m.w, s);
+        return s;
+    }
+    // sum of the first t (0..16) byte counters of group g (words 8 + 4g .. +3), low parts only
+    SCL_HD uint32_t byte_prefix(uint32_t g, uint32_t t) const {
+        const u32x4 m = lds128(masks + (saddr_t)(t * mstride));
+        const saddr_t a = w + (saddr_t)((8 + 4 * g) * stride);
+        uint32_t s = 0;
+        s = dp4a_u(lds32(a), m.x, s);
+        s = dp4a_u(lds32(a + (saddr_t)stride), m.y, s);
+        s = dp4a_u(lds32(a + (saddr_t)(2 * stride)), m.z, s);
+        s = dp4a_u(lds32(a + (saddr_t)(3 * stride)), m.w, s);
+        return s;
+    }
+    SCL_HD uint32_t big_below(uint32_t g, uint32_t lo) const {  // high parts of the symbols of group g below position lo
+        uint32_t s = 0;
+        for (uint32_t k = 0; k < kAecBigMax; ++k) {
+            const uint32_t e = (uint32_t)(big >> (12 * k)) & 0xFFFu, sy = e & 0xFFu;
+            if (e && (sy >> 4) == g && (sy & 15u) < lo) s += (e >> 8) << 8;
+        }
+        return s;
+    }
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const {
+        const uint32_t g = idx >> 4, lo = idx & 15;
+        cum = group_prefix(g) + byte_prefix(g, lo);
+        f = lo_of(idx);
+        if (big) {
+            cum += big_below(g, lo);
+            f += hi_of(idx) << 8;
+        }
+    }
+    SCL_HD void add1(uint32_t idx) {
+        const uint32_t cw = 8 + (idx >> 2), sh = 8 * (idx & 3), gw = idx >> 5;
+        const uint32_t wv = word(cw);
+        if (((wv >> sh) & 0xFFu) == 0xFFu) {
+            set_word(cw, wv - (0xFFu << sh));  // 255 -> 0, carry into the list instead of the neighbour byte
+            big_inc(idx);
+        } else {
+            set_word(cw, wv + (1u << sh));
+        }
+        set_word(gw, word(gw) + (((idx >> 4) & 1) ? 0x10000u : 1u));
+    }
+    // last index whose cumulative count is <= v (numpy.searchsorted(side="right") - 1); v < total
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        uint32_t pre = 0, g = 0, base = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            uint32_t wv = word(j);
+            uint32_t t1 = pre + (wv & 0xFFFFu), t2 = t1 + (wv >> 16);
+            bool c1 = t1 <= v, c2 = t2 <= v;
+            g += (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
+            base = c2 ? t2 : (c1 ? t1 : base);
+            pre = t2;
+        }
+        g = g > 15 ? 15 : g;
+        uint32_t lo = 0, b2 = base;
+        pre = base;
+        if (big == 0) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                const uint32_t wv = word(8 + 4 * g + j);
+#pragma unroll
+                for (uint32_t b = 0; b < 4; ++b) {
+                    const uint32_t t = pre + ((wv >> (8 * b)) & 0xFFu);
+                    const bool c = t <= v;
+                    lo += c ? 1u : 0u;
+                    b2 = c ? t : b2;
+                    pre = t;
+                }
+            }
+        } else {
+            for (uint32_t j = 0; j < 16; ++j) {
+                const uint32_t t = pre + count(g * 16 + j);
+                const bool c = t <= v;
+                lo += c ? 1u : 0u;
+                b2 = c ? t : b2;
+                pre = t;
+            }
+        }
+        lo = lo > 15 ? 15 : lo;
+        const uint32_t idx = g * 16 + lo;
+        cum = b2;
+        f = count(idx);
+        return idx;
+    }
+    SCL_HD void load(const uint32_t *init_freq, uint32_t n_sym, uint64_t &total) {  // every count <= 255 (host-checked)
+        big = 0;
+        ovf = 0;
+        total = 0;
+        for (uint32_t g = 0; g < 16; g += 2) {
+            uint32_t gs[2] = {0, 0};
+            for (uint32_t h = 0; h < 2; ++h)
+                for (uint32_t j = 0; j < 16; j += 4) {
+                    uint32_t wv = 0;
+                    for (uint32_t b = 0; b < 4; ++b) {
+                        const uint32_t i = (g + h) * 16 + j + b;
+                        const uint32_t fr = i < n_sym ? init_freq[i] : 0u;
+                        wv |= (fr & 0xFFu) << (8 * b);
+                        gs[h] += fr;
+                    }
+                    set_word(8 + (((g + h) * 16 + j) >> 2), wv);
+                }
+            set_word(g >> 1, gs[0] | (gs[1] << 16));
+            total += gs[0] + gs[1];
+        }
+    }
+    // AdaptiveIIDFreqModel's halving (probability_models.py:90-92): f = max(f // 2, 1) for every symbol
+    SCL_HD void halve(uint32_t n_sym, uint64_t &total) {
+        uint64_t nbig = 0;
+        uint32_t nk = 0;
+        total = 0;
+        for (uint32_t g = 0; g < 16; ++g) {
+            uint32_t gsum = 0;
+            for (uint32_t j = 0; j < 16; ++j) {
+                const uint32_t i = g * 16 + j;
+                if (i < n_sym) {
+                    uint32_t h = count(i) >> 1;  // reads the OLD list and this symbol's own, still unmodified, byte
+                    h = h > 1 ? h : 1;
+                    const uint32_t cw = 8 + (i >> 2), sh = 8 * (i & 3), wv = word(cw);
+                    set_word(cw, (wv & ~(0xFFu << sh)) | ((h & 0xFFu) << sh));
+                    if (h >> 8) {
+                        nbig |= (uint64_t)(i | ((h >> 8) << 8)) << (12 * nk);
+                        ++nk;  // halving never creates more big symbols than there were
+                    }
+                    gsum += h;
+                }
+            }
+            const uint32_t gw = g >> 1, wv = word(gw);
+            set_word(gw, (g & 1) ? ((wv & 0xFFFFu) | (gsum << 16)) : ((wv & 0xFFFF0000u) | gsum));
+            total += gsum;
+        }
+        big = nbig;
+    }
+};
+
+struct AecIid8Policy {
+    AecModel8 M;
+    uint32_t tot, adaptive, max_total, n_sym;
+    SCL_HD uint32_t total() const { return tot; }
+    SCL_HD void query(uint32_t idx, uint32_t &cum, uint32_t &f) const { M.query(idx, cum, f); }
+    SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
+        uint32_t idx = M.find(v, cum, f);
+        if (idx >= n_sym) {
+            idx = n_sym - 1;
+            M.query(idx, cum, f);
+        }
+        return idx;
+    }
+    SCL_HD uint32_t update(uint32_t idx) {
+        if (adaptive) {
+            M.add1(idx);
+            tot += 1;
+            if (tot >= max_total) {  // :90-92
+                uint64_t t64 = tot;
+                M.halve(n_sym, t64);
+                tot = (uint32_t)t64;
+            }
+        }
+        return M.ovf ? SCL_ST_OVERFLOW : SCL_ST_OK;
+    }
+};
+
 // AdaptiveOrderKFreqModel (probability_models.py:95-168).  Per lane: n_ctx = n_sym^k rows of n_sym
 // 32-bit counters (freqs_kplus1_tuple, row-major) followed by the n_ctx row totals; word i is
 // `stride` bytes after word i-1 like AecModel.  The row index is the base-n_sym number of the past k

@@ -363,6 +363,20 @@ __device__ __forceinline__ void packed_wait_helping(PackCtl &ctl, const BlockIo 
     }
 }
 
+// Diagnostic (scl_debug_copy_only): the copy pool's work WITHOUT the coder beside it -- `warps` warps per CTA re-copy
+// the tasks of a finished fused encode (scratch slots, bit lengths and record offsets as that call left them).
+// Separates "a copy warp is slow because it waits for memory" from "... because 28 coding warps take its issue slots".
+__global__ void __launch_bounds__(1024, 1) copy_only_kernel(BlockIo io, PackedOut po, uint32_t n_tasks) {
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += gridDim.x * W) {
+        const uint64_t base = po.byte_off[(uint64_t)task * 32];
+        if (po.framed)
+            packed_copy_task<true>(io, po, task, base, lane);
+        else
+            packed_copy_task<false>(io, po, task, base, lane);
+    }
+}
+
 template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
 __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
@@ -1026,6 +1040,70 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_decode_kernel(const AecT
     uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
     if (b >= io.n_blocks) return;
     AecIidPolicy pol = aec2_iid_policy(M, s_tab, c);
+    uint64_t used = 0;
+    BitReader r;
+    uint64_t off = io.bit_off[b];
+    r.init(io.in, io.in_bytes, off);
+    uint32_t size = 0;
+    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    io.sizes[b] = size;
+    io.consumed[b] = used;
+    io.status[b] = st;
+}
+
+// The same kernels on the 8-bit-counter model (AecModel8): 9 KiB of shared memory per warp instead of 17, so 20
+// instead of 12 resident warps per SM for a coder that is latency-bound (profiles/r1s).  Selected by the host when
+// the model cannot overflow its escape list (AecHost::model8_ok).
+constexpr uint32_t kAec8ModelBytes = kAecModel8Words * 128;  // per warp
+
+__device__ __forceinline__ AecIid8Policy aec8_setup(uint8_t *smem, const AecTab *g_tab, AecTab *s_tab, uint64_t *mbar, const AecConst &c) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *masks = smem;
+    for (uint32_t i = threadIdx.x; i < 17 * kEncTabCopies * 16; i += blockDim.x) {
+        uint32_t t = i / (kEncTabCopies * 16), k = i % 16;
+        masks[i] = k < t ? 1 : 0;
+    }
+    stage_table(s_tab, g_tab, sizeof(AecTab), mbar);  // includes a __syncthreads
+    __syncthreads();
+    AecIid8Policy pol;
+    pol.M.w = saddr_of(smem + kAec2MaskBytes + warp * kAec8ModelBytes) + lane * 4;
+    pol.M.stride = 128;
+    pol.M.masks = saddr_of(masks) + (lane & (kEncTabCopies - 1)) * 16;
+    pol.M.mstride = kEncTabCopies * 16;
+    uint64_t total = 0;
+    pol.M.load(s_tab->init_freq, c.n_sym, total);
+    pol.tot = (uint32_t)total;
+    pol.adaptive = c.model == SCL_MODEL_ADAPTIVE_IID;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    pol.n_sym = c.n_sym;
+    return pol;
+}
+
+__global__ void __launch_bounds__(kAec2Warps * 32) aec8_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    AecIid8Policy pol = aec8_setup(s_dyn, g_tab, &s_tab, &mbar, c);  // (lanes past the batch load a model nobody uses)
+    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    if (b >= io.n_blocks) return;
+    uint64_t bits = 0;
+    uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
+    FwdBitWriter w;
+    uint8_t *slot = io.out + b * io.out_stride;
+    w.init(slot, slot + io.out_stride);
+    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    io.bit_len[b] = bits;
+    io.bit_off[b] = b * io.out_stride * 8;
+    io.status[b] = st;
+}
+
+__global__ void __launch_bounds__(kAec2Warps * 32) aec8_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    __shared__ AecTab s_tab;
+    __shared__ uint64_t mbar;
+    AecIid8Policy pol = aec8_setup(s_dyn, g_tab, &s_tab, &mbar, c);
+    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    if (b >= io.n_blocks) return;
     uint64_t used = 0;
     BitReader r;
     uint64_t off = io.bit_off[b];
@@ -1833,6 +1911,13 @@ static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
         // second generation: every counter and group total must stay below 65536
+        if (!d_model && !force_v1(c) && dbg_path(c) != 5 && c->aec->model8_ok(block_len)) {  // debug path 5: keep the 16-bit counters
+            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
+            size_t smem = kAec2MaskBytes + kAec2Warps * kAec8ModelBytes;
+            SCL_CUDA(cudaFuncSetAttribute(aec8_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            aec8_encode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            return check_launch("aec8_encode_kernel");
+        }
         if (!d_model && 16 * max_init + block_len < 65536 && !force_v1(c)) {
             uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
             size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;
@@ -1901,6 +1986,17 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
     if (rc) return rc;
     PackIo pio{d_scratch, d_bit_offset, d_bit_len, n_blocks, d_dst, dst_bytes, d_byte_offset, d_status, d_bit_offset};
     return pack_launch(pio, framed != 0, false, s);
+}
+
+extern "C" int scl_debug_copy_only(const scl_coder *c, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride, uint8_t *d_dst,
+                                   uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset, uint64_t *d_bit_offset, uint64_t *d_bit_len,
+                                   uint32_t *d_status, uint32_t warps_per_cta, void *stream) {
+    if (!c || !d_scratch || !d_dst || !d_byte_offset || !d_bit_offset || !d_bit_len || !d_status || warps_per_cta < 1 || warps_per_cta > 32)
+        return SCL_E_INVALID;
+    BlockIo io{nullptr, 0, nullptr, 0, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_status, 0};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, nullptr, framed ? 1u : 0u, 0, kCopyWarps, nullptr};
+    copy_only_kernel<<<c->n_sm > 0 ? c->n_sm : 148, warps_per_cta * 32, 0, (cudaStream_t)stream>>>(io, po, (uint32_t)((n_blocks + 31) / 32));
+    return check_launch("copy_only_kernel");
 }
 
 extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64_t in_bytes, const uint64_t *d_bit_offset,
@@ -1975,6 +2071,13 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         uint32_t g = (uint32_t)((n_blocks + kAecThreads - 1) / kAecThreads);
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
+        if (!d_model && !force_v1(c) && dbg_path(c) != 5 && c->aec->model8_ok(sym_stride)) {  // decoded size <= sym_stride is enforced by the lane
+            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
+            size_t smem = kAec2MaskBytes + kAec2Warps * kAec8ModelBytes;
+            SCL_CUDA(cudaFuncSetAttribute(aec8_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            aec8_decode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            return check_launch("aec8_decode_kernel");
+        }
         if (!d_model && 16 * max_init + sym_stride < 65536 && !force_v1(c)) {  // decoded size <= sym_stride is enforced by the lane
             uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
             size_t smem = kAec2MaskBytes + kAec2Warps * kAec2ModelBytes;

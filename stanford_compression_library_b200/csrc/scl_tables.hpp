@@ -334,6 +334,20 @@ struct AecHost {
     // the size header and the <= P+1 termination bits
     uint64_t max_encoded_bits(uint64_t n) const { return (uint64_t)c.DBSB + (uint64_t)c.P * n + c.P + 2; }
     uint64_t model_words() const { return c.model == SCL_MODEL_ORDER_K ? (uint64_t)c.n_ctx * c.n_sym + 1 : c.n_sym; }
+    // may blocks of up to `block_len` symbols use the 8-bit-counter model (scl_aec.cuh AecModel8)?  Every initial count must
+    // fit a byte, and at most kAecBigMax symbols may ever reach 256 (a count only grows by one per coded symbol; the
+    // halving rule only shrinks them), which also keeps every group total below 65 536.
+    bool model8_ok(uint64_t block_len) const {
+        if (c.model == SCL_MODEL_ORDER_K) return false;
+        uint64_t sum = 0, mx = 0;
+        for (uint32_t i = 0; i < c.n_sym; ++i) {
+            sum += t.init_freq[i];
+            mx = t.init_freq[i] > mx ? t.init_freq[i] : mx;
+        }
+        if (mx > 255) return false;
+        if (c.model == SCL_MODEL_FIXED) return true;
+        return (sum + block_len) / 256 <= kAecBigMax;
+    }
 };
 
 }  // namespace scl

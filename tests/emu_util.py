@@ -40,6 +40,7 @@ def lib():
         L.emu_encode_blocks.argtypes = [vp, vp, u64, vp, u32, u64, vp, u64, vp, vp, vp, vp]
         L.emu_decode_blocks.argtypes = [vp, vp, u64, vp, vp, u64, vp, u64, vp, vp, vp, vp]
         L.emu_set_aec2.argtypes = [vp, ctypes.c_int]
+        L.emu_aec_model8_ok.argtypes = [vp, u64]
         L.emu_aec_renorm_counts.argtypes = [u32, u64, u64, vp, vp, vp, vp]
         L.emu_v2_eligible.argtypes = [vp]
         L.emu_encode_blocks_v2.argtypes = [vp, vp, u64, u32, u64, vp, u64, vp, vp, vp]
@@ -89,7 +90,11 @@ class EmuCoder:
         return enc, dec
 
     def set_aec2(self, on=True):
+        """1 / True = second-generation arithmetic lanes (16-bit counters), 2 = 8-bit counters where eligible"""
         lib().emu_set_aec2(self.h, int(on))
+
+    def aec_model8_ok(self, block_len):
+        return bool(lib().emu_aec_model8_ok(self.h, int(block_len)))
 
     def v2_eligible(self):
         return bool(lib().emu_v2_eligible(self.h))

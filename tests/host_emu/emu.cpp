@@ -30,7 +30,7 @@ struct Emu {
     RangeHost *range = nullptr;
     AecHost *aec = nullptr;
     std::vector<uint32_t> tenc, tdec;
-    bool aec2 = false;  // use the second-generation arithmetic-coder lanes
+    int aec2 = 0;  // 1 = second-generation arithmetic-coder lanes (16-bit counters), 2 = the same with 8-bit counters
     ~Emu() {
         delete rans;
         delete tans;
@@ -68,7 +68,8 @@ const uint8_t *g_aec_masks = &g_mask_table.m[0][0];
 
 extern "C" {
 
-void emu_set_aec2(void *h, int on) { ((Emu *)h)->aec2 = on != 0; }
+void emu_set_aec2(void *h, int on) { ((Emu *)h)->aec2 = on; }
+int emu_aec_model8_ok(void *h, uint64_t block_len) { return ((Emu *)h)->aec && ((Emu *)h)->aec->model8_ok(block_len) ? 1 : 0; }
 
 // closed-form renormalisation counts, exposed for a direct check against the literal loops
 void emu_aec_renorm_counts(uint32_t P, uint64_t low, uint64_t high, uint32_t *n_e12, uint32_t *m_e3, uint64_t *low_out, uint64_t *high_out) {
@@ -163,6 +164,20 @@ static AecIidPolicy make_iid_policy(uint32_t *words, const AecTab &t, const AecC
     pol.n_sym = c.n_sym;
     return pol;
 }
+static AecIid8Policy make_iid8_policy(uint32_t *words, const AecTab &t, const AecConst &c) {
+    AecIid8Policy pol;
+    pol.M.w = saddr_of(words);
+    pol.M.stride = 4;
+    pol.M.masks = saddr_of(g_aec_masks);
+    pol.M.mstride = 16;
+    uint64_t total = 0;
+    pol.M.load(t.init_freq, c.n_sym, total);
+    pol.tot = (uint32_t)total;
+    pol.adaptive = c.model == SCL_MODEL_ADAPTIVE_IID;
+    pol.max_total = c.max_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c.max_total;
+    pol.n_sym = c.n_sym;
+    return pol;
+}
 static AecCtxPolicy make_ctx_policy(uint32_t *words, const AecConst &c) {
     AecCtxPolicy pol;
     pol.w = saddr_of(words);
@@ -229,6 +244,10 @@ int emu_encode_blocks(void *h, const uint8_t *sym, uint64_t sym_stride, const ui
                 pol.load(mm);
                 st = aec2_encode_lane(pol, e->aec->t, e->aec->c, row, sym_stride, n, w, bits);
                 if (mm) pol.store(mm);
+            } else if (e->aec2 == 2 && !model && e->aec->model8_ok(n)) {
+                alignas(16) uint32_t words[kAecModel8Words];
+                AecIid8Policy pol = make_iid8_policy(words, e->aec->t, e->aec->c);
+                st = aec2_encode_lane(pol, e->aec->t, e->aec->c, row, sym_stride, n, w, bits);
             } else if (e->aec2) {
                 alignas(16) uint32_t words[kAecModelWords];
                 uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;
@@ -285,6 +304,10 @@ int emu_decode_blocks(void *h, const uint8_t *in, uint64_t in_bytes, const uint6
             pol.load(mm);
             st = aec2_decode_lane(pol, e->aec->t, e->aec->c, r, avail, row, sym_stride, size, used);
             if (mm) pol.store(mm);
+        } else if (e->aec2 == 2 && !model && e->aec->model8_ok(sym_stride)) {
+            alignas(16) uint32_t words[kAecModel8Words];
+            AecIid8Policy pol = make_iid8_policy(words, e->aec->t, e->aec->c);
+            st = aec2_decode_lane(pol, e->aec->t, e->aec->c, r, avail, row, sym_stride, size, used);
         } else if (e->aec2) {
             alignas(16) uint32_t words[kAecModelWords];
             uint64_t *mm = model ? model + b * e->aec->c.n_sym : nullptr;

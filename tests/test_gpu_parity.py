@@ -871,3 +871,56 @@ def test_aec_full_size_roundtrip_cfg4():
     e, d = _compare_batch_with_oracle(enc, dec, so.Oracle.aec(uni), data, sample=range(0, B, 65536), consumed_equals_length=False)
     bits_per_sym = float(e.bit_len.sum()) / (B * N)
     assert 6.2 < bits_per_sym < 7.0  # Zipf-1.0 entropy 6.22 b/sym + the adaptive model's learning cost over 1 KiB
+
+
+def test_aec_8bit_counter_model_agrees_with_16bit_and_oracle():
+    """The arithmetic coder's 8-bit-counter model (AecModel8: half the shared memory, counters past 255 escape to a
+    per-lane list) against the 16-bit kernels (debug path 5) and the oracle: cfg4-shaped blocks (1 KiB from 256 ones),
+    rows that push one / two counters far past 255, a small max_allowed_total_freq that fires the halving rule with
+    escaped counters present, ragged sizes; and the eligibility bound (blocks of 1280 symbols take the 16-bit kernels)."""
+    from stanford_compression_library_b200 import Frequencies
+    from stanford_compression_library_b200.compressors.arithmetic_coding import AECParams, ArithmeticDecoder, ArithmeticEncoder
+    from stanford_compression_library_b200.compressors.probability_models import AdaptiveIIDFreqModel
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    B, N = 4100, 1024
+    data = sample_blocks(zipf_probabilities(), B, N, seed=77, device="cuda:0")
+    data[0, :] = 7                       # one counter reaches 1025
+    data[1, ::2] = 3
+    data[1, 1::2] = 250                  # two counters reach 513
+    data[2, :300] = 0
+    data[3, :] = torch.arange(N, device="cuda:0") % 256  # flat
+    sizes = _seeded_sizes(1, N + 1, B)
+    sizes[:4] = N
+    uni = Frequencies({b: 1 for b in range(256)})
+    host, hs = data.cpu().numpy(), sizes.cpu().numpy()
+    for max_total in (None, 700):
+        ap = AECParams()
+        mt = ap.MAX_ALLOWED_TOTAL_FREQ if max_total is None else max_total
+        enc = ArithmeticEncoder(ap, AdaptiveIIDFreqModel(uni, mt))
+        dec = ArithmeticDecoder(ap, AdaptiveIIDFreqModel(uni, mt))
+        e8 = enc.encode_blocks(data, sizes=sizes).check()
+        d8 = dec.decode_blocks(e8, N).check()
+        try:
+            _force(5, enc, dec)
+            e16 = enc.encode_blocks(data, sizes=sizes).check()
+            d16 = dec.decode_blocks(e8, N).check()
+        finally:
+            _force(0, enc, dec)
+        assert torch.equal(e8.bit_len, e16.bit_len) and torch.equal(e8.pack().buf, e16.pack().buf)
+        assert torch.equal(d8.bits_consumed, d16.bits_consumed) and torch.equal(d8.sizes, sizes) and torch.equal(d16.sizes, sizes)
+        mask = torch.arange(N, device="cuda:0")[None, :] < sizes[:, None]
+        assert torch.equal(d8.symbols[:, :N][mask], data[mask]) and torch.equal(d16.symbols[:, :N][mask], data[mask])
+        oracle = so.Oracle.aec([1] * 256, max_allowed_total_freq=mt)
+        for b in (0, 1, 2, 3, 4, 5, B - 1):
+            ref, ref_bits = oracle.encode_block(host[b, : hs[b]])
+            assert int(e8.bit_len[b]) == ref_bits and e8.block(b).tobytes() == ref.tobytes(), (max_total, b)
+    # past the bound the library takes the 16-bit kernels by itself: same answers as the oracle
+    long_blocks = sample_blocks(zipf_probabilities(), 64, 1280, seed=78, device="cuda:0")
+    long_blocks[0, :] = 9
+    enc = ArithmeticEncoder(AECParams(), AdaptiveIIDFreqModel(uni, AECParams().MAX_ALLOWED_TOTAL_FREQ))
+    e = enc.encode_blocks(long_blocks).check()
+    oracle = so.Oracle.aec([1] * 256)
+    for b in (0, 1, 63):
+        ref, ref_bits = oracle.encode_block(long_blocks[b].cpu().numpy())
+        assert int(e.bit_len[b]) == ref_bits and e.block(b).tobytes() == ref.tobytes()

@@ -652,3 +652,96 @@ def test_generic_rans_decode_is_bounded_on_a_zero_state():
     # and with no bit_len given the bound is the end of the buffer
     sym, sizes, used, st = coder.decode(buf, [0], None, 8)
     assert st[0] == 4
+
+
+# ---- arithmetic coder, 8-bit counters (csrc/scl_aec.cuh AecModel8 / AecIid8Policy) --------------------------------
+@pytest.mark.parametrize("c", [c for c in CASES if c["coder"] == "aec" and c["model"]["kind"] != "order_k"], ids=case_id)
+def test_emu_aec_model8_matches_golden(c):
+    """the 8-bit-counter model on every golden case it is eligible for (else the call falls back to 16 bits): same
+    bits and bits consumed as the reference"""
+    coder = EmuCoder(params_from_case(c), None, c["freqs"])
+    coder.set_aec2(2)
+    n = c["n"]
+    out, off, ln, st = coder.encode(c["data"].reshape(1, -1))  # no model table: every block from the creation-time counts
+    assert st[0] == 0 and int(ln[0]) == c["nbits"]
+    assert extract_bits(out, off[0], ln[0]).tobytes() == c["enc"].tobytes()
+    if n == 0:
+        return
+    packed, total = with_garbage(c["enc"], c["nbits"], c["garbage"])
+    bits = np.concatenate([np.ones(3, dtype=np.uint8), np.unpackbits(packed)[:total]])
+    buf = np.concatenate([np.packbits(bits), np.zeros(16, dtype=np.uint8)])
+    sym, sizes, used, st = coder.decode(buf, [3], [total], n)
+    assert st[0] == 0 and int(sizes[0]) == n and int(used[0]) == c["consumed"]
+    assert sym[0, :n].tolist() == c["data"].tolist()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_emu_aec_model8_vs_oracle_random(seed):
+    """random alphabets / initial counts / block lengths up to the eligibility bound, skewed sources that push one or
+    several counters past 255 (the `big` list), small max_allowed_total_freq values that fire the halving rule with
+    big symbols present, the fixed model; every stream against the oracle, every block decoded back"""
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    rng = np.random.default_rng(7000 + seed)
+    n_sym = int(rng.choice([1, 2, 3, 17, 100, 256]))
+    init = [int(x) for x in rng.integers(1, 4, size=n_sym)] if seed % 2 else [1] * n_sym
+    B = 6
+    N = int(min(1270, 5 * 256 - sum(init) - 1)) if seed % 3 else int(rng.integers(1, 700))
+    N = max(N, 1)
+    # rows: very skewed (one symbol nearly always), two heavy symbols, flat
+    sym = np.zeros((B, N), dtype=np.uint8)
+    for b in range(B):
+        k = b % 3
+        if k == 0:
+            p = np.full(n_sym, 0.02 / max(1, n_sym - 1))
+            p[rng.integers(0, n_sym)] = 0.98 if n_sym > 1 else 1.0
+        elif k == 1 and n_sym >= 2:
+            p = np.full(n_sym, 0.04 / max(1, n_sym - 2)) if n_sym > 2 else np.zeros(n_sym)
+            i, j = rng.choice(n_sym, size=2, replace=False)
+            p[i], p[j] = 0.5, 0.46 if n_sym > 2 else 0.5
+        else:
+            p = np.ones(n_sym)
+        sym[b] = rng.choice(n_sym, size=N, p=p / p.sum())
+    sizes = np.array([N, N, N, max(1, N // 2), 1, N], dtype=np.uint32)
+    for P, max_total, model in ((32, 1 << 30, _cabi.MODEL_ADAPTIVE_IID), (32, sum(init) + 300, _cabi.MODEL_ADAPTIVE_IID), (16, 1 << 14, _cabi.MODEL_ADAPTIVE_IID),
+                                (32, 700, _cabi.MODEL_ADAPTIVE_IID), (32, 1 << 30, _cabi.MODEL_FIXED)):
+        if sum(init) >= (1 << (P - 2)) or (model == _cabi.MODEL_ADAPTIVE_IID and max_total <= sum(init)):
+            continue
+        oracle = so.Oracle.aec(init, PRECISION=P, max_allowed_total_freq=max_total, model=so.MODEL_ADAPTIVE_IID if model == _cabi.MODEL_ADAPTIVE_IID else so.MODEL_FIXED)
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=P, model=model,
+                        max_allowed_total_freq=max_total)
+        coder = EmuCoder(prm, None, init)
+        assert coder.aec_model8_ok(N)
+        coder.set_aec2(2)
+        out, off, ln, st = coder.encode(sym, sizes=sizes)
+        ok = st == 0
+        for b in range(B):
+            try:
+                enc, nb = oracle.encode_block(sym[b, : sizes[b]])
+            except so.OracleError as e:
+                assert st[b] == e.code, (P, max_total, b, st[b], e.code)
+                continue
+            assert st[b] == 0 and nb == ln[b], (P, max_total, b)
+            assert extract_bits(out, off[b], ln[b]).tobytes() == enc.tobytes(), (P, max_total, b)
+        dsym, dsz, used, st2 = coder.decode(out, off, ln, N)
+        for b in range(B):
+            if ok[b]:
+                assert st2[b] == 0 and dsz[b] == sizes[b], (P, max_total, b)
+                assert dsym[b, : sizes[b]].tolist() == sym[b, : sizes[b]].tolist()
+
+
+def test_emu_aec_model8_eligibility():
+    from stanford_compression_library_b200 import _cabi
+    from stanford_compression_library_b200._cabi import SclParams
+
+    def mk(init, model=_cabi.MODEL_ADAPTIVE_IID):
+        prm = SclParams(coder=_cabi.CODER_AEC, data_block_size_bits=32, num_bits_out=0, range_factor=0, num_state_bits=0, precision=32, model=model,
+                        max_allowed_total_freq=1 << 30)
+        return EmuCoder(prm, None, init)
+
+    c = mk([1] * 256)
+    assert c.aec_model8_ok(1024) and c.aec_model8_ok(1279) and not c.aec_model8_ok(1280)  # (256 + n) // 256 <= 5
+    assert not mk([1] * 255 + [256]).aec_model8_ok(10)  # an initial count does not fit a byte
+    assert mk([255] * 256, _cabi.MODEL_FIXED).aec_model8_ok(1 << 20)  # a fixed model never grows
+    assert not mk([255] * 256).aec_model8_ok(1)
