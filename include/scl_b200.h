@@ -213,8 +213,11 @@ int scl_tans_tables_to_host(const scl_coder *c, uint32_t *enc_table, uint32_t *d
  * first-generation kernels (per-lane direct global access) instead of the TMA/ring kernels; 2 =
  * second-generation decode with per-lane sector stores instead of TMA tile stores; 3 / 4 =
  * second-generation decode always / never in its pipe-balanced instruction selection (normally
- * chosen by batch size); 5 = the arithmetic coder keeps 16-bit counters where it would take 8-bit ones; 0 = default.  Keeps every code path parity-tested.  Set it before issuing
- * work on the handle; it is read at launch time. */
+ * chosen by batch size); 5 = the arithmetic coder keeps 16-bit counters where it would take 8-bit ones; 0 = default.
+ * Higher bits vary the packed encoder's copy pool: 32 = no shared-memory staging rings (every copy through registers),
+ * 64 / 128 = staged pieces of at most 512 / 1024 bytes (default: the largest of 2048 / 1024 / 512 that fits twice),
+ * bits 12-15 = number of dedicated copy warps (0 = the default 4); 256 = split batches at 64 MiB of input instead of
+ * 2^30 blocks.  Keeps every code path parity-tested.  Set it before issuing work on the handle; it is read at launch time. */
 void scl_coder_debug_path(scl_coder *c, int mode);
 
 /* Diagnostic hook, per handle: with a device buffer of n_words uint64 (>= SMs * 32 * 40, zeroed by the caller) the
@@ -225,10 +228,12 @@ void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words);
 
 /* Diagnostic: re-run only the copy stage of a finished scl_encode_blocks_packed call (same buffers, left as that call
  * left them) with `warps_per_cta` warps on each SM and no coder beside them -- how fast is the copy pool alone?
+ * ring_stages = 0: every warp copies through registers (the form coding warps use when they help); >= 2: through a
+ * shared-memory staging ring of that many 592-byte stages filled by bulk async copies (the dedicated copy warps' form).
  * (tools/measure_copy_only.py).  Second-generation rANS / tANS handles only. */
 int scl_debug_copy_only(const scl_coder *c, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride, uint8_t *d_dst,
                         uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset, uint64_t *d_bit_offset,
-                        uint64_t *d_bit_len, uint32_t *d_status, uint32_t warps_per_cta, void *stream);
+                        uint64_t *d_bit_len, uint32_t *d_status, uint32_t warps_per_cta, uint32_t ring_stages, void *stream);
 
 const char *scl_last_cuda_error(void);
 const char *scl_version(void);

@@ -81,7 +81,7 @@ def lib():
     L.scl_coder_debug_path.restype = None
     L.scl_coder_debug_path.argtypes = [vp, i32]
     L.scl_debug_copy_only.restype = i32
-    L.scl_debug_copy_only.argtypes = [vp, u64, vp, u64, vp, u64, u32, vp, vp, vp, vp, u32, vp]
+    L.scl_debug_copy_only.argtypes = [vp, u64, vp, u64, vp, u64, u32, vp, vp, vp, vp, u32, u32, vp]
     L.scl_coder_debug_trace.restype = None
     L.scl_coder_debug_trace.argtypes = [vp, vp, u64]
     L.scl_last_cuda_error.restype = ctypes.c_char_p

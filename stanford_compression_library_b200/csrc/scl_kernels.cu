@@ -213,12 +213,16 @@ __device__ __forceinline__ void tma_tile_2d(void *smem_dst, const CUtensorMap *t
 // then (i) the warp sums its 32 record sizes (__reduce_add_sync), (ii) the last warp of a CTA to finish a round
 // adds up the CTA's tasks -- they are consecutive -- and resolves the cross-CTA exclusive prefix by decoupled
 // look-back over one word per (round, CTA) (scl_pack.cuh), (iii) the streams are copied to their final byte
-// offsets (pack_block_warp_a16).  The CTA is WARP-SPECIALISED: the coding warps never copy while they have
-// symbols left; kCopyWarps extra warps (the CTA has room for 32, the coder uses at most 28) do nothing else,
-// taking resolved tasks from a ticket counter.  The copy is pure memory traffic with a bit shift, the coding is
-// arithmetic, so the two overlap on the SM, and the copy's registers (several chunks in flight per lane) stay
-// out of the coding loop's allocation.  A coding warp that has run out of tasks joins the copy pool, so the
-// last round's streams -- which nothing is left to overlap with -- are moved by the whole CTA.
+// offsets.  The CTA is WARP-SPECIALISED: the coding warps never copy while they have symbols left; kCopyWarps extra
+// warps (the CTA has room for 32, the coder uses at most 28) do nothing else, taking resolved tasks from a ticket
+// counter.  A copy warp is one dependent instruction chain among 28 coding warps that keep the issue slots and the
+// L1/shared pipe ~75 % busy (profiles/r2w): what it costs is instructions, not bytes.  So it stages its source by bulk
+// async copies (TMA) into a small shared-memory ring carved from what the coder leaves free -- pieces of up to 2 KiB,
+// requested ahead across stream boundaries -- and its loop is: wait for a piece, LDS / funnel shift / STG per 16 bytes,
+// hand the stage back (packed_copy_task_ring).  A task's place in the output is handed over through its first block's
+// byte_off entry (one word per task, never reused), so the coder never waits for the pool: what the pool has not moved
+// when a coding warp runs out of tasks is moved by that warp too (through registers: pack_block_warp_a16), i.e. the
+// rest is copied by the whole CTA at memory speed at the end.
 // Depends on the in-order dispatch of CTAs (a CTA only waits for lower-numbered CTAs of the same round, or
 // for earlier rounds), like every single-pass scan.
 constexpr uint32_t kCopyWarps = 4;
@@ -230,6 +234,8 @@ struct PackedOut {
     uint32_t framed;
     uint64_t g_base;         // look-back index of this launch's (round 0, CTA 0): a split batch continues the numbering
     uint32_t copy_warps;     // dedicated copy warps of the CTA (kCopyWarps)
+    uint32_t copy_stages;    // stages of each copy warp's staging ring (from the shared memory the coder leaves free); 0 = copy through registers
+    uint32_t copy_piece_bytes;  // 512 or 1024: stream bytes per stage
     uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
 };
 constexpr uint32_t kTraceWords = 40;  // per warp: [0] start, [1 + r] end of coding round r (r < 19), [20] tasks copied, [21] first copy
@@ -241,11 +247,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 struct PackCtl {  // per CTA, shared memory
     unsigned long long warp_tot[2][kMaxWarps];   // [round & 1] record bytes of each coding warp's task
-    unsigned long long warp_excl[2][kMaxWarps];  // [round & 1] byte offset of each task in dst, valid once `resolved` > round
     uint32_t arrive[2];                          // [round & 1] coding warps that have finished the round
     uint32_t resolved;                           // rounds whose offsets are known (monotonic)
     uint32_t copy_ticket;                        // next task to copy: ticket T = round * W + warp slot (monotonic)
-    uint32_t copy_done;                          // tasks copied so far (monotonic)
+    uint32_t copy_done;                          // tasks copied so far (monotonic; read by nobody but a debugger)
 };
 
 template <bool FRAMED>
@@ -292,14 +297,251 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
     }
 }
 
+// The dedicated copy warps' form of packed_copy_task: the streams arrive in a per-warp shared-memory ring by bulk async
+// copies (scl_pack.cuh: regions, pieces), issued by lane 0 `stages` pieces ahead of the piece being moved -- across
+// stream boundaries, so the warp does not wait for memory between streams either.  Same output, byte for byte.
+// One warp among 28 coding warps runs a dependent instruction chain: what it costs is instructions per piece, so the
+// piece loop is kept to the wait, the chunks (one or two per lane), and the refill of the stage just emptied.
+struct CopyRing {          // identical in every lane of the warp
+    uint32_t buf;          // shared address of stage 0; stage i at buf + i * (piece_bytes + kCopyOverlapBytes)
+    uint32_t bars;         // shared address of mbarrier 0 (right behind the stages); mbarrier i at bars + 8 i
+    uint32_t tab;          // shared address of the per-task stream table: 32 x {bits, pieces, region start, region bytes}
+    uint32_t piece_bytes;  // 512 or 1024: 32 or 64 chunks per piece; 0 = this warp has no ring (copies through registers)
+    uint32_t stage, bar;   // where the next piece lands / its mbarrier (shared addresses)
+    uint32_t par;          // that mbarrier's phase parity
+    uint32_t wait_cycles;  // tracing only: clock cycles spent waiting for pieces to land
+};
+__host__ __device__ constexpr uint32_t copy_ring_bytes(uint32_t stages, uint32_t piece_bytes) {
+    return stages ? stages * (piece_bytes + kCopyOverlapBytes) + ((stages * 8 + 15) & ~15u) + 512 : 0;
+}
+// mem: 16-byte aligned, copy_ring_bytes(); `init` = also initialise the mbarriers (once, before the CTA's first barrier)
+__device__ __forceinline__ CopyRing copy_ring_at(uint8_t *mem, uint32_t stages, uint32_t piece_bytes, bool init) {
+    CopyRing R;
+    R.buf = smem_u32(mem);
+    R.bars = R.buf + stages * (piece_bytes + kCopyOverlapBytes);
+    R.tab = R.bars + ((stages * 8 + 15) & ~15u);
+    R.piece_bytes = stages ? piece_bytes : 0;
+    R.stage = R.buf;
+    R.bar = R.bars;
+    R.par = 0;
+    R.wait_cycles = 0;
+    if (init) {
+        for (uint32_t i = 0; i < stages; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(R.bars + 8 * i) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    return R;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+template <bool FRAMED>
+__device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const PackedOut &po, uint64_t task, uint64_t base, uint32_t lane, CopyRing &R) {
+    const uint32_t PB = R.piece_bytes, SB = PB + kCopyOverlapBytes, PC = PB >> 4;
+    {
+        // lane l describes stream l (the block's record and where its source bytes lie) in the warp's table
+        const uint64_t b = task * 32 + lane;
+        const bool active = b < io.n_blocks;
+        uint32_t bits = 0, nb = 0;
+        if (active && io.status[b] == SCL_ST_OK) {
+            bits = (uint32_t)io.bit_len[b];
+            nb = (uint32_t)packed_size(bits, FRAMED);
+        }
+        uint32_t incl = nb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += u;
+        }
+        const uint64_t at_mine = base + (incl - nb);
+        if (active) {
+            po.byte_off[b] = at_mine;
+            io.bit_off[b] = 8 * at_mine + packed_lead_bits(bits, FRAMED);
+            if (nb && at_mine + nb > po.dst_bytes) {
+                io.status[b] = SCL_ST_OVERFLOW;
+                bits = 0x80000000u | nb;  // dropped: no bits to move, but the record keeps its place in the layout
+            }
+        }
+        uint32_t np = 0, rs = 0, rlen = 0;
+        if (bits && !(bits >> 31)) {
+            const StreamGeo g = stream_geo<FRAMED>(bits, (uint32_t)(uintptr_t)(po.dst + at_mine + (FRAMED ? 4 : 0)) & 15u);
+            const uint32_t off = (uint32_t)(io.out_stride * 8) - bits;
+            const uint32_t a = (off + 8 * g.head - g.lead) >> 7;
+            rs = ((off - g.lead) >> 7) * 16;
+            uint32_t re = (a + g.n_chunks + 3) * 16;
+            if (re > (uint32_t)io.out_stride + 16) re = (uint32_t)io.out_stride + 16;
+            rlen = re - rs;
+            np = g.n_chunks ? (g.n_chunks + PC - 1) / PC : 1u;
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(R.tab + 16 * lane), "r"(bits), "r"(np), "r"(rs), "r"(rlen) : "memory");
+        __syncwarp();
+    }
+    // producer cursor (warp-uniform): stream pl, p_np pieces of it still to request, the next one at p_src, p_left bytes to
+    // the region's end.  A piece always goes into the stage the consumer has just emptied (or, before the first piece is
+    // consumed, into the stages in order), so the producer keeps no stage of its own.
+    const uint8_t *task_src = io.out + (io.block0 + task * 32) * io.out_stride;
+    uint32_t pl = 0xFFFFFFFFu, p_np = 0, p_left = 0;
+    const uint8_t *p_src = task_src;
+    auto next_stream = [&]() {
+        while (p_np == 0 && pl + 1 < 32) {
+            ++pl;
+            const uint4 e = lds_plain128(R.tab + 16 * pl);
+            p_np = e.y;
+            p_src = task_src + (uint64_t)pl * io.out_stride + e.z;
+            p_left = e.w;
+        }
+    };
+    auto issue = [&](uint32_t stage, uint32_t bar) {
+        if (p_np == 0) return;
+        const uint32_t nbytes = p_left < SB ? p_left : SB;
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage), "l"(p_src), "r"(nbytes), "r"(bar)
+                         : "memory");
+        }
+        p_src += PB;
+        p_left -= PB;
+        if (--p_np == 0) next_stream();
+    };
+    next_stream();
+    {
+        uint32_t st = R.stage, br = R.bar;
+        for (; p_np; ) {  // fill the ring
+            issue(st, br);
+            st += SB;
+            br += 8;
+            if (st == R.bars) {
+                st = R.buf;
+                br = R.bars;
+            }
+            if (st == R.stage) break;
+        }
+    }
+    uint64_t at = base;
+    for (uint32_t l = 0; l < 32; ++l) {
+        uint32_t bits_l;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bits_l) : "r"(R.tab + 16 * l));
+        if (bits_l >> 31) {  // a dropped record: its place stays
+            at += bits_l & 0x7FFFFFFFu;
+            continue;
+        }
+        if (bits_l == 0) continue;
+        uint8_t *d = po.dst + at;
+        at += (uint32_t)packed_size(bits_l, FRAMED);
+        const StreamGeo g = stream_geo<FRAMED>(bits_l, (uint32_t)(uintptr_t)(d + (FRAMED ? 4 : 0)) & 15u);
+        if (FRAMED) {
+            if (lane < 4) d[lane] = (uint8_t)(g.payload_bytes >> (8 * (3 - lane)));
+            d += 4;
+        }
+        const uint32_t off = (uint32_t)(io.out_stride * 8) - bits_l;
+        const uint32_t g0 = (off - g.lead) >> 7, S0 = off + 8 * g.head - g.lead, offr = off - 128 * g0;
+        const uint32_t lofs = 16 * (lane + (S0 >> 7) - g0), sh = S0 & 31u;
+        const uint32_t last_piece = g.n_chunks ? (g.n_chunks - 1) / PC : 0u;
+        if (po.trace) {
+            const uint32_t c0 = (uint32_t)clock64();
+            mbar_wait_s(R.bar, R.par);
+            R.wait_cycles += (uint32_t)clock64() - c0;
+        } else {
+            mbar_wait_s(R.bar, R.par);  // the stream's first piece
+        }
+        if (lane < g.head) {
+            const int32_t pos = (int32_t)(8 * lane) - (int32_t)g.lead;
+            d[lane] = (uint8_t)(stream_byte_masked_smem(R.stage, (uint32_t)((int32_t)offr + pos), pos, bits_l) | ((FRAMED && lane == 0) ? (g.num_pad << 5) : 0u));
+        }
+        // this lane's tail byte, all worked out except for the two words it is cut from: bit offset inside the last piece
+        // (or none), keep-mask | bits to OR in << 8, and its address relative to the lane's chunk pointer in that piece
+        uint32_t t_S = 0xFFFFFFFFu, t_ko = 0;
+        int32_t t_ofs = 0;
+        {
+            const uint32_t i = g.tail0 + lane;
+            if (i < g.payload_bytes) {
+                const int32_t pos = (int32_t)(8 * i) - (int32_t)g.lead;
+                t_S = (uint32_t)((int32_t)offr + pos) - 8 * PB * last_piece;
+                uint32_t keep = 0xFFu;
+                if (pos < 0) keep = pos <= -8 ? 0u : (0xFFu >> (uint32_t)(-pos));
+                const int32_t r = (int32_t)bits_l - pos;
+                if (r < 8) keep &= r <= 0 ? 0u : ~(0xFFu >> (uint32_t)r);
+                t_ko = keep | ((FRAMED && i == 0) ? (g.num_pad << 13) : 0u);
+                t_ofs = (int32_t)i - (int32_t)(g.head + 16 * lane + PB * last_piece);
+            }
+        }
+        uint8_t *dp = d + g.head + 16 * lane;
+        uint32_t rem = g.n_chunks;  // chunks from the current piece on
+        auto pieces = [&](auto w0_tag) {
+            constexpr int W0 = decltype(w0_tag)::value;
+            while (true) {
+                const uint32_t sa = R.stage + lofs;
+                // (the loads are unconditional: anything inside the ring may be read, only the stores are guarded)
+                {
+                    const uint4 A0 = lds_plain128(sa), B0 = lds_plain128(sa + 16);
+                    if (PB >= 1024) {
+                        const uint4 A1 = lds_plain128(sa + 512), B1 = lds_plain128(sa + 528);
+                        if (lane < rem) st_plain128(dp, pack_chunk_from_pair_raw<W0>(A0, B0, sh));
+                        if (lane + 32 < rem) st_plain128(dp + 512, pack_chunk_from_pair_raw<W0>(A1, B1, sh));
+                    } else {
+                        if (lane < rem) st_plain128(dp, pack_chunk_from_pair_raw<W0>(A0, B0, sh));
+                    }
+                }
+                if (PB == 2048 && rem > 64) {
+                    const uint4 A2 = lds_plain128(sa + 1024), B2 = lds_plain128(sa + 1040);
+                    const uint4 A3 = lds_plain128(sa + 1536), B3 = lds_plain128(sa + 1552);
+                    if (lane + 64 < rem) st_plain128(dp + 1024, pack_chunk_from_pair_raw<W0>(A2, B2, sh));
+                    if (lane + 96 < rem) st_plain128(dp + 1536, pack_chunk_from_pair_raw<W0>(A3, B3, sh));
+                }
+                const bool last = rem <= PC;
+                if (last && t_S != 0xFFFFFFFFu) {
+                    const uint32_t wa = R.stage + ((t_S >> 5) << 2);
+                    uint32_t w0, w1;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(wa + 4));
+                    dp[t_ofs] = (uint8_t)(((funnel_l(w1, w0, t_S & 31u) >> 24) & t_ko) | (t_ko >> 8));
+                }
+                __syncwarp();  // every lane has used what it read from the stage: it can be refilled
+                issue(R.stage, R.bar);
+                R.stage += SB;
+                R.bar += 8;
+                if (R.stage == R.bars) {
+                    R.stage = R.buf;
+                    R.bar = R.bars;
+                    R.par ^= 1;
+                }
+                if (last) break;
+                rem -= PC;
+                dp += PB;
+                if (po.trace) {
+                    const uint32_t c0 = (uint32_t)clock64();
+                    mbar_wait_s(R.bar, R.par);
+                    R.wait_cycles += (uint32_t)clock64() - c0;
+                } else {
+                    mbar_wait_s(R.bar, R.par);
+                }
+            }
+        };
+        switch ((S0 >> 5) & 3u) {  // the word the chunks start at inside their 16-byte granule: fixed per stream
+        case 0: pieces(std::integral_constant<int, 0>{}); break;
+        case 1: pieces(std::integral_constant<int, 1>{}); break;
+        case 2: pieces(std::integral_constant<int, 2>{}); break;
+        default: pieces(std::integral_constant<int, 3>{}); break;
+        }
+    }
+}
+
 // The copy pool.  Ticket T = (round T / W, warp slot T % W); tickets run through the CTA's tasks in order.
 // One task: claim the next ticket and copy it.  `block` = wait for the ticket's round to be resolved (the dedicated
 // copy warps, and coding warps that have run out of symbols); otherwise only a ticket whose round IS resolved is
 // claimed (a coding warp that helps while it waits must never wait for a round it has yet to arrive at).
 // Returns 0 = nothing left at all, 1 = copied one task, 2 = nothing claimable right now.
 // (__noinline__: one copy of the code for its three call sites, registers allocated apart from the coding loop's.)
+// RING = through the calling copy warp's staging ring (its own instantiation: its own register allocation).
+template <bool RING>
 __device__ __noinline__ uint32_t packed_copy_one(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
-                                                 uint32_t n_tasks, uint32_t lane, bool block) {
+                                                 uint32_t n_tasks, uint32_t lane, bool block, CopyRing *ring) {
     uint32_t T = 0, got = 1;
     if (lane == 0) {
         if (block) {
@@ -330,11 +572,25 @@ __device__ __noinline__ uint32_t packed_copy_one(PackCtl &ctl, const BlockIo &io
     }
     __syncwarp();
     __threadfence_block();
-    const uint64_t base = *(const volatile unsigned long long *)&ctl.warp_excl[r & 1][slot];
-    if (po.framed)
+    const uint64_t base = *(const volatile unsigned long long *)&po.byte_off[task * 32];
+    if (RING) {
+        // the slots were written through the generic proxy (by warps that fenced at gpu scope before arriving); the
+        // bulk copies read them through the async proxy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        CopyRing R = *ring;
+        if (po.framed)
+            packed_copy_task_ring<true>(io, po, task, base, lane, R);
+        else
+            packed_copy_task_ring<false>(io, po, task, base, lane, R);
+        ring->stage = R.stage;
+        ring->bar = R.bar;
+        ring->par = R.par;
+        if (po.trace && lane == 0) po.trace[((uint64_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * kTraceWords + 25] += R.wait_cycles;
+    } else if (po.framed) {
         packed_copy_task<true>(io, po, task, base, lane);
-    else
+    } else {
         packed_copy_task<false>(io, po, task, base, lane);
+    }
     __syncwarp();
     if (lane == 0) {
         __threadfence_block();
@@ -351,15 +607,15 @@ __device__ __noinline__ uint32_t packed_copy_one(PackCtl &ctl, const BlockIo &io
     return 1;
 }
 
-// Wait until *word >= target, copying resolved tasks meanwhile (a coding warp held up by the pool's back-pressure is
-// the pool's best helper: it turns the wait into the work that ends it).  The whole warp calls this.
+// Wait until *word >= target, copying resolved tasks meanwhile (a coding warp that has to wait for a round's
+// look-back -- i.e. for slower CTAs -- spends the wait on the pool's work).  The whole warp calls this.
 __device__ __forceinline__ void packed_wait_helping(PackCtl &ctl, const BlockIo &io, const PackedOut &po, uint32_t W, uint32_t total_warps,
                                                     uint32_t n_tasks, uint32_t lane, const uint32_t *word, uint32_t target) {
     while (true) {
         uint32_t v = 0;
         if (lane == 0) v = *(const volatile uint32_t *)word;
         if (__shfl_sync(0xffffffffu, v, 0) >= target) return;
-        if (packed_copy_one(ctl, io, po, W, total_warps, n_tasks, lane, false) != 1) __nanosleep(200);
+        if (packed_copy_one<false>(ctl, io, po, W, total_warps, n_tasks, lane, false, nullptr) != 1) __nanosleep(200);
     }
 }
 
@@ -367,10 +623,18 @@ __device__ __forceinline__ void packed_wait_helping(PackCtl &ctl, const BlockIo 
 // the tasks of a finished fused encode (scratch slots, bit lengths and record offsets as that call left them).
 // Separates "a copy warp is slow because it waits for memory" from "... because 28 coding warps take its issue slots".
 __global__ void __launch_bounds__(1024, 1) copy_only_kernel(BlockIo io, PackedOut po, uint32_t n_tasks) {
+    extern __shared__ __align__(16) uint8_t copy_smem[];
     const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CopyRing R = copy_ring_at(copy_smem + warp * copy_ring_bytes(po.copy_stages, po.copy_piece_bytes), po.copy_stages, po.copy_piece_bytes, lane == 0);
+    __syncthreads();
     for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += gridDim.x * W) {
         const uint64_t base = po.byte_off[(uint64_t)task * 32];
-        if (po.framed)
+        if (po.copy_stages) {
+            if (po.framed)
+                packed_copy_task_ring<true>(io, po, task, base, lane, R);
+            else
+                packed_copy_task_ring<false>(io, po, task, base, lane, R);
+        } else if (po.framed)
             packed_copy_task<true>(io, po, task, base, lane);
         else
             packed_copy_task<false>(io, po, task, base, lane);
@@ -404,6 +668,9 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
         ctl.arrive[0] = ctl.arrive[1] = 0;
         ctl.resolved = ctl.copy_ticket = ctl.copy_done = 0;
     }
+    // the copy warps' staging rings lie behind the mbarriers
+    auto copy_mem = [&]() { return (uint8_t *)(((uintptr_t)(mbars + W * kTileStages + 1) + 15) & ~(uintptr_t)15) + (warp - W) * copy_ring_bytes(po.copy_stages, po.copy_piece_bytes); };
+    if (PACKED && warp >= W && lane == 0 && po.copy_stages) (void)copy_ring_at(copy_mem(), po.copy_stages, po.copy_piece_bytes, true);
     __syncthreads();
     if (threadIdx.x == 0) {
         tma_expect(tab_bar, kEncTabBytes + tab2_bytes);
@@ -420,9 +687,19 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     const uint32_t swz = (lane >> 1) & 3;
 
     if (PACKED && po.trace && lane == 0) po.trace[((uint64_t)blockIdx.x * 32 + warp) * kTraceWords] = globaltimer_ns();
+    if (PACKED && warp >= W) {  // a copy warp has no tasks: it serves the pool until the CTA has nothing left
+        if (po.copy_stages) {
+            CopyRing R = copy_ring_at(copy_mem(), po.copy_stages, po.copy_piece_bytes, false);
+            while (packed_copy_one<true>(ctl, io, po, W, total_warps, n_tasks, lane, true, &R)) {
+            }
+        } else {
+            while (packed_copy_one<false>(ctl, io, po, W, total_warps, n_tasks, lane, true, nullptr)) {
+            }
+        }
+        return;
+    }
     uint32_t round = 0;
-    // a copy warp (PACKED, warp >= W) has no tasks: it goes straight to the pool below
-    for (uint32_t task = (PACKED && warp >= W) ? n_tasks : blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
+    for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         if (lane == 0) {
@@ -498,9 +775,9 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             const uint32_t par = round & 1;
             uint32_t old = 0;
             // warp_tot[par] / arrive[par] still belong to round - 2 until that round is resolved (its last warp may be
-            // waiting for the copy pool): nobody arrives at this round before.  This is also how the pool's
-            // back-pressure reaches every coding warp, not just the resolving one -- and a warp held up here copies.
+            // in the look-back, waiting for lower-numbered CTAs): nobody arrives at this round before.
             if (round >= 2) packed_wait_helping(ctl, io, po, W, total_warps, n_tasks, lane, &ctl.resolved, round - 1);
+            __threadfence();  // this task's slots: visible at gpu scope before anybody (generic or async proxy) is told to read them
             if (lane == 0) {
                 *(volatile unsigned long long *)&ctl.warp_tot[par][warp] = T;
                 __threadfence_block();
@@ -521,19 +798,18 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
                     if (lane == 0) st_relaxed_gpu(po.cta_state + g, kLbPrefix | (excl + A));
                 }
                 if (lane == 0 && first + nvalid == n_tasks) po.byte_off[io.n_blocks] = excl + A;  // the very last round: grand total
-                // warp_excl[par] still serves the copy of round - 2: wait until all of it (and everything before) is done.
-                // Also the back-pressure: the coder never runs more than two rounds ahead of the copy pool.
-                if (round >= 2) packed_wait_helping(ctl, io, po, W, total_warps, n_tasks, lane, &ctl.copy_done, (round - 1) * W);
-                __syncwarp();
-                if (lane < nvalid) *(volatile unsigned long long *)&ctl.warp_excl[par][lane] = excl + incl - t;
+                // Each task's place goes to its first block's entry of byte_off (the copier rewrites it with the same value):
+                // one word per task, never reused, so the coder does not wait for the copy pool -- what the pool has not
+                // moved when the symbols run out is moved by the whole CTA at the end.
+                if (lane < nvalid) *(volatile unsigned long long *)&po.byte_off[(uint64_t)(first + lane) * 32] = excl + incl - t;
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0) *(volatile uint32_t *)&ctl.resolved = round + 1;
             }
         }
     }
-    if (PACKED)  // a copy warp, or a coding warp that is out of symbols: move streams until the CTA has none left
-        while (packed_copy_one(ctl, io, po, W, total_warps, n_tasks, lane, true)) {
+    if (PACKED)  // a coding warp that is out of symbols joins the pool (through registers: it has no staging ring)
+        while (packed_copy_one<false>(ctl, io, po, W, total_warps, n_tasks, lane, true, nullptr)) {
         }
 }
 
@@ -1645,9 +1921,10 @@ static void pick_launch(uint32_t n_tasks, int n_sm, uint32_t max_w, uint32_t *gr
 extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
     if (c) c->debug_mode = mode;
 }
-// debug_mode: low 4 bits = the path selection above; bit 4 = 8 copy warps (24 coding warps) in the packed encoder
-// (measured slower: tools/sweep_knobs.py), bit 8 = split batches at 64 MiB of rows instead of 2^30 blocks (so that
-// tests reach the multi-launch path)
+// debug_mode: low 4 bits = the path selection above; bit 8 = split batches at 64 MiB of rows instead of 2^30 blocks (so
+// that tests reach the multi-launch path).  Copy pool of the packed encoder (tools/sweep_knobs.py; tests run every
+// variant): bit 5 = no staging rings (every copy through registers), bit 6 / bit 7 = pieces of at most 512 / 1024 bytes,
+// bits 12-15 = number of dedicated copy warps (0 = kCopyWarps).
 static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
 static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
 extern "C" void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words) {
@@ -1685,7 +1962,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     const uint32_t n_tasks_all = (uint32_t)((io.n_blocks + 31) / 32);
     uint32_t grid, warps;
     size_t fixed = kEncTabBytes + tab2_bytes + (kMaxWarps * kTileStages + 1) * sizeof(uint64_t) + 2048 + (packed ? 2048 : 0);  // PACKED: the static PackCtl block
-    const uint32_t copy_warps = packed ? ((c->debug_mode & 16) ? 8u : kCopyWarps) : 0u;
+    const uint32_t copy_warps = packed ? ((c->debug_mode >> 12) & 15 ? (uint32_t)((c->debug_mode >> 12) & 15) : kCopyWarps) : 0u;
     uint32_t max_w = max_warps_for(kEncWarpSmem, fixed);
     if (max_w > 32 - copy_warps) max_w = 32 - copy_warps;
     pick_launch(n_tasks_all, c->n_sm, max_w, &grid, &warps);
@@ -1696,6 +1973,19 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
     if (packed) {
         po = *packed;
         po.copy_warps = copy_warps;
+        // staging rings for the copy warps out of whatever shared memory the coder leaves (227 KiB - 1 KiB static)
+        const size_t free_smem = 226 * 1024 > smem + 16 ? 226 * 1024 - smem - 16 : 0;
+        // the largest pieces (fewest instructions per byte) of which at least two fit, else no ring
+        const size_t per_warp = free_smem / copy_warps > 528 ? free_smem / copy_warps - 528 : 0;  // minus the stream table and padding
+        uint32_t stages = 0;
+        for (uint32_t pb = (c->debug_mode & 64) ? 512u : (c->debug_mode & 128) ? 1024u : 2048u; pb >= 512; pb >>= 1) {
+            po.copy_piece_bytes = pb;
+            stages = (uint32_t)(per_warp / (pb + kCopyOverlapBytes + 8));
+            if (stages >= 2) break;
+        }
+        if (stages > 8) stages = 8;
+        po.copy_stages = (stages < 2 || (c->debug_mode & 32)) ? 0u : stages;
+        smem += 16 + (size_t)copy_warps * copy_ring_bytes(po.copy_stages, po.copy_piece_bytes);
         po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
         // one look-back word per (round, CTA) of the WHOLE batch: the launches of a split batch are whole rounds, so the
         // numbering (and with it the running prefix) simply continues from launch to launch
@@ -1976,7 +2266,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, 0, 0, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);
@@ -1990,12 +2280,17 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
 
 extern "C" int scl_debug_copy_only(const scl_coder *c, uint64_t n_blocks, uint8_t *d_scratch, uint64_t scratch_stride, uint8_t *d_dst,
                                    uint64_t dst_bytes, uint32_t framed, uint64_t *d_byte_offset, uint64_t *d_bit_offset, uint64_t *d_bit_len,
-                                   uint32_t *d_status, uint32_t warps_per_cta, void *stream) {
+                                   uint32_t *d_status, uint32_t warps_per_cta, uint32_t ring_stages, void *stream) {
     if (!c || !d_scratch || !d_dst || !d_byte_offset || !d_bit_offset || !d_bit_len || !d_status || warps_per_cta < 1 || warps_per_cta > 32)
         return SCL_E_INVALID;
     BlockIo io{nullptr, 0, nullptr, 0, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_status, 0};
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, nullptr, framed ? 1u : 0u, 0, kCopyWarps, nullptr};
-    copy_only_kernel<<<c->n_sm > 0 ? c->n_sm : 148, warps_per_cta * 32, 0, (cudaStream_t)stream>>>(io, po, (uint32_t)((n_blocks + 31) / 32));
+    const uint32_t piece_bytes = (ring_stages & 0x200) ? 2048u : (ring_stages & 0x100) ? 1024u : 512u;  // bits 8, 9 of ring_stages: 64- / 128-chunk pieces
+    ring_stages &= 0xFF;
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, nullptr, framed ? 1u : 0u, 0, kCopyWarps, ring_stages, piece_bytes, nullptr};
+    const size_t smem = (size_t)warps_per_cta * copy_ring_bytes(ring_stages, piece_bytes);
+    if (ring_stages == 1 || smem > 200 * 1024) return SCL_E_INVALID;
+    SCL_CUDA(cudaFuncSetAttribute(copy_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    copy_only_kernel<<<c->n_sm > 0 ? c->n_sm : 148, warps_per_cta * 32, smem, (cudaStream_t)stream>>>(io, po, (uint32_t)((n_blocks + 31) / 32));
     return check_launch("copy_only_kernel");
 }
 

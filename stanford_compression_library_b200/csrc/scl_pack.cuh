@@ -238,6 +238,56 @@ __device__ __forceinline__ void pack_block_warp_a16(const uint8_t *__restrict__ 
     }
 }
 
+// ---- the same copy out of a shared-memory staging ring (the fused encoder's dedicated copy warps) ---------------
+// A copy warp that loads into registers exposes one memory latency per batch of chunks (~2200 cycles per 4 KiB:
+// profiles/r2q_copy_only.jsonl).  Here the source arrives by bulk async copy (TMA), several pieces ahead and across
+// stream boundaries, so the warp only ever touches shared memory and the destination.
+//   region of a stream  = the 16-byte granules from the one holding its first needed bit (g0) to two past the one
+//                         holding its last bit;
+//   piece p of a region = granules [PC p, PC p + PC + 5), PC = 32 or 64 chunks per piece: chunk c needs granules
+//                         c + dlt and c + dlt + 1 (dlt = 0..2, the distance from g0 to chunk 0's granule), and the last
+//                         piece also holds the granules the tail bytes are cut from.  Pieces overlap by 5 granules (80
+//                         bytes read twice, from L2).
+constexpr uint32_t kCopyOverlapBytes = 5 * 16;  // a stage holds its piece's chunks' bytes + 5 granules
+
+struct StreamGeo {  // where a stream of `nbits` goes when its record's payload starts at address d (only d % 16 matters)
+    uint32_t num_pad, lead, payload_bytes, head, n_chunks, tail0;
+};
+template <bool FRAMED>
+__device__ __forceinline__ StreamGeo stream_geo(uint32_t nbits, uint32_t d_low4) {  // as pack_block_warp_a16
+    StreamGeo g;
+    g.num_pad = FRAMED ? ((8u - (nbits + 3u) % 8u) % 8u) : 0u;
+    g.lead = FRAMED ? 3u + g.num_pad : 0u;
+    g.payload_bytes = FRAMED ? (nbits + g.lead) >> 3 : (nbits + 7u) >> 3;
+    g.head = (16u - d_low4) & 15u;
+    if (FRAMED && 8 * g.head < g.lead) g.head += 16;
+    if (g.head > g.payload_bytes) g.head = g.payload_bytes;
+    g.n_chunks = (8 * g.head + 128 <= nbits + g.lead) ? ((nbits + g.lead - 8 * g.head) >> 7) : 0u;
+    g.tail0 = g.head + 16 * g.n_chunks;
+    return g;
+}
+
+// stream_byte_masked_raw out of a staged piece: `sb` = shared address of the piece's first granule, S = distance in
+// bits from there to stream position `pos`
+__device__ __forceinline__ uint32_t stream_byte_masked_smem(uint32_t sb, uint32_t S, int32_t pos, uint32_t nbits) {
+    const uint32_t wa = sb + ((S >> 5) << 2);
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(wa + 4));
+    const uint32_t v = funnel_l(w1, w0, S & 31u) >> 24;
+    uint32_t keep = 0xFFu;
+    if (pos < 0) keep = pos <= -8 ? 0u : (0xFFu >> (uint32_t)(-pos));
+    const int32_t r = (int32_t)nbits - pos;
+    if (r < 8) keep &= r <= 0 ? 0u : ~(0xFFu >> (uint32_t)r);
+    return v & keep;
+}
+
+__device__ __forceinline__ uint4 lds_plain128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+
 // ---- decoupled look-back ----------------------------------------------------------------------------------
 // state[i] = flag << 62 | value: flag 0 = not there yet, 1 = the producer's own total, 2 = inclusive prefix up to
 // and including producer i.  One 64-bit word carries flag and value together, so relaxed accesses suffice.

@@ -328,3 +328,27 @@ def test_split_launches_give_the_same_streams(framed):
     assert torch.equal(p1.byte_offset, p2.byte_offset) and torch.equal(p1.bit_offset, p2.bit_offset) and torch.equal(p1.buf[:total], p2.buf[:total])
     for d in (d1, d2, d3):
         assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, e1.bit_len)
+
+
+@pytest.mark.parametrize("framed", [False, True], ids=["packed", "framed"])
+@pytest.mark.parametrize("mode", [0, 32, 64, 128, 5 << 12, (8 << 12) | 64, (1 << 12) | 128], ids=["default", "no_ring", "piece512", "piece1024", "copy5", "copy8_piece512", "copy1_piece1024"])
+@pytest.mark.parametrize("name", ["rans_default", "tans"])
+def test_copy_pool_variants_give_the_same_bytes(name, mode, framed):
+    """The fused encoder's copy pool has two forms of the same copy -- through registers (coding warps that ran out of
+    symbols) and through a shared-memory ring filled by bulk async copies, in pieces of 512 / 1024 / 2048 bytes (the
+    dedicated copy warps) -- and which one moves a given stream depends on timing.  Every variant, forced through the
+    per-handle hook, must produce the bytes of encode + pack: streams shorter than one 16-byte chunk, streams of one
+    piece, of several pieces, and of exactly a whole number of pieces' worth of chunks all occur here."""
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    enc, dec = _codec(name)
+    try:
+        enc.device_coder().debug_path(mode)
+        for (B, N), seed in (((148 * 28 * 32 + 777, 8), 1), ((20000, 150), 2), ((9000, 700), 3), ((4737 * 2, 2600), 4), ((4200, 5400), 5)):
+            data = sample_blocks(zipf_probabilities(), B, N, seed=seed, device="cuda:0")
+            # rows of very different compressibility: every bit / word / granule alignment of the source occurs
+            data[::3] &= 0x0F
+            data[1::7] = 0
+            _check_against_slots(enc, dec, data, framed)
+    finally:
+        enc.device_coder().debug_path(0)

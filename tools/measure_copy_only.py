@@ -32,17 +32,17 @@ def main():
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     h = enc.device_coder()._h
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    for warps in (1, 2, 4, 8, 16, 32):
+    for stages, warps in [(st, w) for st in (0, 0x104, 0x202, 0x203, 0x204) for w in (1, 4, 8, 16) if w * ((st & 255) * (2140 if st >> 9 else 1120 if st >> 8 else 608) + 512) <= 200 * 1024]:
         p.buf.zero_()
 
         def run():
             rc = lib.scl_debug_copy_only(h, B, ptr(scratch), stride, ptr(p.buf), p.buf.numel() - 16, 0, ptr(p.byte_offset), ptr(p.bit_offset), ptr(p.bit_len),
-                                         ptr(p.status), warps, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                         ptr(p.status), warps, stages, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
             assert rc == 0
 
         run()
         torch.cuda.synchronize()
-        assert torch.equal(p.buf[:total], ref), "copy-only output differs"
+        assert torch.equal(p.buf[:total], ref), "copy-only output differs (stages %d, warps %d)" % (stages, warps)
         best = 1e9
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,7 +52,7 @@ def main():
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         tasks_per_warp = (B / 32) / (n_sm * warps)
-        print(json.dumps({"warps_per_sm": warps, "ms": best, "us_per_task_per_warp": best * 1e3 / tasks_per_warp, "GBps_read_plus_write": 2 * total / best / 1e6,
+        print(json.dumps({"ring_stages": stages & 255, "piece_bytes": 2048 if stages >> 9 else 1024 if stages >> 8 else 512, "warps_per_sm": warps, "ms": best, "us_per_task_per_warp": best * 1e3 / tasks_per_warp, "GBps_read_plus_write": 2 * total / best / 1e6,
                           "GBps_per_warp": total / best / 1e6 / (n_sm * warps)}), flush=True)
 
 

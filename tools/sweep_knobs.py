@@ -1,6 +1,6 @@
 """Experiment knobs of the second-generation rANS kernels (scl_coder_debug_path high bits).  The CTA round barrier and
 the L1 prefetch this tool was written for measured no effect (profiles/r2f_sweep.jsonl) and are gone from the kernels;
-what is left is the copy-warp count of the packed encoder.  Diagnostic; one JSON line per (blocks, mode).
+what is left are the variants of the packed encoder's copy pool (staging rings on / off, piece size, copy warps).  Diagnostic; one JSON line per (blocks, mode).
     python tools/sweep_knobs.py [--blocks 262144 2097152]"""
 import argparse
 import json
@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams  # noqa: E402
 from stanford_compression_library_b200.workloads import sample_blocks, zipf_frequencies, zipf_probabilities  # noqa: E402
 
-COPY8, L1, SYNC1, SYNC2 = 16, 32, 64, 128
+NO_RING, PIECE_512, PIECE_1024 = 32, 64, 128  # scl_coder_debug_path bits; bits 12-15 = copy warps
 
 
 def timeit(fn, iters=5):
@@ -52,7 +52,7 @@ def main():
             td = timeit(lambda: dec.decode_blocks(p, N, reuse=d))
             assert torch.equal(d.symbols[:, :N], data)
             print(json.dumps({"blocks": B, "mode": mode, "encode_slots_ms_per_GiB": te / gib, "decode_ms_per_GiB": td / gib}), flush=True)
-        for mode in (0, COPY8):
+        for mode in (0, NO_RING, PIECE_512, PIECE_1024, 5 << 12, 6 << 12, 8 << 12):
             enc.device_coder().debug_path(mode)
             tp = timeit(lambda: enc.encode_blocks_packed(data, capacity=B * N, reuse=p))
             p.check()

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blocks", type=int, default=262144)
     ap.add_argument("--block-len", type=int, default=4096)
+    ap.add_argument("--mode", type=int, default=0, help="scl_coder_debug_path value (copy pool variants)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     enc = rANSEncoder(rANSParams(zipf_frequencies()))
@@ -28,6 +29,7 @@ def main():
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
     trace = torch.zeros(n_sm * 32 * WORDS, dtype=torch.int64, device="cuda:0")
     dc = enc.device_coder()
+    dc.debug_path(a.mode)
     for _ in range(2):
         enc.encode_blocks_packed(data, reuse=p)
     torch.cuda.synchronize()
@@ -43,7 +45,7 @@ def main():
     start = t[:, :, 0]
     t0 = start[start > 0].min()
     us = lambda x: (x - t0) / 1e3  # noqa: E731
-    out = {"blocks": a.blocks, "block_len": a.block_len, "kernel_ms_cuda_events": ev0.elapsed_time(ev1)}
+    out = {"mode": a.mode, "blocks": a.blocks, "block_len": a.block_len, "kernel_ms_cuda_events": ev0.elapsed_time(ev1)}
     rounds = []
     for r in range(19):
         e = t[:, :, 1 + r]
@@ -60,7 +62,7 @@ def main():
             busy, wait = t[:, :, 23][m] / 1e3, t[:, :, 24][m] / 1e3
             out[name] = {"warps": int(m.sum()), "tasks_total": int(tasks[m].sum()), "tasks_per_warp_median": float(np.median(tasks[m])),
                          "busy_us_median": float(np.median(busy)), "busy_us_max": float(busy.max()), "waiting_for_resolution_us_median": float(np.median(wait)),
-                         "us_per_task_median": float(np.median(busy / tasks[m])),
+                         "us_per_task_median": float(np.median(busy / tasks[m])), "ring_wait_cycles_per_task_median": float(np.median(t[:, :, 25][m] / tasks[m])),
                          "first_copy_start_us_median": us(np.median(t[:, :, 21][m])), "last_copy_end_us_median": us(np.median(t[:, :, 22][m])),
                          "last_copy_end_us_max": us(t[:, :, 22][m].max())}
     last_code = max(r["end_us_max"] for r in rounds) if rounds else 0.0
