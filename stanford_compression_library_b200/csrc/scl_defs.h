@@ -59,6 +59,13 @@ struct alignas(16) TansSym {  // per byte value
     int32_t row;       // row offset into enc_table minus min_shrunk_state: index = row + x_shrunk
     uint32_t pad;
 };
+// The second-generation encoder's form of the same row, 8 bytes (one LDS.64 instead of LDS.128: the tANS encoder is bound
+// by L1/shared wavefronts, profiles/r2n_tans_kernels_ncu_summary.json): w = row << 7 | nb0, so that (int32)w >> 5 is
+// the row offset in BYTES and w & 31 the bit count (nb0 <= 24; |row| < 2^23).  w = 0xFFFFFFFF = invalid byte.
+struct alignas(8) TansSym8 {
+    uint32_t thresh;
+    uint32_t w;
+};
 // dec_packed[x - L] = x_shrunk << 8 | byte value   (base_decode_step_table, tANS.py:208-215)
 
 // ---- range coder (range_coder.py), PRECISION in {24, 32} ----------------------------------

@@ -24,6 +24,7 @@ constexpr uint32_t kRingStrideWords = 32;  // [word][lane] interleave: one bank 
 constexpr uint32_t kEncRingWords = 16;     // per-lane capacity of the encoder's output ring
 constexpr uint32_t kDecRingWords = 32;     // per-lane capacity of the decoder's input ring (+1 wrap duplicate)
 constexpr uint32_t kEncTabCopies = 8;      // bank-rotated replicas of the 16-byte encode entries
+constexpr uint32_t kTansTabCopies = 16;    // ... of the tANS encoder's 8-byte symbol rows (the same 128 bytes per byte value)
 constexpr uint32_t kFastMaxBitsPerSym = 16;
 
 SCL_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) {  // (hi:lo) >> min(s,32), low word
@@ -46,6 +47,11 @@ __device__ __forceinline__ u32x4 lds128(saddr_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
     return r;
 }
+__device__ __forceinline__ u32x2 lds64(saddr_t a) {
+    u32x2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+    return r;
+}
 __device__ __forceinline__ uint32_t lds32(saddr_t a) {
     uint32_t r;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
@@ -56,6 +62,7 @@ __device__ __forceinline__ void sts32(saddr_t a, uint32_t v) { asm volatile("st.
 typedef uintptr_t saddr_t;
 inline saddr_t saddr_of(const void *p) { return (uintptr_t)p; }
 inline u32x4 lds128(saddr_t a) { return *(const u32x4 *)a; }
+inline u32x2 lds64(saddr_t a) { return *(const u32x2 *)a; }
 inline uint32_t lds32(saddr_t a) { return *(const uint32_t *)a; }
 inline void sts32(saddr_t a, uint32_t v) { *(uint32_t *)a = v; }
 #endif
@@ -516,29 +523,29 @@ SCL_HD void dec_group16(DecLaneV2 &D, const DecConst &c, uint32_t w[4]) {
 //   enc_table[row + x_shrunk] = next state        dec_packed[x - L] = x_shrunk << 8 | byte
 // ------------------------------------------------------------------------------------------------
 template <bool CHECK, class Lane>
-SCL_HD void tans_enc_step(Lane &L, const u32x4 &e, saddr_t enc_table) {
+SCL_HD void tans_enc_step(Lane &L, const u32x2 &e, saddr_t enc_table) {  // e = TansSym8 {thresh, row << 7 | nb0}
     if (CHECK && e.y == 0xFFFFFFFFu) {
         L.bad = 1;
         return;
     }
-    uint32_t k = e.y + (L.x >= e.x ? 1u : 0u);  // shrink_state_num_out_bits_base + threshold test
+    uint32_t k = (e.y & 31u) + (L.x >= e.x ? 1u : 0u);  // shrink_state_num_out_bits_base + threshold test
     L.lo = funnel_r(L.lo, L.hi, k);
     L.hi = funnel_r(L.hi, L.x, k);
     L.room -= k;
-    L.x = lds32(enc_table + (saddr_t)(((L.x >> k) + e.z) << 2));  // base_encode_step_table[(s, x_shrunk)]
+    L.x = lds32(enc_table + (saddr_t)(int32_t)(((int32_t)e.y >> 5) + (int32_t)((L.x >> k) << 2)));  // base_encode_step_table[(s, x_shrunk)]
 }
 
 template <bool CHECK, class Lane>
 SCL_HD void tans_enc_chunk16(Lane &L, saddr_t symtab, uint32_t sym_stride, saddr_t enc_table, const u32x4 &v) {
     const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-    u32x4 e[4], nx[4];  // per-symbol rows fetched one word ahead of their use, as in enc_chunk16
+    u32x2 e[4], nx[4];  // per-symbol rows fetched one word ahead of their use, as in enc_chunk16
 #pragma unroll
-    for (int b = 0; b < 4; ++b) e[b] = lds128(symtab + (saddr_t)mad32(byte_of(wd[0], b), sym_stride, 0u));
+    for (int b = 0; b < 4; ++b) e[b] = lds64(symtab + (saddr_t)mad32(byte_of(wd[0], b), sym_stride, 0u));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (j < 3) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) nx[b] = lds128(symtab + (saddr_t)mad32(byte_of(wd[j + 1], b), sym_stride, 0u));
+            for (int b = 0; b < 4; ++b) nx[b] = lds64(symtab + (saddr_t)mad32(byte_of(wd[j + 1], b), sym_stride, 0u));
         }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -559,13 +566,13 @@ SCL_HD void tans_enc_chunk(Lane &L, saddr_t symtab, uint32_t sym_stride, saddr_t
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                tans_enc_step<CHECK>(L, lds128(symtab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)), enc_table);
+                tans_enc_step<CHECK>(L, lds64(symtab + (saddr_t)mad32(byte_of(wd[j], b), sym_stride, 0u)), enc_table);
                 if (b & 1) L.spill_check();
             }
         }
     } else {
         for (uint32_t i = 0; i < cnt; ++i) {
-            tans_enc_step<CHECK>(L, lds128(symtab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)), enc_table);
+            tans_enc_step<CHECK>(L, lds64(symtab + (saddr_t)(((wd[i >> 2] >> (8 * (i & 3))) & 0xFFu) * sym_stride)), enc_table);
             L.spill_check();
         }
     }

@@ -679,7 +679,9 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     }
     mbar_wait(tab_bar, 0);
 
-    const saddr_t my_tab = saddr_of(s_tab) + (lane & (kEncTabCopies - 1)) * 16;  // this lane's bank-rotated replica
+    // this lane's bank-rotated replica: 8 x 16-byte entries (rANS, LDS.128: a quarter warp per wavefront) or 16 x 8-byte rows
+    // (tANS, LDS.64: half a warp per wavefront) -- 128 bytes per byte value either way
+    const saddr_t my_tab = saddr_of(s_tab) + (KIND == 0 ? (lane & (kEncTabCopies - 1)) * 16 : (lane & (kTansTabCopies - 1)) * 8);
     const uint32_t n = io.block_len;
     const uint32_t n_tiles = (n + kTileCols - 1) / kTileCols;
     const uint32_t total_warps = gridDim.x * W;
@@ -1656,7 +1658,7 @@ struct scl_coder {
     uint32_t dec32_bytes = 0;
     RansGeneric *d_gen = nullptr;
     TansSym *d_tsym = nullptr;
-    TansSym *d_tsymx8 = nullptr;  // bank-rotated replicas for the v2 tANS encoder
+    TansSym8 *d_tsymx8 = nullptr;  // bank-rotated replicas (16 x 8 bytes per byte value) for the v2 tANS encoder
     uint32_t *d_tenc = nullptr, *d_tdec = nullptr;
     uint32_t ttab_bytes = 0;
     RangeTab *d_range = nullptr;
@@ -1768,10 +1770,11 @@ extern "C" int scl_coder_create(const scl_params *params, const uint8_t *alphabe
         rc = upload(&c->d_gen, &t.r.gen, sizeof(RansGeneric), sizeof(RansGeneric), s);
         if (!rc) rc = upload(&c->d_tsym, t.sym_tab.data(), sizeof(TansSym) * 256, sizeof(TansSym) * 256, s);
         if (!rc) rc = upload(&d_rows, t.row_of_idx.data(), sizeof(uint32_t) * n_sym, sizeof(uint32_t) * n_sym, s);
-        std::vector<TansSym> trep(256 * kEncTabCopies);
+        std::vector<TansSym8> trep(256 * kTansTabCopies);
         for (uint32_t sy = 0; sy < 256; ++sy)
-            for (uint32_t j = 0; j < kEncTabCopies; ++j) trep[sy * kEncTabCopies + j] = t.sym_tab[sy];
-        if (!rc) rc = upload(&c->d_tsymx8, trep.data(), trep.size() * sizeof(TansSym), trep.size() * sizeof(TansSym), s);
+            for (uint32_t j = 0; j < kTansTabCopies; ++j) trep[sy * kTansTabCopies + j] = t.sym_tab8[sy];
+        static_assert(256 * kTansTabCopies * sizeof(TansSym8) == kEncTabBytes, "both encoders stage a 32 KiB symbol table");
+        if (!rc) rc = upload(&c->d_tsymx8, trep.data(), trep.size() * sizeof(TansSym8), trep.size() * sizeof(TansSym8), s);
         if (rc) {
             cudaStreamSynchronize(s);  // the uploads issued so far read host vectors that die with this scope
             cudaFree(d_rows);

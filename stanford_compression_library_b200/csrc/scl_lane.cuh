@@ -66,6 +66,9 @@ SCL_HD uint64_t mask64(uint32_t k) { return k >= 64 ? ~0ull : ((1ull << k) - 1ul
 struct u32x4 {
     uint32_t x, y, z, w;
 };
+struct alignas(8) u32x2 {
+    uint32_t x, y;
+};
 
 // streaming 16-byte load/store of the lane's own row (bypass L1 allocation: every byte is touched once)
 SCL_HD u32x4 ld_stream16(const uint8_t *p) {

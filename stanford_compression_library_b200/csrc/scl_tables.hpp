@@ -199,6 +199,7 @@ struct RansHost {
 struct TansHost {
     RansHost r;
     std::vector<TansSym> sym_tab;  // 256 by byte value
+    std::vector<TansSym8> sym_tab8;  // the same rows in the second-generation encoder's 8-byte form
     std::vector<uint32_t> row_of_idx;  // enc_table row offset per alphabet index
     int init(const scl_params &p, const uint8_t *alphabet, const uint64_t *f, uint32_t n_sym) {
         int rc = r.init(p, alphabet, f, n_sym);
@@ -207,6 +208,7 @@ struct TansHost {
         if (!is_pow2_u64(r.c.M) || r.c.NBO != 1) return SCL_E_INVALID;
         if (r.c.L > (1ull << 23)) return SCL_E_UNSUPPORTED;  // dec_packed keeps x_shrunk in 24 bits
         sym_tab.assign(256, TansSym{0, 0xFFFFFFFFu, 0, 0});
+        sym_tab8.assign(256, TansSym8{0, 0xFFFFFFFFu});
         row_of_idx.assign(n_sym, 0);
         uint64_t row = 0;
         for (uint32_t i = 0; i < n_sym; ++i) {
@@ -221,6 +223,7 @@ struct TansHost {
             e.row = (int32_t)((int64_t)row - (int64_t)mn);
             e.pad = 0;
             sym_tab[r.a.idx2sym[i]] = e;
+            sym_tab8[r.a.idx2sym[i]] = TansSym8{e.thresh, ((uint32_t)e.row << 7) | e.nb0};  // L <= 2^23: |row| < 2^23, nb0 <= 24
             row_of_idx[i] = (uint32_t)row;
             row += mn;  // RF*f entries per symbol; total = L
         }

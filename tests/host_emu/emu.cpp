@@ -387,9 +387,9 @@ static void tans_enc_v2_block(const Emu &e, const uint8_t *row, uint32_t n, uint
         u32x4 v;
         memcpy(&v, tmp, 16);
         if (r.c.check_sym)
-            tans_enc_chunk<true>(L, saddr_of(e.tans->sym_tab.data()), 16, saddr_of(e.tenc.data()), v, cnt);
+            tans_enc_chunk<true>(L, saddr_of(e.tans->sym_tab8.data()), 8, saddr_of(e.tenc.data()), v, cnt);
         else
-            tans_enc_chunk<false>(L, saddr_of(e.tans->sym_tab.data()), 16, saddr_of(e.tenc.data()), v, cnt);
+            tans_enc_chunk<false>(L, saddr_of(e.tans->sym_tab8.data()), 8, saddr_of(e.tenc.data()), v, cnt);
     }
     L.put(L.x, r.c.NSB);
     uint32_t st = SCL_ST_OK;
