@@ -70,7 +70,7 @@ SCL_HD bool range_needs_norm(uint32_t low, uint32_t range) { return (range <= (~
 // ------------------------------------------------------------------------------------------------
 struct RangeEncV2 {
     uint32_t low, range;
-    uint32_t ahi, alo, nb;  // byte window and the number of bytes in it (<= 7)
+    uint32_t ahi, alo, nbits;  // byte window and the number of BITS in it (<= 56, a multiple of 8)
     uint32_t wofs, rofs;    // words spilled / drained so far, * 128
     saddr_t ring;
     uint8_t *gbegin, *gend;  // output slot; the stream starts at gbegin
@@ -82,7 +82,7 @@ struct RangeEncV2 {
         neg1 = 0xFFFFFFFFu - (shift >> 8);
         low = 0;
         range = 0xFFFFFFFFu;  // range_coder.py:191-192
-        ahi = alo = nb = 0;
+        ahi = alo = nbits = 0;
         wofs = rofs = 0;
         ring = ring_;
         gbegin = slot_begin;
@@ -99,20 +99,20 @@ struct RangeEncV2 {
     SCL_HD void put_byte(uint32_t b) {
         ahi = funnel_l(alo, ahi, 8);
         alo = (alo << 8) | b;
-        nb += 1;
+        nbits += 8;
     }
     SCL_HD void put_word(uint32_t w) {  // 4 bytes, most significant first (the size header)
         ahi = alo;
         alo = w;
-        nb += 4;
+        nbits += 32;
     }
-    // at most 4 new bytes since the last call (two symbols' fixed rounds): nb <= 7
+    // at most 4 new bytes since the last call (two symbols' fixed rounds): at most 7 bytes in the window
     SCL_HD void spill_check() {
-        if (nb >= 4) {
-            const uint32_t w = funnel_r(alo, ahi, (nb - 4) * 8);  // the oldest four bytes
+        if (nbits >= 32) {
+            const uint32_t w = funnel_r(alo, ahi, nbits - 32);  // the oldest four bytes
             sts32(ring_slot(wofs), w);
             wofs += 128;
-            nb -= 4;
+            nbits -= 32;
         }
     }
     SCL_HD void drain_check() {
@@ -135,9 +135,25 @@ struct RangeEncV2 {
         const uint32_t k = go ? 8u : 0u;
         ahi = funnel_l(alo, ahi, k);
         alo = funnel_l(low, alo, k);  // (alo << 8) | (low >> 24), or alo unchanged
-        nb += k >> 3;
+        nbits += k;
         low <<= k;
         range <<= k;
+    }
+    // The two fixed rounds of a symbol as one: a round changes `range` (underflow) and shifts low / range, but the bytes
+    // it releases are simply the next top byte of `low`, so the window takes both rounds' bytes in ONE funnel-shift pair
+    // (the ALU pipe is the busy one: profiles/r2n_range_v2_ncu_summary.json).  A lane that did not shift in the first
+    // round does not in the second (state unchanged).
+    SCL_HD void norm_twice() {
+        const uint32_t k1 = range_norm_test(low, range) ? 8u : 0u;
+        const uint32_t low1 = low << k1;
+        range <<= k1;
+        const uint32_t k2 = range_norm_test(low1, range) ? 8u : 0u;
+        range <<= k2;
+        const uint32_t kt = k1 + k2;
+        ahi = funnel_l(alo, ahi, kt);
+        alo = funnel_l(low, alo, kt);  // the top kt bits of low
+        nbits += kt;
+        low = low1 << k2;
     }
     // e = freq << 16 | cum for the symbol (0xFFFFFFFF: not in the alphabet)
     template <bool CHECK, bool VOTE>
@@ -149,8 +165,7 @@ struct RangeEncV2 {
         const uint32_t r = range >> rshift;  // range // T: shrink_range (range_coder.py:88-105)
         low = mad32(e & 0xFFFFu, r, low);
         range = r * mulhi_fma(e, 1u << 16);
-        norm_once();
-        norm_once();  // a lane that did not shift in the first round does not in the second (state unchanged)
+        norm_twice();
         // Two rounds are enough for all but ~0.02 % of symbols (Zipf data: 30 % shift 0 bytes, 62 % one, 8 % two),
         // i.e. for ~99.3 % of a warp's steps; whether a third is needed is tested without changing the state.
         const bool need = range_needs_norm(low, range);
@@ -186,14 +201,14 @@ struct RangeEncV2 {
             else
                 ovf = 1;
         }
-        if (nb) {  // nb < 4: left-align the remaining bytes in one last word
+        if (nbits) {  // < 32: left-align the remaining bytes in one last word
             uint8_t *dst = gbegin + 4ull * words;
             if (dst + 4 <= gend)
-                st_word(dst, bswap32(alo << (8 * (4 - nb))));
+                st_word(dst, bswap32(alo << (32 - nbits)));
             else
                 ovf = 1;
         }
-        return 8ull * (4ull * words + nb);
+        return 32ull * words + nbits;
     }
 };
 
@@ -264,6 +279,19 @@ struct RangeDecV2 {
         low <<= k;
         range <<= k;
     }
+    // both fixed rounds at once (see RangeEncV2::norm_twice): the state takes the rounds' bytes in one funnel shift
+    SCL_HD void norm_twice(DecLaneV2 &D) {
+        const uint32_t k1 = range_norm_test(low, range) ? 8u : 0u;
+        const uint32_t low1 = low << k1;
+        range <<= k1;
+        const uint32_t k2 = range_norm_test(low1, range) ? 8u : 0u;
+        range <<= k2;
+        const uint32_t kt = k1 + k2;
+        state = funnel_l(bits, state, kt);  // (state << kt) | the next kt stream bits
+        bits <<= kt;
+        D.bp += kt;
+        low = low1 << k2;
+    }
     // decode_symbol (range_coder.py:225-238) + normalize (:240-267); returns the LUT entry (byte value in bits 0..7)
     template <bool VOTE>
     SCL_HD uint32_t symbol(DecLaneV2 &D, const RangeDecConst &c) {
@@ -285,8 +313,7 @@ struct RangeDecV2 {
         if (last) e = c.last;
         low = mad32(mulhi_fma(e, 1u << 24) & 0xFFFu, r, low);
         range = r * mulhi_fma(e, 1u << 12);
-        norm_once(D, c.neg1);
-        norm_once(D, c.neg1);
+        norm_twice(D);
         const bool need = range_needs_norm(low, range);  // see RangeEncV2::step
         if (SCL_UNLIKELY(VOTE ? warp_any(need) : need)) extra_rounds<VOTE>(D, need, c.neg1);
         return e;
