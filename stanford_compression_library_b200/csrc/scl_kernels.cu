@@ -1357,12 +1357,13 @@ __device__ __forceinline__ AecIid8Policy aec8_setup(uint8_t *smem, const AecTab 
     return pol;
 }
 
-__global__ void __launch_bounds__(kAec2Warps * 32) aec8_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io) {
+constexpr uint32_t kAec8MaxWarps = 24;  // 24 x 9 KiB of models + masks + table: one CTA fills an SM's shared memory
+__global__ void __launch_bounds__(kAec8MaxWarps * 32) aec8_encode_kernel(const AecTab *__restrict__ g_tab, AecConst c, BlockIo io) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ AecTab s_tab;
     __shared__ uint64_t mbar;
     AecIid8Policy pol = aec8_setup(s_dyn, g_tab, &s_tab, &mbar, c);  // (lanes past the batch load a model nobody uses)
-    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= io.n_blocks) return;
     uint64_t bits = 0;
     uint32_t n = io.sizes ? io.sizes[b] : io.block_len;
@@ -1375,12 +1376,12 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec8_encode_kernel(const AecT
     io.status[b] = st;
 }
 
-__global__ void __launch_bounds__(kAec2Warps * 32) aec8_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io) {
+__global__ void __launch_bounds__(kAec8MaxWarps * 32) aec8_decode_kernel(const AecTab *__restrict__ g_tab, AecConst c, DecodeIo io) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     __shared__ AecTab s_tab;
     __shared__ uint64_t mbar;
     AecIid8Policy pol = aec8_setup(s_dyn, g_tab, &s_tab, &mbar, c);
-    uint64_t b = (uint64_t)blockIdx.x * (kAec2Warps * 32) + threadIdx.x;
+    uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= io.n_blocks) return;
     uint64_t used = 0;
     BitReader r;
@@ -1930,6 +1931,15 @@ extern "C" void scl_coder_debug_path(scl_coder *c, int mode) {
 // bits 12-15 = number of dedicated copy warps (0 = kCopyWarps).
 static inline int dbg_path(const scl_coder *c) { return c->debug_mode & 15; }
 static inline bool force_v1(const scl_coder *c) { return dbg_path(c) == 1; }
+// Warps per CTA of the 8-bit-counter arithmetic coder: CTAs of 4 warps (five resident per SM = 20 warps), or ONE CTA of
+// 24 warps per SM when the batch is at least eight such waves deep (a wave of big CTAs ends as one: +3-4 % at
+// 1 048 576 blocks, -10 % at 262 144: profiles/r3e_aec_warps.jsonl).  debug_mode bits 16-20 override (tools/measure_aec_warps.py).
+static inline uint32_t aec8_warps(const scl_coder *c, uint64_t n_blocks) {
+    const uint32_t w = (uint32_t)(c->debug_mode >> 16) & 31u;
+    if (w >= 1 && w <= 24) return w;
+    const uint64_t n_sm = c->n_sm > 0 ? (uint64_t)c->n_sm : 148;
+    return n_blocks >= n_sm * 24 * 32 * 8 ? 24u : 4u;
+}
 extern "C" void scl_coder_debug_trace(scl_coder *c, uint64_t *d_trace, uint64_t n_words) {
     if (c) {
         c->d_trace = d_trace;
@@ -2205,10 +2215,11 @@ static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
         // second generation: every counter and group total must stay below 65536
         if (!d_model && !force_v1(c) && dbg_path(c) != 5 && c->aec->model8_ok(block_len)) {  // debug path 5: keep the 16-bit counters
-            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
-            size_t smem = kAec2MaskBytes + kAec2Warps * kAec8ModelBytes;
+            const uint32_t w8 = aec8_warps(c, n_blocks);
+            uint32_t g2 = (uint32_t)((n_blocks + w8 * 32 - 1) / (w8 * 32));
+            size_t smem = kAec2MaskBytes + w8 * kAec8ModelBytes;
             SCL_CUDA(cudaFuncSetAttribute(aec8_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            aec8_encode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            aec8_encode_kernel<<<g2, w8 * 32, smem, s>>>(c->d_aec, c->aec->c, io);
             return check_launch("aec8_encode_kernel");
         }
         if (!d_model && 16 * max_init + block_len < 65536 && !force_v1(c)) {
@@ -2370,10 +2381,11 @@ extern "C" int scl_decode_blocks(const scl_coder *c, const uint8_t *d_in, uint64
         uint64_t max_init = 0;
         for (uint32_t i = 0; i < c->aec->c.n_sym; ++i) max_init = c->aec->t.init_freq[i] > max_init ? c->aec->t.init_freq[i] : max_init;
         if (!d_model && !force_v1(c) && dbg_path(c) != 5 && c->aec->model8_ok(sym_stride)) {  // decoded size <= sym_stride is enforced by the lane
-            uint32_t g2 = (uint32_t)((n_blocks + kAec2Warps * 32 - 1) / (kAec2Warps * 32));
-            size_t smem = kAec2MaskBytes + kAec2Warps * kAec8ModelBytes;
+            const uint32_t w8 = aec8_warps(c, n_blocks);
+            uint32_t g2 = (uint32_t)((n_blocks + w8 * 32 - 1) / (w8 * 32));
+            size_t smem = kAec2MaskBytes + w8 * kAec8ModelBytes;
             SCL_CUDA(cudaFuncSetAttribute(aec8_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            aec8_decode_kernel<<<g2, kAec2Warps * 32, smem, s>>>(c->d_aec, c->aec->c, io);
+            aec8_decode_kernel<<<g2, w8 * 32, smem, s>>>(c->d_aec, c->aec->c, io);
             return check_launch("aec8_decode_kernel");
         }
         if (!d_model && 16 * max_init + sym_stride < 65536 && !force_v1(c)) {  // decoded size <= sym_stride is enforced by the lane
