@@ -352,3 +352,41 @@ def test_copy_pool_variants_give_the_same_bytes(name, mode, framed):
             _check_against_slots(enc, dec, data, framed)
     finally:
         enc.device_coder().debug_path(0)
+
+
+def test_rans_cfg5_whole_stream_on_one_gpu_packed_vs_oracle():
+    """BASELINE configs[4] at N = 1: all 2 097 152 blocks x 4 KiB (8 GiB) in ONE fused launch (16 rounds of the
+    persistent grid: the copy pool lags rounds behind the coder and the whole CTA finishes the rest) and one decode
+    launch.  Every block round-trips with exact bit accounting; the record offsets are the running sum of the record
+    sizes; a strided 48-block sample (first and last block included) is bit-compared with the oracle.
+    Skipped on devices with less than 48 GB of free memory.  Reference behaviour matched: rANS.py:186-210, 270-297,
+    encoded_stream.py:150-175 (concatenation order = block order)."""
+    from stanford_compression_library_b200.compressors.rANS import rANSDecoder, rANSEncoder, rANSParams
+    from stanford_compression_library_b200.workloads import sample_stream_blocks, zipf_freq_list, zipf_frequencies, zipf_probabilities
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48 << 30:
+        pytest.skip("needs 48 GB of free device memory")
+    B, N = 2097152, 4096
+    params = rANSParams(zipf_frequencies())
+    enc, dec = rANSEncoder(params), rANSDecoder(params)
+    data = sample_stream_blocks(zipf_probabilities(), 0, B, N, "cuda:0")
+    p = enc.encode_blocks_packed(data, capacity=B * N).check()
+    nbytes = (p.bit_len + 7) // 8
+    total = int(p.byte_offset[-1])
+    assert total == int(nbytes.sum())
+    assert torch.equal(p.byte_offset[1:], torch.cumsum(nbytes, 0).to(p.byte_offset.dtype)) and int(p.byte_offset[0]) == 0
+    assert torch.equal(p.bit_offset, 8 * p.byte_offset[:-1])
+    d = dec.decode_blocks(p, N).check()
+    assert torch.equal(d.symbols[:, :N], data) and torch.equal(d.bits_consumed, p.bit_len)
+    del d
+    oracle = so.Oracle.rans(zipf_freq_list())
+    idx = sorted({int(round(i * (B - 1) / 47)) for i in range(48)})
+    host = data[torch.tensor(idx, device="cuda:0")].cpu().numpy()
+    offs = p.byte_offset.cpu().numpy()
+    for j, b in enumerate(idx):
+        ref_bytes, ref_bits = oracle.encode_block(host[j])
+        assert int(p.bit_len[b]) == ref_bits
+        assert p.buf[offs[b] : offs[b + 1]].cpu().numpy().tobytes() == ref_bytes.tobytes(), "block %d differs from the oracle" % b
+    del p, data
+    torch.cuda.empty_cache()
