@@ -344,6 +344,7 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 template <bool FRAMED>
 __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const PackedOut &po, uint64_t task, uint64_t base, uint32_t lane, CopyRing &R) {
     const uint32_t PB = R.piece_bytes, SB = PB + kCopyOverlapBytes, PC = PB >> 4;
+    const uint32_t pb_log2 = 31u - (uint32_t)__clz(PB), pc_log2 = pb_log2 - 4;  // PB is a power of two: no divisions in the loops
     {
         // lane l describes stream l (the block's record and where its source bytes lie) in the warp's table
         const uint64_t b = task * 32 + lane;
@@ -377,7 +378,7 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
             uint32_t re = (a + g.n_chunks + 3) * 16;
             if (re > (uint32_t)io.out_stride + 16) re = (uint32_t)io.out_stride + 16;
             rlen = re - rs;
-            np = g.n_chunks ? (g.n_chunks + PC - 1) / PC : 1u;
+            np = g.n_chunks ? (g.n_chunks + PC - 1) >> pc_log2 : 1u;
         }
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(R.tab + 16 * lane), "r"(bits), "r"(np), "r"(rs), "r"(rlen) : "memory");
         __syncwarp();
@@ -442,7 +443,7 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
         const uint32_t off = (uint32_t)(io.out_stride * 8) - bits_l;
         const uint32_t g0 = (off - g.lead) >> 7, S0 = off + 8 * g.head - g.lead, offr = off - 128 * g0;
         const uint32_t lofs = 16 * (lane + (S0 >> 7) - g0), sh = S0 & 31u;
-        const uint32_t last_piece = g.n_chunks ? (g.n_chunks - 1) / PC : 0u;
+        const uint32_t last_piece = g.n_chunks ? (g.n_chunks - 1) >> pc_log2 : 0u;
         if (po.trace) {
             const uint32_t c0 = (uint32_t)clock64();
             mbar_wait_s(R.bar, R.par);
@@ -462,13 +463,13 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
             const uint32_t i = g.tail0 + lane;
             if (i < g.payload_bytes) {
                 const int32_t pos = (int32_t)(8 * i) - (int32_t)g.lead;
-                t_S = (uint32_t)((int32_t)offr + pos) - 8 * PB * last_piece;
+                t_S = (uint32_t)((int32_t)offr + pos) - (last_piece << (pb_log2 + 3));
                 uint32_t keep = 0xFFu;
                 if (pos < 0) keep = pos <= -8 ? 0u : (0xFFu >> (uint32_t)(-pos));
                 const int32_t r = (int32_t)bits_l - pos;
                 if (r < 8) keep &= r <= 0 ? 0u : ~(0xFFu >> (uint32_t)r);
                 t_ko = keep | ((FRAMED && i == 0) ? (g.num_pad << 13) : 0u);
-                t_ofs = (int32_t)i - (int32_t)(g.head + 16 * lane + PB * last_piece);
+                t_ofs = (int32_t)i - (int32_t)(g.head + 16 * lane + (last_piece << pb_log2));
             }
         }
         uint8_t *dp = d + g.head + 16 * lane;
