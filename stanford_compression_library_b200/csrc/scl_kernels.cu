@@ -281,15 +281,17 @@ __device__ __forceinline__ void packed_copy_task(const BlockIo &io, const Packed
     // one shuffle per stream (its bit count) is all the lanes exchange.  The NEXT stream is requested into L2 while
     // this one is copied (one line per lane, no registers held): the slots were written ~400 MB of traffic ago.
     const uint64_t stride_bits = io.out_stride * 8;
+    const uint8_t *const src = io.out;  // (registers, not the caller's frame: see packed_copy_task_ring)
+    uint8_t *const dst = po.dst;
     uint64_t slot_end = (io.block0 + task * 32 + 1) * stride_bits, at = base;
     uint32_t bits_l = __shfl_sync(0xffffffffu, bits, 0), nb_l = __shfl_sync(0xffffffffu, nb, 0);
     for (uint32_t l = 0; l < 32; ++l) {
         const uint32_t bits_n = __shfl_sync(0xffffffffu, bits, (l + 1) & 31), nb_n = __shfl_sync(0xffffffffu, nb, (l + 1) & 31);
         if (l + 1 < 32 && bits_n) {
-            const uint8_t *p0 = io.out + (((slot_end + stride_bits - bits_n) >> 3) & ~127ull);
+            const uint8_t *p0 = src + (((slot_end + stride_bits - bits_n) >> 3) & ~127ull);
             for (uint32_t o = lane * 128; o < (bits_n >> 3) + 160; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         }
-        if (bits_l) pack_block_warp_a16<FRAMED>(io.out, slot_end - bits_l, bits_l, po.dst + at, lane);
+        if (bits_l) pack_block_warp_a16<FRAMED>(src, slot_end - bits_l, bits_l, dst + at, lane);
         at += nb_l;
         slot_end += stride_bits;
         bits_l = bits_n;
@@ -343,6 +345,11 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 
 template <bool FRAMED>
 __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const PackedOut &po, uint64_t task, uint64_t base, uint32_t lane, CopyRing &R) {
+    // (io / po live in the caller's frame and every shared-memory / mbarrier asm here is a memory barrier to the compiler:
+    // what the loops need is copied to registers once, or it is re-loaded from local memory after every such statement)
+    const uint64_t out_stride = io.out_stride;
+    uint8_t *const dst = po.dst;
+    const bool tracing = po.trace != nullptr;
     const uint32_t PB = R.piece_bytes, SB = PB + kCopyOverlapBytes, PC = PB >> 4;
     const uint32_t pb_log2 = 31u - (uint32_t)__clz(PB), pc_log2 = pb_log2 - 4;  // PB is a power of two: no divisions in the loops
     {
@@ -371,12 +378,12 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
         }
         uint32_t np = 0, rs = 0, rlen = 0;
         if (bits && !(bits >> 31)) {
-            const StreamGeo g = stream_geo<FRAMED>(bits, (uint32_t)(uintptr_t)(po.dst + at_mine + (FRAMED ? 4 : 0)) & 15u);
-            const uint32_t off = (uint32_t)(io.out_stride * 8) - bits;
+            const StreamGeo g = stream_geo<FRAMED>(bits, (uint32_t)(uintptr_t)(dst + at_mine + (FRAMED ? 4 : 0)) & 15u);
+            const uint32_t off = (uint32_t)(out_stride * 8) - bits;
             const uint32_t a = (off + 8 * g.head - g.lead) >> 7;
             rs = ((off - g.lead) >> 7) * 16;
             uint32_t re = (a + g.n_chunks + 3) * 16;
-            if (re > (uint32_t)io.out_stride + 16) re = (uint32_t)io.out_stride + 16;
+            if (re > (uint32_t)out_stride + 16) re = (uint32_t)out_stride + 16;
             rlen = re - rs;
             np = g.n_chunks ? (g.n_chunks + PC - 1) >> pc_log2 : 1u;
         }
@@ -386,7 +393,7 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
     // producer cursor (warp-uniform): stream pl, p_np pieces of it still to request, the next one at p_src, p_left bytes to
     // the region's end.  A piece always goes into the stage the consumer has just emptied (or, before the first piece is
     // consumed, into the stages in order), so the producer keeps no stage of its own.
-    const uint8_t *task_src = io.out + (io.block0 + task * 32) * io.out_stride;
+    const uint8_t *task_src = io.out + (io.block0 + task * 32) * out_stride;
     uint32_t pl = 0xFFFFFFFFu, p_np = 0, p_left = 0;
     const uint8_t *p_src = task_src;
     auto next_stream = [&]() {
@@ -394,7 +401,7 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
             ++pl;
             const uint4 e = lds_plain128(R.tab + 16 * pl);
             p_np = e.y;
-            p_src = task_src + (uint64_t)pl * io.out_stride + e.z;
+            p_src = task_src + (uint64_t)pl * out_stride + e.z;
             p_left = e.w;
         }
     };
@@ -433,18 +440,18 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
             continue;
         }
         if (bits_l == 0) continue;
-        uint8_t *d = po.dst + at;
+        uint8_t *d = dst + at;
         at += (uint32_t)packed_size(bits_l, FRAMED);
         const StreamGeo g = stream_geo<FRAMED>(bits_l, (uint32_t)(uintptr_t)(d + (FRAMED ? 4 : 0)) & 15u);
         if (FRAMED) {
             if (lane < 4) d[lane] = (uint8_t)(g.payload_bytes >> (8 * (3 - lane)));
             d += 4;
         }
-        const uint32_t off = (uint32_t)(io.out_stride * 8) - bits_l;
+        const uint32_t off = (uint32_t)(out_stride * 8) - bits_l;
         const uint32_t g0 = (off - g.lead) >> 7, S0 = off + 8 * g.head - g.lead, offr = off - 128 * g0;
         const uint32_t lofs = 16 * (lane + (S0 >> 7) - g0), sh = S0 & 31u;
         const uint32_t last_piece = g.n_chunks ? (g.n_chunks - 1) >> pc_log2 : 0u;
-        if (po.trace) {
+        if (tracing) {
             const uint32_t c0 = (uint32_t)clock64();
             mbar_wait_s(R.bar, R.par);
             R.wait_cycles += (uint32_t)clock64() - c0;
@@ -515,7 +522,7 @@ __device__ __forceinline__ void packed_copy_task_ring(const BlockIo &io, const P
                 if (last) break;
                 rem -= PC;
                 dp += PB;
-                if (po.trace) {
+                if (tracing) {
                     const uint32_t c0 = (uint32_t)clock64();
                     mbar_wait_s(R.bar, R.par);
                     R.wait_cycles += (uint32_t)clock64() - c0;
