@@ -575,7 +575,7 @@ __device__ __noinline__ uint32_t packed_copy_one(PackCtl &ctl, const BlockIo &io
     if (lane == 0) {
         if (tr) t0 = globaltimer_ns();
         const volatile uint32_t *res = &ctl.resolved;
-        while (*res <= r) __nanosleep(200);
+        for (uint32_t ns = 100; *res <= r; ns = ns < 1600 ? 2 * ns : 1600) __nanosleep(ns);  // (a poll costs issue slots the coder wants)
         if (tr) t1 = globaltimer_ns();
     }
     __syncwarp();
@@ -1996,10 +1996,13 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
         po.copy_warps = copy_warps;
         // staging rings for the copy warps out of whatever shared memory the coder leaves (227 KiB - 1 KiB static)
         const size_t free_smem = 226 * 1024 > smem + 16 ? 226 * 1024 - smem - 16 : 0;
-        // the largest pieces (fewest instructions per byte) of which at least two fit, else no ring
+        // the largest pieces (fewest instructions per byte) of which at least two fit; 512-byte pieces cost more
+        // instructions than they save latency (profiles/r3i_sweep.jsonl: 1.128 vs 1.103 ms per GiB without a ring), so
+        // a coder that leaves less than ~9 KB free (tANS with its 16 KB encode table) copies through registers
         const size_t per_warp = free_smem / copy_warps > 528 ? free_smem / copy_warps - 528 : 0;  // minus the stream table and padding
         uint32_t stages = 0;
-        for (uint32_t pb = (c->debug_mode & 64) ? 512u : (c->debug_mode & 128) ? 1024u : 2048u; pb >= 512; pb >>= 1) {
+        const uint32_t pb_min = (c->debug_mode & 64) ? 512u : 1024u;
+        for (uint32_t pb = (c->debug_mode & 64) ? 512u : (c->debug_mode & 128) ? 1024u : 2048u; pb >= pb_min; pb >>= 1) {
             po.copy_piece_bytes = pb;
             stages = (uint32_t)(per_warp / (pb + kCopyOverlapBytes + 8));
             if (stages >= 2) break;
