@@ -818,9 +818,21 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             }
         }
     }
-    if (PACKED)  // a coding warp that is out of symbols joins the pool (through registers: it has no staging ring)
-        while (packed_copy_one<false>(ctl, io, po, W, total_warps, n_tasks, lane, true, nullptr)) {
+    if (PACKED) {  // a coding warp that is out of symbols joins the pool
+        if (po.copy_stages) {
+            // its tile buffers are idle from here on (every tile load it issued has been waited for): 4 KiB = a ring of three
+            // 1 KiB stages, its mbarriers and the stream table
+            static_assert(copy_ring_bytes(3, 1024) <= kTileStages * kTileBytes, "the tile buffers hold a 3 x 1 KiB staging ring");
+            __syncwarp();
+            CopyRing Rw = copy_ring_at(tiles, 3, 1024, lane == 0);
+            __syncwarp();
+            while (packed_copy_one<true>(ctl, io, po, W, total_warps, n_tasks, lane, true, &Rw)) {
+            }
+        } else {
+            while (packed_copy_one<false>(ctl, io, po, W, total_warps, n_tasks, lane, true, nullptr)) {
+            }
         }
+    }
 }
 
 // Decode.  Output goes through a per-warp 32 x 64-byte tile in shared memory (64-byte swizzle, so
