@@ -235,7 +235,8 @@ struct PackedOut {
     uint64_t g_base;         // look-back index of this launch's (round 0, CTA 0): a split batch continues the numbering
     uint32_t copy_warps;     // dedicated copy warps of the CTA (kCopyWarps)
     uint32_t copy_stages;    // stages of each copy warp's staging ring (from the shared memory the coder leaves free); 0 = copy through registers
-    uint32_t copy_piece_bytes;  // 512 or 1024: stream bytes per stage
+    uint32_t copy_piece_bytes;  // 512, 1024 or 2048: stream bytes per stage
+    uint32_t helper_ring;    // 1 = a coding warp that has run out of tasks copies through a ring in its idle tile buffers
     uint64_t *trace;         // scl_coder_debug_trace: NULL, or [gridDim.x][32 warps][kTraceWords] timestamps (tools/trace_packed.py)
 };
 constexpr uint32_t kTraceWords = 40;  // per warp: [0] start, [1 + r] end of coding round r (r < 19), [20] tasks copied, [21] first copy
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
         }
     }
     if (PACKED) {  // a coding warp that is out of symbols joins the pool
-        if (po.copy_stages) {
+        if (po.helper_ring) {
             // its tile buffers are idle from here on (every tile load it issued has been waited for): 4 KiB = a ring of three
             // 1 KiB stages, its mbarriers and the stream table
             static_assert(copy_ring_bytes(3, 1024) <= kTileStages * kTileBytes, "the tile buffers hold a 3 x 1 KiB staging ring");
@@ -2021,6 +2022,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
         }
         if (stages > 8) stages = 8;
         po.copy_stages = (stages < 2 || (c->debug_mode & 32)) ? 0u : stages;
+        po.helper_ring = (c->debug_mode & 32) ? 0u : 1u;
         smem += 16 + (size_t)copy_warps * copy_ring_bytes(po.copy_stages, po.copy_piece_bytes);
         po.trace = c->d_trace && c->trace_words >= (uint64_t)grid * 32 * kTraceWords ? c->d_trace : nullptr;
         // one look-back word per (round, CTA) of the WHOLE batch: the launches of a split batch are whole rounds, so the
@@ -2303,7 +2305,7 @@ extern "C" int scl_encode_blocks_packed(const scl_coder *c, const uint8_t *d_sym
         SCL_CUDA(cudaMemsetAsync(d_byte_offset, 0, sizeof(uint64_t), s));
         return SCL_E_OK;
     }
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, 0, 0, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, (uint64_t *)d_workspace, framed ? 1u : 0u, 0, kCopyWarps, 0, 0, 0, nullptr};
     bool fused = false;
     int rc = encode_blocks_impl(c, d_sym, sym_stride, d_sizes, block_len, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_model,
                                 d_status, &po, &fused, stream);
@@ -2323,7 +2325,7 @@ extern "C" int scl_debug_copy_only(const scl_coder *c, uint64_t n_blocks, uint8_
     BlockIo io{nullptr, 0, nullptr, 0, n_blocks, d_scratch, scratch_stride, d_bit_offset, d_bit_len, d_status, 0};
     const uint32_t piece_bytes = (ring_stages & 0x200) ? 2048u : (ring_stages & 0x100) ? 1024u : 512u;  // bits 8, 9 of ring_stages: 64- / 128-chunk pieces
     ring_stages &= 0xFF;
-    PackedOut po{d_dst, dst_bytes, d_byte_offset, nullptr, framed ? 1u : 0u, 0, kCopyWarps, ring_stages, piece_bytes, nullptr};
+    PackedOut po{d_dst, dst_bytes, d_byte_offset, nullptr, framed ? 1u : 0u, 0, kCopyWarps, ring_stages, piece_bytes, 0, nullptr};
     const size_t smem = (size_t)warps_per_cta * copy_ring_bytes(ring_stages, piece_bytes);
     if (ring_stages == 1 || smem > 200 * 1024) return SCL_E_INVALID;
     SCL_CUDA(cudaFuncSetAttribute(copy_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
