@@ -556,15 +556,12 @@ SCL_HD uint32_t aec_e12_count(uint64_t low, uint64_t high, uint32_t P) {
     const uint32_t sh = 32 - P;
     uint32_t x = (lo ^ hm) << sh;  // P-bit view aligned to bit 31
     uint32_t n = x ? clz32(x) : P;
-    const uint32_t full = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u);
-    if (hm != full) {
-        uint32_t jA = P - 1 - ctz32(~hm);  // ctz(~hm) = number of trailing ones
-        n = jA < n ? jA : n;
-    }
-    if (lo != 0) {
-        uint32_t jB = P - 1 - ctz32(lo);
-        n = jB < n ? jB : n;
-    }
+    // branch-free: hm all ones (P of them) gives ctz32(~hm) >= P, lo == 0 gives ctz32 = 32 -- both candidates then wrap to
+    // values far above P and lose the minimum, exactly as if they had been skipped
+    const uint32_t jA = P - 1 - ctz32(~hm);  // ctz(~hm) = number of trailing ones
+    const uint32_t jB = P - 1 - ctz32(lo);
+    n = jA < n ? jA : n;
+    n = jB < n ? jB : n;
     return n;
 }
 // E3 loop (:146-150): every iteration deletes bit P-2 of low and hm (keeping the top bits).  It runs
@@ -574,22 +571,18 @@ SCL_HD uint32_t aec_e12_count(uint64_t low, uint64_t high, uint32_t P) {
 SCL_HD uint32_t aec_e3_count(uint64_t low, uint64_t high, uint32_t P) {
     const uint32_t lo = (uint32_t)low, hm = (uint32_t)(high - 1);
     const uint32_t top = 1u << (P - 1);
-    uint32_t m = 0xFFFFFFFFu;
     const uint32_t sh = 33 - P;  // drops the top bit, aligns bit P-2 to bit 31 (P >= 2; sh == 32 handled for P == 1 never)
-    if (!(lo & top)) {
-        uint32_t body = sh >= 32 ? 0u : (lo << sh);
-        uint32_t r1 = clz32(~body);  // leading ones
-        r1 = r1 > P - 1 ? P - 1 : r1;
-        if (r1 > 0 && ctz32(lo) == P - 1 - r1) r1 -= 1;
-        m = r1;
-    }
-    if (hm & top) {
-        uint32_t body = sh >= 32 ? 0u : (hm << sh);
-        uint32_t r0 = clz32(body);  // leading zeros
-        r0 = r0 > P - 1 ? P - 1 : r0;
-        if (r0 > 0 && ctz32(~hm) == P - 1 - r0) r0 -= 1;
-        m = r0 < m ? r0 : m;
-    }
+    // both candidates are always worked out (straight-line code), the conditions only select
+    const uint32_t body1 = sh >= 32 ? 0u : (lo << sh);
+    uint32_t r1 = clz32(~body1);  // leading ones
+    r1 = r1 > P - 1 ? P - 1 : r1;
+    r1 -= (r1 > 0 && ctz32(lo) == P - 1 - r1) ? 1u : 0u;
+    const uint32_t body0 = sh >= 32 ? 0u : (hm << sh);
+    uint32_t r0 = clz32(body0);  // leading zeros
+    r0 = r0 > P - 1 ? P - 1 : r0;
+    r0 -= (r0 > 0 && ctz32(~hm) == P - 1 - r0) ? 1u : 0u;
+    const uint32_t m1 = (lo & top) ? 0xFFFFFFFFu : r1, m0 = (hm & top) ? r0 : 0xFFFFFFFFu;
+    const uint32_t m = m0 < m1 ? m0 : m1;
     return m == 0xFFFFFFFFu ? 0u : m;
 }
 // n E1/E2 steps: v -> 2^n v - prefix * 2^P  (prefix = top n bits of low); exact in 64-bit integers
@@ -655,12 +648,13 @@ SCL_HD uint32_t aec_target(uint32_t state, uint32_t low, uint32_t hm, uint32_t t
 }
 
 // ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
-template <class Policy>
+// PFIX = 0: PRECISION from c.P; PFIX = 32: the reference's default as a compile-time constant (masks and shift amounts fold)
+template <class Policy, uint32_t PFIX = 0>
 SCL_HD uint32_t aec2_encode_lane(Policy &M, const AecTab &tab, const AecConst &c, const uint8_t *sym, uint64_t sym_cap, uint32_t n,
                                  FwdBitWriter &w, uint64_t &bits_out) {
     SymWindow sw;
     sw.init(sym, sym_cap);
-    const uint32_t P = c.P;
+    const uint32_t P = PFIX ? PFIX : c.P;
     const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
     uint32_t low = 0, hm = pm, num_mid = 0;  // high = FULL
     uint32_t st = SCL_ST_OK;
@@ -734,10 +728,10 @@ SCL_HD uint32_t aec_get_bits(BitReader &r, uint64_t &nbc, uint64_t A, uint32_t k
 }
 
 // ArithmeticDecoder.decode_block (arithmetic_coding.py:203-287)
-template <class Policy>
+template <class Policy, uint32_t PFIX = 0>
 SCL_HD uint32_t aec2_decode_lane(Policy &M, const AecTab &tab, const AecConst &c, BitReader &r, uint64_t avail_bits, uint8_t *out,
                                  uint64_t out_cap, uint32_t &size_out, uint64_t &bits_consumed) {
-    const uint32_t P = c.P;
+    const uint32_t P = PFIX ? PFIX : c.P;
     const uint32_t pm = P == 32 ? 0xFFFFFFFFu : ((1u << P) - 1u), HALF = 1u << (P - 1), QTR = 1u << (P - 2);
     uint64_t size64 = r.get64(c.DBSB);
     size_out = 0;

@@ -1325,7 +1325,8 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_encode_kernel(const AecT
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    uint32_t st = c.P == 32 ? aec2_encode_lane<decltype(pol), 32>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits)
+                            : aec2_encode_lane<decltype(pol), 0>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
     io.status[b] = st;
@@ -1344,7 +1345,8 @@ __global__ void __launch_bounds__(kAec2Warps * 32) aec2_decode_kernel(const AecT
     uint64_t off = io.bit_off[b];
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
-    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    uint32_t st = c.P == 32 ? aec2_decode_lane<decltype(pol), 32>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used)
+                            : aec2_decode_lane<decltype(pol), 0>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
@@ -1391,7 +1393,8 @@ __global__ void __launch_bounds__(kAec8MaxWarps * 32) aec8_encode_kernel(const A
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    uint32_t st = c.P == 32 ? aec2_encode_lane<decltype(pol), 32>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits)
+                            : aec2_encode_lane<decltype(pol), 0>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
     io.status[b] = st;
@@ -1409,7 +1412,8 @@ __global__ void __launch_bounds__(kAec8MaxWarps * 32) aec8_decode_kernel(const A
     uint64_t off = io.bit_off[b];
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
-    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    uint32_t st = c.P == 32 ? aec2_decode_lane<decltype(pol), 32>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used)
+                            : aec2_decode_lane<decltype(pol), 0>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
     io.sizes[b] = size;
     io.consumed[b] = used;
     io.status[b] = st;
@@ -1454,7 +1458,8 @@ __global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_encode_kernel(co
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    uint32_t st = c.P == 32 ? aec2_encode_lane<decltype(pol), 32>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits)
+                            : aec2_encode_lane<decltype(pol), 0>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     if (my_model) pol.store(my_model);
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
@@ -1476,7 +1481,8 @@ __global__ void __launch_bounds__(kAecCtxMaxWarps * 32) aec_ctx_decode_kernel(co
     uint64_t off = io.bit_off[b];
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
-    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    uint32_t st = c.P == 32 ? aec2_decode_lane<decltype(pol), 32>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used)
+                            : aec2_decode_lane<decltype(pol), 0>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
     if (my_model) pol.store(my_model);
     io.sizes[b] = size;
     io.consumed[b] = used;
@@ -1513,7 +1519,8 @@ __global__ void __launch_bounds__(kAecCtxGlobalWarps * 32) aec_ctx_global_encode
     FwdBitWriter w;
     uint8_t *slot = io.out + b * io.out_stride;
     w.init(slot, slot + io.out_stride);
-    uint32_t st = aec2_encode_lane(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
+    uint32_t st = c.P == 32 ? aec2_encode_lane<decltype(pol), 32>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits)
+                            : aec2_encode_lane<decltype(pol), 0>(pol, s_tab, c, io.sym + b * io.sym_stride, io.sym_stride, n, w, bits);
     pol.store();
     io.bit_len[b] = bits;
     io.bit_off[b] = b * io.out_stride * 8;
@@ -1534,7 +1541,8 @@ __global__ void __launch_bounds__(kAecCtxGlobalWarps * 32) aec_ctx_global_decode
     uint64_t off = io.bit_off[b];
     r.init(io.in, io.in_bytes, off);
     uint32_t size = 0;
-    uint32_t st = aec2_decode_lane(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
+    uint32_t st = c.P == 32 ? aec2_decode_lane<decltype(pol), 32>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used)
+                            : aec2_decode_lane<decltype(pol), 0>(pol, s_tab, c, r, avail_bits_of(io, b, off), io.sym + b * io.sym_stride, io.sym_stride, size, used);
     pol.store();
     io.sizes[b] = size;
     io.consumed[b] = used;
