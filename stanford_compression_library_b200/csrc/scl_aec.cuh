@@ -676,27 +676,29 @@ SCL_HD uint32_t aec2_encode_lane(Policy &M, const AecTab &tab, const AecConst &c
         aec_shrink(low, hm, cc, f, total);
         st = M.update(idx);  // update_model (:118)
         if (st != SCL_ST_OK) break;
-        const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
-        if (ne) {
-            const uint32_t prefix = low >> (P - ne);
+        // Renormalisation without branches on the counts: in a warp some lane almost always has bits to release, so a
+        // branch would run both sides anyway.  With ne == 0 (me == 0) every step below is an identity and zero bits go out.
+        const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);  // <= P - 1
+        {
+            const uint32_t prefix = (low >> 1) >> (P - 1 - ne);  // low >> (P - ne); 0 for ne == 0
             aec_shift_e12(low, hm, ne, pm);
             // released bits: first prefix bit, then num_mid copies of its complement, then the rest
-            const uint32_t b0 = (prefix >> (ne - 1)) & 1u;
-            if (num_mid + ne <= 32) {
-                const uint32_t run = b0 ? 0u : mask32(num_mid);
-                w.put((b0 << (num_mid + ne - 1)) | (run << (ne - 1)) | (prefix & mask32(ne - 1)), num_mid + ne);
-            } else {
+            const uint32_t nem1 = (ne - 1) & 31u;
+            const uint32_t b0 = ne ? (prefix >> nem1) & 1u : 0u;
+            const uint32_t tot = ne ? num_mid + ne : 0u;
+            if (SCL_UNLIKELY(tot > 32)) {
                 w.put(b0, 1);
                 w.put_run(b0 ^ 1u, num_mid);
                 if (ne > 1) w.put(prefix & mask32(ne - 1), ne - 1);
+            } else {
+                const uint32_t run = b0 ? 0u : mask32(ne ? num_mid : 0u);
+                w.put(ne ? ((b0 << ((tot - 1) & 31u)) | (run << nem1) | (prefix & mask32(nem1))) : 0u, tot);
             }
-            num_mid = 0;
+            num_mid = ne ? 0u : num_mid;
         }
         const uint32_t me = aec_e3_count(low, (uint64_t)hm + 1, P);
-        if (me) {
-            num_mid += me;
-            aec_shift_e3(low, hm, me, HALF, pm);
-        }
+        num_mid += me;
+        aec_shift_e3(low, hm, me, HALF, pm);
         if (w.ovf) break;
     }
     num_mid += 1;  // :153-159
@@ -767,16 +769,13 @@ SCL_HD uint32_t aec2_decode_lane(Policy &M, const AecTab &tab, const AecConst &c
         st = M.update(idx);
         if (st != SCL_ST_OK) break;
         if (i == size) break;  // :242-243
+        // (no branches on the counts: with ne == 0 / me == 0 the steps are identities and no bits are read -- see the encoder)
         const uint32_t ne = aec_e12_count(low, (uint64_t)hm + 1, P);
-        if (ne) {
-            aec_shift_e12(low, hm, ne, pm);
-            state = ((state << ne) & pm) | aec_get_bits(r, nbc, A, ne);  // the dropped top bits are the common prefix (:252-256)
-        }
+        aec_shift_e12(low, hm, ne, pm);
+        state = ((state << ne) & pm) | aec_get_bits(r, nbc, A, ne);  // the dropped top bits are the common prefix (:252-256)
         const uint32_t me = aec_e3_count(low, (uint64_t)hm + 1, P);
-        if (me) {
-            aec_shift_e3(low, hm, me, HALF, pm);
-            state = ((((state - HALF) << me) + HALF) & pm) + aec_get_bits(r, nbc, A, me);
-        }
+        aec_shift_e3(low, hm, me, HALF, pm);
+        state = ((((state - HALF) << me) + HALF) & pm) + aec_get_bits(r, nbc, A, me);
     }
     ow.flush(st == SCL_ST_OK ? size : 0);
     const uint64_t low64 = low, high64 = (uint64_t)hm + 1, state64 = state;
