@@ -309,7 +309,7 @@ struct CopyRing {          // identical in every lane of the warp
     uint32_t buf;          // shared address of stage 0; stage i at buf + i * (piece_bytes + kCopyOverlapBytes)
     uint32_t bars;         // shared address of mbarrier 0 (right behind the stages); mbarrier i at bars + 8 i
     uint32_t tab;          // shared address of the per-task stream table: 32 x {bits, pieces, region start, region bytes}
-    uint32_t piece_bytes;  // 512 or 1024: 32 or 64 chunks per piece; 0 = this warp has no ring (copies through registers)
+    uint32_t piece_bytes;  // 512, 1024 or 2048: 32, 64 or 128 chunks per piece; 0 = this warp has no ring (copies through registers)
     uint32_t stage, bar;   // where the next piece lands / its mbarrier (shared addresses)
     uint32_t par;          // that mbarrier's phase parity
     uint32_t wait_cycles;  // tracing only: clock cycles spent waiting for pieces to land
