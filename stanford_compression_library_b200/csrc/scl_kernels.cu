@@ -650,7 +650,9 @@ __global__ void __launch_bounds__(1024, 1) copy_only_kernel(BlockIo io, PackedOu
     }
 }
 
-template <int KIND, uint32_t NBO, bool CHECK, bool PACKED>
+// RAGGED: the blocks have their own sizes (io.sizes; io.block_len = the row capacity): a warp runs as many tiles as its
+// longest block needs and every lane stops at its own end.
+template <int KIND, uint32_t NBO, bool CHECK, bool PACKED, bool RAGGED>
 __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     fast_encode_v2_kernel(const __grid_constant__ CUtensorMap tmap, const void *__restrict__ g_tab8, const uint32_t *__restrict__ g_tab2,
                           uint32_t tab2_bytes, RansConst c, BlockIo io, uint32_t n_tasks, PackedOut po) {
@@ -691,8 +693,8 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     // this lane's bank-rotated replica: 8 x 16-byte entries (rANS, LDS.128: a quarter warp per wavefront) or 16 x 8-byte rows
     // (tANS, LDS.64: half a warp per wavefront) -- 128 bytes per byte value either way
     const saddr_t my_tab = saddr_of(s_tab) + (KIND == 0 ? (lane & (kEncTabCopies - 1)) * 16 : (lane & (kTansTabCopies - 1)) * 8);
-    const uint32_t n = io.block_len;
-    const uint32_t n_tiles = (n + kTileCols - 1) / kTileCols;
+    const uint32_t n_uniform = io.block_len;
+    const uint32_t n_tiles_uniform = (n_uniform + kTileCols - 1) / kTileCols;
     const uint32_t total_warps = gridDim.x * W;
     uint32_t tile_seq = 0;  // tiles consumed by this warp so far (selects stage and mbarrier parity)
     const uint32_t swz = (lane >> 1) & 3;
@@ -713,6 +715,11 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
     for (uint32_t task = blockIdx.x * W + warp; task < n_tasks; task += total_warps, ++round) {
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
+        uint32_t n = n_uniform, n_tiles = n_tiles_uniform;  // RAGGED: n is this lane's, n_tiles the warp's
+        if (RAGGED) {
+            n = active ? io.sizes[b] : 0u;
+            n_tiles = (__reduce_max_sync(0xffffffffu, n) + kTileCols - 1) / kTileCols;
+        }
         if (lane == 0) {
             for (uint32_t t = 0; t < kTileStages && t < n_tiles; ++t) {
                 uint32_t st = (tile_seq + t) % kTileStages;
@@ -727,8 +734,8 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             const uint32_t st = tile_seq % kTileStages;
             mbar_wait(my_bar + st, (tile_seq / kTileStages) & 1);
             const uint8_t *row = tiles + st * kTileBytes + lane * kTileCols;
-            const uint32_t left = n - t * kTileCols;
-            if (left >= kTileCols) {
+            const uint32_t left = RAGGED ? (n > t * kTileCols ? n - t * kTileCols : 0u) : n - t * kTileCols;
+            if (RAGGED ? __all_sync(0xffffffffu, !active || left >= kTileCols) : left >= kTileCols) {
                 // full tile: four whole chunks, no per-chunk bookkeeping
                 if (active) {
 #pragma unroll 1
@@ -2043,6 +2050,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
         const uint64_t b0 = t0 * 32;
         BlockIo cio = io;
         cio.sym = io.sym + b0 * io.sym_stride;
+        cio.sizes = io.sizes ? io.sizes + b0 : nullptr;
         cio.n_blocks = io.n_blocks - b0 < chunk_tasks * 32 ? io.n_blocks - b0 : chunk_tasks * 32;
         cio.bit_off = io.bit_off + b0;
         cio.bit_len = io.bit_len + b0;
@@ -2062,11 +2070,18 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
             po.g_base = (t0 / per_round) * grid;
         }
         cudaError_t e;
-#define SCL_LAUNCH_ENC(CHK, PK)                                                                                                    \
-    do {                                                                                                                           \
-        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                          \
-        fast_encode_v2_kernel<KIND, NBO, CHK, PK><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, cio, n_tasks, po); \
+#define SCL_LAUNCH_ENC2(CHK, PK, RG)                                                                                                   \
+    do {                                                                                                                               \
+        e = cudaFuncSetAttribute(fast_encode_v2_kernel<KIND, NBO, CHK, PK, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");                                                              \
+        fast_encode_v2_kernel<KIND, NBO, CHK, PK, RG><<<grid, (warps + copy_warps) * 32, smem, s>>>(tmap, tab8, tab2, tab2_bytes, rc, cio, n_tasks, po); \
+    } while (0)
+#define SCL_LAUNCH_ENC(CHK, PK)              \
+    do {                                     \
+        if (cio.sizes)                       \
+            SCL_LAUNCH_ENC2(CHK, PK, true);  \
+        else                                 \
+            SCL_LAUNCH_ENC2(CHK, PK, false); \
     } while (0)
         if (rc.check_sym) {
             if (packed)
@@ -2080,6 +2095,7 @@ static int launch_encode_v2(const scl_coder *c, const RansConst &rc, const void 
                 SCL_LAUNCH_ENC(false, false);
         }
 #undef SCL_LAUNCH_ENC
+#undef SCL_LAUNCH_ENC2
         int rc2 = check_launch("fast_encode_v2_kernel");
         if (rc2) return rc2;
     }
@@ -2175,7 +2191,7 @@ static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t
     if (c->rans) {
         const RansHost &r = *c->rans;
         // second-generation kernel: uniform block length, TMA-compatible input, sector-aligned output
-        if (r.enc32 && c->v2_ok && !force_v1(c) && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 &&
+        if (r.enc32 && c->v2_ok && !force_v1(c) && block_len >= kTileCols && (sym_stride % 16) == 0 &&
             (((uintptr_t)d_sym) & 15) == 0 && (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
             (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
             int rc2 = r.c.NBO == 1 ? launch_encode_v2<0, 1>(c, r.c, c->d_enc32x8, nullptr, 0, io, packed, s)
@@ -2197,7 +2213,7 @@ static int encode_blocks_impl(const scl_coder *c, const uint8_t *d_sym, uint64_t
     }
     if (c->tans) {
         const TansHost &t = *c->tans;
-        if (c->v2_ok && !force_v1(c) && !d_sizes && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
+        if (c->v2_ok && !force_v1(c) && block_len >= kTileCols && (sym_stride % 16) == 0 && (((uintptr_t)d_sym) & 15) == 0 &&
             (out_stride % 32) == 0 && (((uintptr_t)d_out) & 31) == 0 && n_blocks < (1ull << 36) &&
             (uint64_t)block_len * kFastMaxBitsPerSym < (1ull << 31)) {
             int rc2 = launch_encode_v2<1, 1>(c, t.r.c, c->d_tsymx8, c->d_tenc, c->ttab_bytes, io, packed, s);

@@ -390,3 +390,54 @@ def test_rans_cfg5_whole_stream_on_one_gpu_packed_vs_oracle():
         assert p.buf[offs[b] : offs[b + 1]].cpu().numpy().tobytes() == ref_bytes.tobytes(), "block %d differs from the oracle" % b
     del p, data
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name", ["rans_default", "rans_nbo8", "tans"])
+def test_ragged_batches_take_the_fast_encoder_and_match_the_oracle(name):
+    """Blocks of different sizes in one batch (`sizes`): the second-generation encoder runs as many tiles per warp as the
+    warp's longest block needs and every lane stops at its own end.  Sizes 0, 1, 63, 64, 65, a full row and random ones in
+    between; slot output, fused packed and fused framed output are compared with the first-generation kernels on every
+    block (bytes and bit lengths) and with the oracle on a sample; the decoder returns every block at its own size."""
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_freq_list, zipf_probabilities
+
+    enc, dec = _codec(name)
+    B, N = 148 * 28 * 32 + 1000, 448
+    data = sample_blocks(zipf_probabilities(), B, N, seed=33, device="cuda:0")
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(5)
+    sizes = torch.randint(0, N + 1, (B,), generator=g, device="cuda:0", dtype=torch.int32)
+    sizes[:6] = torch.tensor([0, 1, 63, 64, 65, N], dtype=torch.int32, device="cuda:0")
+    sizes[-1] = 0
+    sizes[5000:5032] = N  # one warp of full rows (the full-tile path) among ragged ones
+    e = enc.encode_blocks(data, sizes=sizes).check()
+    try:
+        enc.device_coder().debug_path(1)  # first-generation kernels
+        e1 = enc.encode_blocks(data, sizes=sizes).check()
+    finally:
+        enc.device_coder().debug_path(0)
+    assert torch.equal(e.bit_len, e1.bit_len)
+    want = e1.pack()
+    got = e.pack()
+    total = e1.total_bytes()
+    assert torch.equal(got.buf[:total], want.buf[:total]) and torch.equal(got.byte_offset, want.byte_offset)
+    for framed in (False, True):
+        p = enc.encode_blocks_packed(data, sizes=sizes, framed=framed).check()
+        assert torch.equal(p.bit_len, e1.bit_len)
+        if framed:
+            fw, foffs = e1.frame()
+            assert torch.equal(p.byte_offset, foffs) and torch.equal(p.buf[: fw.numel()], fw)
+        else:
+            assert torch.equal(p.byte_offset, want.byte_offset) and torch.equal(p.buf[:total], want.buf[:total])
+        d = dec.decode_blocks(p, N).check()
+        assert torch.equal(d.sizes, sizes)
+        mask = torch.arange(N, device="cuda:0")[None, :] < sizes[:, None]
+        assert torch.equal(d.symbols[:, :N][mask], data[mask])
+    kind = "tans" if name == "tans" else "rans"
+    kw = dict(NUM_BITS_OUT=8, RANGE_FACTOR=1 << 12) if name == "rans_nbo8" else (dict(RANGE_FACTOR=1) if name == "tans" else {})
+    oracle = getattr(so.Oracle, kind)(zipf_freq_list(), **kw)
+    offs = want.byte_offset.cpu().numpy()
+    host, hs = data.cpu().numpy(), sizes.cpu().numpy()
+    for b in list(range(8)) + [5000, 5031, B - 2, B - 1] + list(range(100, B, B // 23)):
+        ref_bytes, ref_bits = oracle.encode_block(host[b, : hs[b]])
+        assert int(e.bit_len[b]) == ref_bits
+        assert got.buf[offs[b] : offs[b + 1]].cpu().numpy().tobytes() == ref_bytes.tobytes(), "block %d (size %d) differs from the oracle" % (b, hs[b])
