@@ -1673,6 +1673,81 @@ __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(const uint8_
             if (s_total[i]) atomicAdd(&total[i], (unsigned long long)s_total[i]);
 }
 
+// Second form: ONE LANE PER BLOCK, like the coders.  Every lane owns 256 32-bit counters in shared memory in the
+// [counter][lane] interleave (its bank is its lane number: the increments are fire-and-forget shared-memory reductions
+// that never conflict and never wait for each other), reads its own row in whole 32-byte sectors and, at the end of a
+// block, writes its column out as the block's counts.  Grid totals are the column sums of what a lane has counted over ALL
+// its blocks when no per-block counts are asked for (no zeroing in between), otherwise a second small kernel sums the
+// per-block counts.  Rows must be 32-byte aligned.
+constexpr uint32_t kHist2Warps = 7;  // 7 x 32 KiB of counters
+__global__ void __launch_bounds__(kHist2Warps * 32, 1) histogram_lanes_kernel(const uint8_t *__restrict__ sym, uint64_t sym_stride, const uint32_t *__restrict__ sizes,
+                                                                              uint32_t block_len, uint64_t n_blocks, uint32_t *__restrict__ counts,
+                                                                              unsigned long long *__restrict__ total) {
+    extern __shared__ __align__(128) uint32_t s_cnt[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const saddr_t mine = saddr_of(s_cnt + warp * (256 * 32)) + lane * 4;  // counter v of this lane at mine + 128 v
+    auto zero = [&]() {
+#pragma unroll 8
+        for (uint32_t v = 0; v < 256; ++v) sts32(mine + v * 128, 0u);
+    };
+    auto bump = [&](uint32_t byte) {  // byte value already multiplied by 128
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(mine + byte) : "memory");
+    };
+    zero();
+    const uint64_t warps_total = (uint64_t)gridDim.x * kHist2Warps;
+    for (uint64_t task = (uint64_t)blockIdx.x * kHist2Warps + warp; task * 32 < n_blocks; task += warps_total) {
+        const uint64_t b = task * 32 + lane;
+        const bool active = b < n_blocks;
+        const uint32_t n = active ? (sizes ? sizes[b] : block_len) : 0u;
+        const uint8_t *row = sym + (active ? b : 0) * sym_stride;
+        uint32_t i = 0;
+        for (; i + 32 <= n; i += 32) {
+            const u32x8 q = ld_sector32(row + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t w = q.v[j];
+                bump((w & 0xFFu) << 7);
+                bump((w >> 1) & (0xFFu << 7));
+                bump((w >> 9) & (0xFFu << 7));
+                bump((w >> 17) & (0xFFu << 7));
+            }
+        }
+        for (; i < n; ++i) bump((uint32_t)row[i] << 7);
+        if (counts) {
+            if (active) {
+                uint32_t *dst = counts + b * 256;
+#pragma unroll 4
+                for (uint32_t v = 0; v < 256; v += 4) {
+                    uint4 o;
+                    o.x = lds32(mine + (v + 0) * 128);
+                    o.y = lds32(mine + (v + 1) * 128);
+                    o.z = lds32(mine + (v + 2) * 128);
+                    o.w = lds32(mine + (v + 3) * 128);
+                    *(uint4 *)(dst + v) = o;
+                }
+            }
+            zero();
+        }
+    }
+    if (total && !counts) {  // the lanes' running counts: column sums per warp, one atomic per value and warp
+        __syncwarp();
+        const uint32_t *col = s_cnt + warp * (256 * 32);
+        for (uint32_t v = lane; v < 256; v += 32) {
+            unsigned long long acc = 0;
+            for (uint32_t j = 0; j < 32; ++j) acc += col[v * 32 + ((j + lane) & 31)];  // skewed: one bank per lane
+            if (acc) atomicAdd(&total[v], acc);
+        }
+    }
+}
+// total[v] += sum over blocks of counts[b][v]
+__global__ void __launch_bounds__(256) histogram_total_kernel(const uint32_t *__restrict__ counts, uint64_t n_blocks, unsigned long long *__restrict__ total) {
+    const uint64_t per = (n_blocks + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per, hi = lo + per < n_blocks ? lo + per : n_blocks;
+    unsigned long long acc = 0;
+    for (uint64_t b = lo; b < hi; ++b) acc += counts[b * 256 + threadIdx.x];
+    if (acc) atomicAdd(&total[threadIdx.x], acc);
+}
+
 }  // namespace scl
 
 // ====================================================================================================
@@ -2510,6 +2585,18 @@ extern "C" int scl_histogram_blocks(const uint8_t *d_sym, uint64_t sym_stride, c
     int dev = 0, n_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    // lane-per-block form: whole 32-byte sectors of every row, and enough blocks to give every lane one
+    if ((sym_stride % 32) == 0 && (((uintptr_t)d_sym) & 31) == 0 && n_blocks >= (uint64_t)n_sm * kHist2Warps * 32 &&
+        (n_blocks / ((uint64_t)n_sm * kHist2Warps * 32) + 2) * (uint64_t)block_len < (1ull << 32)) {  // a lane's running 32-bit counts
+        const int smem2 = kHist2Warps * 256 * 32 * 4;
+        SCL_CUDA(cudaFuncSetAttribute(histogram_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        histogram_lanes_kernel<<<n_sm, kHist2Warps * 32, smem2, (cudaStream_t)stream>>>(d_sym, sym_stride, d_sizes, block_len, n_blocks, d_counts,
+                                                                                       (unsigned long long *)d_total);
+        int rc = check_launch("histogram_lanes_kernel");
+        if (rc || !(d_total && d_counts)) return rc;
+        histogram_total_kernel<<<4 * n_sm, 256, 0, (cudaStream_t)stream>>>(d_counts, n_blocks, (unsigned long long *)d_total);
+        return check_launch("histogram_total_kernel");
+    }
     uint64_t want = (n_blocks + kHistWarps - 1) / kHistWarps;
     const uint64_t per_sm = (227 * 1024) / (kHistWarps * kHistSub * 1024 + 2048);  // resident CTAs per SM by shared memory
     uint32_t grid = (uint32_t)(want < (uint64_t)n_sm * per_sm ? want : (uint64_t)n_sm * per_sm);  // grid-stride over blocks

@@ -785,6 +785,33 @@ def test_histogram_blocks_vs_numpy_and_end_to_end_model():
         assert len(got) == ref_bits and got.tobytes() == ref_bytes.tobytes()
 
 
+def test_histogram_lane_per_block_form_vs_torch():
+    """The histogram's lane-per-block form (batches of at least one block per lane of the grid, 32-byte aligned rows):
+    per-block counts and grid totals, uniform and ragged sizes, totals alone (running counts, no per-block output) --
+    against torch.bincount on every block."""
+    from stanford_compression_library_b200.stats import histogram_blocks
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    B, N = 148 * 7 * 32 * 2 + 777, 608  # N % 32 == 0 (aligned rows), the tail loop runs for ragged sizes
+    data = sample_blocks(zipf_probabilities(), B, N, seed=41, device="cuda:0")
+    data[:, ::5] = 0
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(3)
+    sizes = torch.randint(0, N + 1, (B,), generator=g, device="cuda:0", dtype=torch.int32)
+    sizes[:4] = torch.tensor([0, 1, 31, N], dtype=torch.int32, device="cuda:0")
+    for sz in (None, sizes):
+        n = torch.full((B,), N, device="cuda:0", dtype=torch.int64) if sz is None else sz.to(torch.int64)
+        mask = torch.arange(N, device="cuda:0")[None, :] < n[:, None]
+        keys = (torch.arange(B, device="cuda:0", dtype=torch.int64)[:, None] * 256 + data.to(torch.int64))[mask]
+        ref = torch.bincount(keys, minlength=B * 256).reshape(B, 256)
+        counts, tot = histogram_blocks(data, sizes=sz)
+        assert torch.equal(counts.to(torch.int64), ref) and torch.equal(tot, ref.sum(0))
+        _, tot_only = histogram_blocks(data, sizes=sz, per_block=False)
+        assert torch.equal(tot_only, ref.sum(0))
+        counts_only, none = histogram_blocks(data, sizes=sz, total=False)
+        assert none is None and torch.equal(counts_only.to(torch.int64), ref)
+
+
 def test_aec_kernel_generations_agree():
     """arithmetic coder: the closed-form / dp2a kernels (default for batches) vs the loop-literal
     first-generation kernels, plus the oracle on sampled blocks; ragged sizes; PRECISION 32 and 16."""
