@@ -795,7 +795,12 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             // warp_tot[par] / arrive[par] still belong to round - 2 until that round is resolved (its last warp may be
             // in the look-back, waiting for lower-numbered CTAs): nobody arrives at this round before.
             if (round >= 2) packed_wait_helping(ctl, io, po, W, total_warps, n_tasks, lane, &ctl.resolved, round - 1);
-            __threadfence();  // this task's slots: visible at gpu scope before anybody (generic or async proxy) is told to read them
+            // One fence for both directions: (acquire) what the resolver of round - 2 wrote before it published `resolved` --
+            // the reset of arrive[par] -- is ordered before this warp's arrival; (release) this task's slots are visible at gpu
+            // scope before anybody (generic or async proxy) is told to read them.
+            // (These hand-overs -- warp_tot / arrive, resolved -- are flag-and-fence message passing, not barriers: racecheck,
+            // which only knows barriers, reports them: profiles/r4d_racecheck.log.)
+            __threadfence();
             if (lane == 0) {
                 *(volatile unsigned long long *)&ctl.warp_tot[par][warp] = T;
                 __threadfence_block();
