@@ -716,8 +716,11 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
         const uint64_t b = (uint64_t)task * 32 + lane;
         const bool active = b < io.n_blocks;
         uint32_t n = n_uniform, n_tiles = n_tiles_uniform;  // RAGGED: n is this lane's, n_tiles the warp's
+        bool too_long = false;  // RAGGED: a size beyond the row's capacity (a caller error) codes nothing and is reported
         if (RAGGED) {
             n = active ? io.sizes[b] : 0u;
+            too_long = n > n_uniform;
+            n = too_long ? 0u : n;
             n_tiles = (__reduce_max_sync(0xffffffffu, n) + kTileCols - 1) / kTileCols;
         }
         if (lane == 0) {
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(PACKED ? 1024 : kMaxWarps * 32, 1)
             L.put64((uint64_t)n, c.DBSB);
             uint64_t bits = L.finish();
             if (L.bad) st = SCL_ST_BAD_SYMBOL;
-            if (L.ovf) st = SCL_ST_OVERFLOW;
+            if (L.ovf || (RAGGED && too_long)) st = SCL_ST_OVERFLOW;
             io.bit_len[b] = bits;
             if (!PACKED) io.bit_off[b] = (io.block0 + b + 1) * io.out_stride * 8 - bits;
             io.status[b] = st;

@@ -441,3 +441,24 @@ def test_ragged_batches_take_the_fast_encoder_and_match_the_oracle(name):
         ref_bytes, ref_bits = oracle.encode_block(host[b, : hs[b]])
         assert int(e.bit_len[b]) == ref_bits
         assert got.buf[offs[b] : offs[b + 1]].cpu().numpy().tobytes() == ref_bytes.tobytes(), "block %d (size %d) differs from the oracle" % (b, hs[b])
+
+
+def test_ragged_size_beyond_the_row_is_reported_not_read():
+    """A `sizes` entry larger than the row (a caller error) must not make the fast encoder read past the row: the block
+    codes nothing and carries the overflow status; its neighbours are untouched."""
+    from stanford_compression_library_b200.workloads import sample_blocks, zipf_probabilities
+
+    enc, dec = _codec("rans_default")
+    B, N = 4000, 256
+    data = sample_blocks(zipf_probabilities(), B, N, seed=9, device="cuda:0")
+    sizes = torch.full((B,), N, dtype=torch.int32, device="cuda:0")
+    good = enc.encode_blocks(data, sizes=sizes).check()
+    sizes[1234] = N + 1
+    e = enc.encode_blocks(data, sizes=sizes)
+    st = e.status.cpu().numpy()
+    assert st[1234] != 0 and (np.delete(st, 1234) == 0).all()
+    keep = torch.ones(B, dtype=torch.bool, device="cuda:0")
+    keep[1234] = False
+    assert torch.equal(e.bit_len[keep], good.bit_len[keep])
+    with pytest.raises(Exception):
+        e.check()
