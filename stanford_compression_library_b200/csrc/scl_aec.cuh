@@ -309,28 +309,45 @@ struct AecModel8 {
         }
         set_word(gw, word(gw) + (((idx >> 4) & 1) ? 0x10000u : 1u));
     }
-    // last index whose cumulative count is <= v (numpy.searchsorted(side="right") - 1); v < total
+    // last index whose cumulative count is <= v (numpy.searchsorted(side="right") - 1); v < total.
+    // Two levels, each searched hierarchically: the inclusive prefixes are non-decreasing, so "how many are <= v" and
+    // "the largest one <= v" locate the group (then the counter) -- first by whole words (one dot product per word
+    // gives the running prefix), then inside the one word that holds the answer.
     SCL_HD uint32_t find(uint32_t v, uint32_t &cum, uint32_t &f) const {
-        uint32_t pre = 0, g = 0, base = 0;
+        uint32_t g, base;
+        {
+            uint32_t P = 0, nw = 0, bw = 0;  // words (pairs of groups) wholly <= v, and their prefix
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) {
-            uint32_t wv = word(j);
-            uint32_t t1 = pre + (wv & 0xFFFFu), t2 = t1 + (wv >> 16);
-            bool c1 = t1 <= v, c2 = t2 <= v;
-            g += (c1 ? 1u : 0u) + (c2 ? 1u : 0u);
-            base = c2 ? t2 : (c1 ? t1 : base);
-            pre = t2;
+            for (uint32_t j = 0; j < 8; ++j) {
+                P = dp2a_lo(word(j), 0x0101u, P);  // + both 16-bit group totals of word j
+                const bool c = P <= v;
+                nw += c ? 1u : 0u;
+                bw = c ? P : bw;
+            }
+            const uint32_t wv = word(nw < 8 ? nw : 7);  // the word the answer lies in (v < total: nw <= 7)
+            const uint32_t t1 = bw + (wv & 0xFFFFu);
+            const bool c1 = nw < 8 && t1 <= v;
+            g = 2 * nw + (c1 ? 1u : 0u);
+            base = c1 ? t1 : bw;
+            g = g > 15 ? 15 : g;
         }
-        g = g > 15 ? 15 : g;
         uint32_t lo = 0, b2 = base;
-        pre = base;
         if (big == 0) {
+            const saddr_t a = w + (saddr_t)((8 + 4 * g) * stride);
+            const uint32_t w0 = lds32(a), w1 = lds32(a + (saddr_t)stride), w2 = lds32(a + (saddr_t)(2 * stride)), w3 = lds32(a + (saddr_t)(3 * stride));
+            const uint32_t s0 = dp4a_u(w0, 0x01010101u, base), s1 = dp4a_u(w1, 0x01010101u, s0), s2 = dp4a_u(w2, 0x01010101u, s1),
+                           s3 = dp4a_u(w3, 0x01010101u, s2);
+            const bool c0 = s0 <= v, c1 = s1 <= v, c2 = s2 <= v, c3 = s3 <= v;
+            const uint32_t kw = (c0 ? 1u : 0u) + (c1 ? 1u : 0u) + (c2 ? 1u : 0u) + (c3 ? 1u : 0u);  // words of four counters wholly <= v
+            uint32_t pre = c2 ? s2 : (c1 ? s1 : (c0 ? s0 : base));
+            pre = c3 ? s3 : pre;
+            const uint32_t wv = c2 ? w3 : (c1 ? w2 : (c0 ? w1 : w0));  // kw == 4 (cannot happen for v < total): w3 again, nothing counted
+            lo = 4 * kw;
+            b2 = pre;
+            if (kw < 4) {
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                const uint32_t wv = word(8 + 4 * g + j);
-#pragma unroll
-                for (uint32_t b = 0; b < 4; ++b) {
-                    const uint32_t t = pre + ((wv >> (8 * b)) & 0xFFu);
+                for (uint32_t bb = 0; bb < 4; ++bb) {
+                    const uint32_t t = pre + ((wv >> (8 * bb)) & 0xFFu);
                     const bool c = t <= v;
                     lo += c ? 1u : 0u;
                     b2 = c ? t : b2;
@@ -338,6 +355,7 @@ struct AecModel8 {
                 }
             }
         } else {
+            uint32_t pre = base;
             for (uint32_t j = 0; j < 16; ++j) {
                 const uint32_t t = pre + count(g * 16 + j);
                 const bool c = t <= v;
