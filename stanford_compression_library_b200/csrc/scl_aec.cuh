@@ -631,6 +631,19 @@ SCL_HD void aec_shift_e3(uint32_t &low, uint32_t &hm, uint32_t m, uint32_t half,
 }
 // floor(a / t) for integer-valued doubles a < 2^53, t >= 1, rcp = 1 / t: the product estimate is
 // within 1 of the quotient and the fused remainder a - q t is exact, so one correction suffices.
+// 1 / x for the quotient ESTIMATE of aec_floor_div (x in [1, 2^32]): the hardware's reciprocal seed (>= 20 bits) and one
+// Newton step give > 40 bits, the estimate of a quotient below 2^32 is then off by far less than one, and
+// aec_floor_div's exact remainder test settles the rest -- a full IEEE division (seed, two steps, range checks and a
+// slow-path call) is not needed.  On the host: the plain division (the corrected quotient is the same).
+SCL_HD double aec_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+#else
+    return 1.0 / x;
+#endif
+}
 SCL_HD double aec_floor_div(double a, double t, double rcp) {
     double q = floor(a * rcp);
     double r = fma(-q, t, a);
@@ -649,7 +662,7 @@ SCL_HD void aec_shrink(uint32_t &low, uint32_t &hm, uint32_t cc, uint32_t f, uin
         hm = (uint32_t)(lo64 + rng * (uint64_t)(cc + f) / total - 1);
         low = (uint32_t)(lo64 + rng * (uint64_t)cc / total);
     } else {
-        const double low_d = (double)low, t_d = (double)total, rcp_t = 1.0 / t_d;
+        const double low_d = (double)low, t_d = (double)total, rcp_t = aec_rcp(t_d);
         const double rng_d = (double)hm - low_d + 1.0;
         hm = (uint32_t)(low_d + aec_floor_div(rng_d * (double)(cc + f), t_d, rcp_t) - 1.0);
         low = (uint32_t)(low_d + aec_floor_div(rng_d * (double)cc, t_d, rcp_t));
@@ -662,7 +675,7 @@ SCL_HD uint32_t aec_target(uint32_t state, uint32_t low, uint32_t hm, uint32_t t
         return (uint32_t)((((uint64_t)state - low + 1) * total - 1) / rng);
     }
     const double low_d = (double)low, rng_d = (double)hm - low_d + 1.0;
-    return (uint32_t)aec_floor_div(((double)state - low_d + 1.0) * (double)total - 1.0, rng_d, 1.0 / rng_d);
+    return (uint32_t)aec_floor_div(((double)state - low_d + 1.0) * (double)total - 1.0, rng_d, aec_rcp(rng_d));
 }
 
 // ArithmeticEncoder.encode_block (arithmetic_coding.py:80-161)
