@@ -52,7 +52,7 @@ def main():
             td = timeit(lambda: dec.decode_blocks(p, N, reuse=d))
             assert torch.equal(d.symbols[:, :N], data)
             print(json.dumps({"blocks": B, "mode": mode, "encode_slots_ms_per_GiB": te / gib, "decode_ms_per_GiB": td / gib}), flush=True)
-        for mode in (0, NO_RING, PIECE_512, PIECE_1024, 5 << 12, 6 << 12, 8 << 12):
+        for mode in (0, 2 << 12, 3 << 12, 5 << 12):
             enc.device_coder().debug_path(mode)
             tp = timeit(lambda: enc.encode_blocks_packed(data, capacity=B * N, reuse=p))
             p.check()
